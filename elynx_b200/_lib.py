@@ -1,0 +1,100 @@
+"""ctypes binding of libelynx_b200.so -- the C ABI declared in include/elynx_b200.h.
+
+The library is the product; there is no Python/CPU fallback.  If the shared object is missing this
+module raises ImportError (build it with `python -m elynx_b200.build`)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libelynx_b200.so")
+
+ELX_OK = 0
+ELX_E_INVALID = -1
+ELX_E_CUDA = -2
+ELX_E_UNSUPPORTED = -3
+ELX_E_NOMEM = -4
+ELX_E_BAD_WEIGHTS = -5
+ELX_FLAG_FORCE_GENERIC = 1
+
+
+class ElxError(RuntimeError):
+    """Raised where the reference calls `error` (MarkovProcess.hs:35-37, RateMatrix.hs:125, ...)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s (elx status %d)" % (msg, code))
+        self.code = code
+        self.msg = msg
+
+
+class elx_model(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("n_components", C.c_int32), ("is_mixture", C.c_int32),
+                ("weights", C.POINTER(C.c_double)), ("pi", C.POINTER(C.c_double)), ("exch", C.POINTER(C.c_double))]
+
+
+class elx_tree(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("parent", C.POINTER(C.c_int32)), ("brlen", C.POINTER(C.c_double)),
+                ("leaf_row", C.POINTER(C.c_int32))]
+
+
+class elx_opts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("philox_rounds", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+_VP, _I64, _U64, _I32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32
+_CSTRS = C.POINTER(C.c_char_p)
+
+# name -> (restype, argtypes); every symbol include/elynx_b200.h declares
+SIGNATURES = {
+    "elx_version": (C.c_int, []),
+    "elx_last_error": (C.c_char_p, [_VP]),
+    "elx_create": (C.c_int, [C.POINTER(elx_model), C.POINTER(elx_tree), C.POINTER(elx_opts), C.POINTER(_VP)]),
+    "elx_destroy": (None, [_VP]),
+    "elx_n_leaves": (_I32, [_VP]),
+    "elx_n_nodes": (_I32, [_VP]),
+    "elx_n_states": (_I32, [_VP]),
+    "elx_n_components": (_I32, [_VP]),
+    "elx_stream": (_VP, [_VP]),
+    "elx_ptables_get": (C.c_int, [_VP, _VP, C.c_int]),
+    "elx_ptables_set": (C.c_int, [_VP, _VP]),
+    "elx_alias_columns": (_I32, [_VP]),
+    "elx_alias_get": (C.c_int, [_VP, _VP, _VP]),
+    "elx_simulate": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
+    "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
+    "elx_simulate_injected": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
+    "elx_simulate_injected_device": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
+    "elx_fasta_size": (_I64, [_VP, _CSTRS, _I64]),
+    "elx_fasta_pack_device": (C.c_int, [_VP, _VP, _I64, _I64, _I64, _I64, _CSTRS, C.c_char_p, _VP]),
+    "elx_simulate_fasta": (C.c_int, [_VP, _U64, _I64, _CSTRS, C.c_char_p, _VP, _I64, _VP]),
+    "elx_histogram_device": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _VP]),
+    "elx_launch_count": (_I64, [_VP]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libelynx_b200.so is missing (no CPU fallback exists): run `python -m elynx_b200.build`")
+        _lib = C.CDLL(LIB_PATH)
+        from . import _model_sigs
+
+        for table in (SIGNATURES, _model_sigs.SIGNATURES):
+            for name, (res, args) in table.items():
+                fn = getattr(_lib, name)
+                fn.restype = res
+                fn.argtypes = args
+    return _lib
+
+
+def last_error(handle=None) -> str:
+    s = lib().elx_last_error(handle)
+    return s.decode(errors="replace") if s else ""
+
+
+def check(rc: int, handle=None):
+    if rc != 0:
+        raise ElxError(rc, last_error(handle))

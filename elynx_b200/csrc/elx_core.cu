@@ -1,0 +1,816 @@
+// elynx_b200 core: handle, kernels K1 (P(t) tables), K2 (tree simulation: injected + generic free-running),
+// K3 (FASTA packer), validation histograms, and the C ABI of include/elynx_b200.h.
+//
+// Reference behaviour restated here (paths relative to /root/reference):
+//   probMatrix                 elynx-markov/src/ELynx/Simulate/MarkovProcess.hs:33-41
+//   jump = categorical (p ! i) elynx-markov/src/ELynx/Simulate/MarkovProcess.hs:48-49
+//   walk / draw order          elynx-markov/src/ELynx/Simulate/MarkovProcessAlongTree.hs:57-63,88-98,163-173,195-208
+//   FASTA layout               elynx-seq/src/ELynx/Sequence/Export/Fasta.hs:24-36
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/elynx_b200.h"
+#include "elx_device.cuh"
+#include "elx_internal.hpp"
+#include "elx_state.hpp"
+
+namespace elx {
+
+static thread_local std::string g_last_error;
+
+int fail(elx_handle *h, int code, const std::string &msg) {
+  if (h) h->last_error = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// K1: batched P(t) = I + A diag(expm1(lambda t)) B for every (node, component), one thread per row.
+// Writes the probabilities and the per-row cumulative sums (sequential left-to-right fp64 adds, the
+// order of mwc-random's scanl1 (+)).  t == 0 gives the identity exactly (MarkovProcess.hs:36).
+// Algorithmic bytes: N*C*K*K*16 written once.  Tiny and batched -> no tensor cores.
+// ---------------------------------------------------------------------------------------------
+__global__ void k1_ptables(int N, int C, int K, const double *__restrict__ brlen, const double *__restrict__ lambda,
+                           const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ P,
+                           double *__restrict__ cum) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t rows = (int64_t)N * C * K;
+  if (r >= rows) return;
+  int i = (int)(r % K);
+  int c = (int)((r / K) % C);
+  int n = (int)(r / ((int64_t)K * C));
+  double t = brlen[n];
+  double *prow = P + r * K;
+  double *crow = cum + r * K;
+  double ak[64];
+  if (t != 0.0) {
+    const double *Ai = A + ((int64_t)c * K + i) * K;
+    const double *lam = lambda + (int64_t)c * K;
+    for (int k = 0; k < K; ++k) ak[k] = Ai[k] * expm1(lam[k] * t);
+  }
+  double acc = 0.0;
+  for (int j = 0; j < K; ++j) {
+    double p;
+    if (t == 0.0) {
+      p = (i == j) ? 1.0 : 0.0;
+    } else {
+      const double *Bc = B + (int64_t)c * K * K + j;
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) s = fma(ak[k], Bc[(int64_t)k * K], s);
+      p = (i == j ? 1.0 : 0.0) + s;
+      if (!(p > 0.0)) p = 0.0;  // rounding noise on vanishing entries (also maps NaN to 0)
+    }
+    prow[j] = p;
+    acc = (j == 0) ? p : __dadd_rn(acc, p);
+    crow[j] = acc;
+  }
+}
+
+// Rebuild the cumulative tables from caller-supplied probabilities (elx_ptables_set).
+__global__ void k1_cum_from_p(int64_t rows, int K, const double *__restrict__ P, double *__restrict__ cum) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double acc = 0.0;
+  for (int j = 0; j < K; ++j) {
+    double p = P[r * K + j];
+    acc = (j == 0) ? p : __dadd_rn(acc, p);
+    cum[r * K + j] = acc;
+  }
+}
+
+// Alias tables for the free-running sampler, built in exact integer arithmetic (one thread per row).
+// Row masses m_i = round(p_i / sum p * 2^47) (residual added to the largest), column capacity 2^(47-A).
+__global__ void k1_alias(int64_t rows, int K, int A, const double *__restrict__ P, uint16_t *__restrict__ e16,
+                         uint32_t *__restrict__ qlo) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int KP = 1 << A;
+  const int QB = 47 - A;
+  const int64_t CAP = (int64_t)1 << QB;
+  int64_t m[64];
+  int alias[64];
+  int64_t q[64];
+  int small[64], large[64];
+  double sum = 0.0;
+  for (int j = 0; j < K; ++j) {
+    double p = P[r * K + j];
+    if (!(p > 0.0)) p = 0.0;
+    sum += p;
+  }
+  int64_t tot = 0;
+  int big = 0;
+  for (int j = 0; j < KP; ++j) {
+    double p = 0.0;
+    if (j < K) { p = P[r * K + j]; if (!(p > 0.0)) p = 0.0; }
+    int64_t v = sum > 0.0 ? (int64_t)llrint(p / sum * 0x1p47) : (j == 0 ? ((int64_t)1 << 47) : 0);
+    m[j] = v;
+    tot += v;
+    if (v > m[big]) big = j;
+  }
+  m[big] += ((int64_t)1 << 47) - tot;
+  int ns = 0, nl = 0;
+  for (int j = KP - 1; j >= 0; --j) {
+    alias[j] = j;
+    q[j] = CAP;
+    if (m[j] < CAP) small[ns++] = j; else large[nl++] = j;
+  }
+  while (ns > 0 && nl > 0) {
+    int s = small[--ns];
+    int l = large[--nl];
+    q[s] = m[s];
+    alias[s] = l;
+    m[l] -= CAP - m[s];
+    if (m[l] < CAP) small[ns++] = l; else large[nl++] = l;
+  }
+  // whatever is left holds exactly CAP: always accept (alias = self)
+  for (int j = 0; j < KP; ++j) {
+    int64_t qq = q[j];
+    int al = alias[j];
+    if (qq >= CAP) { qq = CAP - 1; al = j; }
+    e16[r * KP + j] = (uint16_t)(((qq >> 32) << (A + 1)) | ((int64_t)al << 1));
+    qlo[r * KP + j] = (uint32_t)(qq & 0xffffffffu);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (injected-uniforms mode): one thread per site, reference semantics bit for bit.
+// categorical: cv = row-cumulative table; p = cv[K-1] * u (one rounded fp64 multiply); first i with cv[i] >= p.
+// Test mode only (reads 8 bytes per draw) -- never benchmarked.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_SLOTS = 32;
+
+
+__device__ __forceinline__ int categorical_cum(const double *__restrict__ cv, int K, double u) {
+  double p = __dmul_rn(cv[K - 1], u);
+  for (int i = 0; i < K; ++i)
+    if (cv[i] >= p) return i;
+  return -1;
+}
+
+__global__ void k2_injected(SimArgs a) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.nsites) return;
+  uint8_t slot[MAX_SLOTS];
+  int64_t row = 0;
+  int comp = 0;
+  if (a.is_mixture) {
+    comp = categorical_cum(a.cumw, a.C, a.U[s]);
+    if (comp < 0) { atomicExch(a.error_flag, a.N + 1); comp = 0; }
+    row = 1;
+  }
+  if (a.comps) a.comps[s] = comp;
+  int root = categorical_cum(a.cumpi + (int64_t)comp * a.K, a.K, a.U[row * a.u_pitch + s]);
+  if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
+  row += 1;
+  slot[0] = (uint8_t)root;
+  const int64_t KK = (int64_t)a.K * a.K;
+  for (int k = 0; k < a.N; ++k) {
+    WalkRec rec = a.walk[k];
+    int par = slot[rec.src];
+    const double *cv = a.cum + ((int64_t)rec.node * a.C + comp) * KK + (int64_t)par * a.K;
+    int child = categorical_cum(cv, a.K, a.U[(row + rec.node) * a.u_pitch + s]);
+    if (child < 0) { atomicExch(a.error_flag, 1 + rec.node); child = 0; }
+    if (rec.dst >= 0) slot[rec.dst] = (uint8_t)child;
+    if (rec.leaf_row >= 0) a.leaves[(int64_t)rec.leaf_row * a.leaves_pitch + s] = (uint8_t)child;
+    if (a.internal) a.internal[(int64_t)rec.node * a.internal_pitch + s] = (uint8_t)child;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (free-running, generic): any K <= 64, any C; tables read through L1/L2.  One thread per group of
+// 8 consecutive sites (= one Philox4x32 call per node).  The tiled kernels in elx_fast.cu implement
+// the same draw specification for the shapes that fit shared memory; this one is the fallback for big
+// mixtures and the cross-check.
+// ---------------------------------------------------------------------------------------------
+template <int ROUNDS>
+__device__ __forceinline__ int draw_child(const SimArgs &a, int node, int comp, int par, uint32_t x16, uint64_t site,
+                                          uint2 key) {
+  const int KP = 1 << a.A;
+  int j = (x16 >> 1) & (KP - 1);
+  uint32_t r = x16 >> (a.A + 1);
+  int64_t idx = (((int64_t)node * a.C + comp) * a.K + par) * KP + j;
+  uint32_t e = __ldg(a.e16 + idx);
+  uint32_t qh = e >> (a.A + 1);
+  int al = (e >> 1) & (KP - 1);
+  if (r < qh) return j;
+  if (r > qh) return al;
+  uint4 c = philox4x32<ROUNDS>(make_uint4((uint32_t)site, (uint32_t)(site >> 32), (uint32_t)node, TAG_REFINE), key);
+  return c.x < __ldg(a.qlo + idx) ? j : al;
+}
+
+template <int ROUNDS>
+__global__ void k2_freerun_generic(SimArgs a) {
+  // groups are aligned on global site index multiples of 8
+  int64_t g0 = a.site0 >> 3;
+  int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t sbase = g << 3;
+  if (sbase >= a.site0 + a.nsites) return;
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  uint64_t slot[MAX_SLOTS];
+  int comp[8];
+  uint64_t st = 0;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    uint64_t s = (uint64_t)sbase + d;
+    int c = 0;
+    if (a.is_mixture) {
+      uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_COMP), key);
+      c = categorical_cum(a.cumw, a.C, u53_positive(x.x, x.y));
+      if (c < 0) { atomicExch(a.error_flag, a.N + 1); c = 0; }
+    }
+    comp[d] = c;
+    uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_ROOT), key);
+    int root = categorical_cum(a.cumpi + (int64_t)c * a.K, a.K, u53_positive(x.x, x.y));
+    if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
+    st |= (uint64_t)root << (8 * d);
+    int64_t col = (int64_t)s - a.site0;
+    if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = c;
+  }
+  slot[0] = st;
+  const bool full = (sbase >= a.site0) && (sbase + 8 <= a.site0 + a.nsites);
+  const bool vec_ok = full && (((sbase - a.site0) & 7) == 0);
+  for (int k = 0; k < a.N; ++k) {
+    WalkRec rec = a.walk[k];
+    uint64_t par = slot[rec.src];
+    uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)g, (uint32_t)((uint64_t)g >> 32), (uint32_t)rec.node, TAG_NODE), key);
+    uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    uint64_t out = 0;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      uint32_t x16 = (w[d >> 1] >> ((d & 1) * 16)) & 0xffffu;
+      int child = draw_child<ROUNDS>(a, rec.node, comp[d], (int)((par >> (8 * d)) & 0xff), x16, (uint64_t)sbase + d, key);
+      out |= (uint64_t)child << (8 * d);
+    }
+    if (rec.dst >= 0) slot[rec.dst] = out;
+    if (rec.leaf_row >= 0) {
+      uint8_t *dst = a.leaves + (int64_t)rec.leaf_row * a.leaves_pitch + (sbase - a.site0);
+      if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+        *reinterpret_cast<uint64_t *>(dst) = out;
+      } else {
+        for (int d = 0; d < 8; ++d) {
+          int64_t col = sbase + d - a.site0;
+          if (col >= 0 && col < a.nsites) dst[d] = (uint8_t)(out >> (8 * d));
+        }
+      }
+    }
+    if (a.internal) {
+      uint8_t *dst = a.internal + (int64_t)rec.node * a.internal_pitch + (sbase - a.site0);
+      for (int d = 0; d < 8; ++d) {
+        int64_t col = sbase + d - a.site0;
+        if (col >= 0 && col < a.nsites) dst[d] = (uint8_t)(out >> (8 * d));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: FASTA packer.  states -> alphabet characters, written into the whole-file image.
+// Algorithmic bytes: 2 per cell (1 read + 1 written).
+// ---------------------------------------------------------------------------------------------
+__global__ void k3_fasta_body(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t site0, int64_t nsites,
+                              const int64_t *__restrict__ seq_off, const uint8_t *__restrict__ lut, int K,
+                              uint8_t *__restrict__ out) {
+  __shared__ uint8_t slut[64];
+  if (threadIdx.x < 64) slut[threadIdx.x] = threadIdx.x < K ? lut[threadIdx.x] : (uint8_t)'?';
+  __syncthreads();
+  int t = blockIdx.y;
+  const uint8_t *src = leaves + (int64_t)t * pitch;
+  uint8_t *dst = out + seq_off[t] + site0;
+  // each thread owns 16 destination-aligned bytes where possible
+  int64_t mis = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;  // bytes until dst is 16-aligned
+  int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // chunk 0 = head, chunks >= 1 aligned
+  int64_t lo = chunk == 0 ? 0 : mis + (chunk - 1) * 16;
+  int64_t hi = chunk == 0 ? mis : lo + 16;
+  if (hi > nsites) hi = nsites;
+  if (lo >= hi) return;
+  if (hi - lo == 16) {
+    uint32_t wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v |= (uint32_t)slut[src[lo + q * 4 + b] & 63] << (8 * b);
+      wv[q] = v;
+    }
+    *reinterpret_cast<uint4 *>(dst + lo) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+  } else {
+    for (int64_t i = lo; i < hi; ++i) dst[i] = slut[src[i] & 63];
+  }
+}
+
+__global__ void k3_fasta_frame(int T, const int64_t *__restrict__ seq_off, const int64_t *__restrict__ name_off,
+                               const uint8_t *__restrict__ names, int64_t total_sites, int write_head, int write_tail,
+                               uint8_t *__restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  if (write_head) {
+    int64_t len = name_off[t + 1] - name_off[t];
+    uint8_t *p = out + seq_off[t] - len - 2;
+    p[0] = '>';
+    for (int64_t i = 0; i < len; ++i) p[1 + i] = names[name_off[t] + i];
+    p[1 + len] = '\n';
+  }
+  if (write_tail) out[seq_off[t] + total_sites] = '\n';
+}
+
+// ---------------------------------------------------------------------------------------------
+// Validation histograms (accumulated into caller buffers; summed across GPUs with one NCCL all-reduce).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_state_counts(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, int K,
+                               unsigned long long *__restrict__ counts) {
+  __shared__ unsigned int h[64];
+  if (threadIdx.x < 64) h[threadIdx.x] = 0;
+  __syncthreads();
+  int t = blockIdx.y;
+  const uint8_t *src = leaves + (int64_t)t * pitch;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsites; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&h[src[i] & 63], 1u);
+  __syncthreads();
+  if (threadIdx.x < K && h[threadIdx.x]) atomicAdd(&counts[(int64_t)t * K + threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+__global__ void k_pattern_counts(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, int T, int K,
+                                 unsigned long long *__restrict__ counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsites; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t idx = 0;
+    for (int t = 0; t < T; ++t) idx = idx * K + leaves[(int64_t)t * pitch + i];
+    atomicAdd(&counts[idx], 1ull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int build_tables_from_p(elx_handle *h, bool have_p) {
+  const int64_t rows = (int64_t)h->N * h->C * h->K;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((rows + threads - 1) / threads);
+  if (!have_p) {
+    k1_ptables<<<blocks, threads, 0, h->stream>>>(h->N, h->C, h->K, h->d_brlen, h->d_lambda, h->d_A, h->d_B, h->d_P, h->d_cum);
+  } else {
+    k1_cum_from_p<<<blocks, threads, 0, h->stream>>>(rows, h->K, h->d_P, h->d_cum);
+  }
+  h->launches++;
+  k1_alias<<<blocks, threads, 0, h->stream>>>(rows, h->K, h->A, h->d_P, h->d_e16, h->d_qlo);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  int rc = fast_tables_build(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n) {
+  return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1);
+}
+
+static int check_sim_args(elx_handle *h, int64_t site0, int64_t nsites, const void *leaves, int64_t lp, const void *internal,
+                          int64_t ip) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "null handle");
+  if (nsites < 0 || site0 < 0) return fail(h, ELX_E_INVALID, "simulate: negative site range");
+  if (!leaves && nsites > 0) return fail(h, ELX_E_INVALID, "simulate: leaves buffer is NULL");
+  if (lp < nsites) return fail(h, ELX_E_INVALID, "simulate: leaves_pitch < nsites");
+  if (internal && ip < nsites) return fail(h, ELX_E_INVALID, "simulate: internal_pitch < nsites");
+  return 0;
+}
+
+static int check_error_flag(elx_handle *h) {
+  int flag = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&flag, h->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (flag != 0) {
+    int zero = 0;
+    cudaMemcpyAsync(h->d_error_flag, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    char buf[128];
+    snprintf(buf, sizeof buf, "categorical: bad weights! (draw site %d)", flag);
+    return fail(h, ELX_E_BAD_WEIGHTS, buf);
+  }
+  return 0;
+}
+
+static SimArgs base_args(elx_handle *h) {
+  SimArgs a;
+  memset(&a, 0, sizeof a);
+  a.N = h->N; a.K = h->K; a.C = h->C; a.is_mixture = h->is_mixture; a.n_slots = h->n_slots; a.A = h->A;
+  a.rounds = h->rounds;
+  a.walk = h->d_walk; a.cum = h->d_cum; a.cumw = h->d_cumw; a.cumpi = h->d_cumpi; a.e16 = h->d_e16; a.qlo = h->d_qlo;
+  a.error_flag = h->d_error_flag;
+  return a;
+}
+
+}  // namespace elx
+
+using namespace elx;
+
+extern "C" {
+
+int elx_version(void) { return 100; }
+
+const char *elx_last_error(const elx_handle *h) { return h ? h->last_error.c_str() : g_last_error.c_str(); }
+
+int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opts, elx_handle **out) {
+  if (!out) return fail(nullptr, ELX_E_INVALID, "elx_create: out is NULL");
+  *out = nullptr;
+  if (!model || !tree) return fail(nullptr, ELX_E_INVALID, "elx_create: model/tree is NULL");
+  const int K = model->n_states, C = model->n_components, N = tree->n_nodes;
+  if (K < 2 || K > 64) return fail(nullptr, ELX_E_INVALID, "model: n_states must be in 2..64");
+  if (C < 1) return fail(nullptr, ELX_E_INVALID, "fromSubstitutionModels: No weights given.");
+  if (!model->is_mixture && C != 1) return fail(nullptr, ELX_E_INVALID, "model: the single-model API takes exactly one component");
+  if (!model->pi || !model->exch || (model->is_mixture && !model->weights))
+    return fail(nullptr, ELX_E_INVALID, "model: NULL array");
+  if (N < 1 || !tree->parent || !tree->brlen || !tree->leaf_row) return fail(nullptr, ELX_E_INVALID, "tree: empty or NULL arrays");
+  for (int n = 0; n < N; ++n) {
+    if (tree->brlen[n] < 0) return fail(nullptr, ELX_E_INVALID, "probMatrix: Time is negative.");
+    if (!std::isfinite(tree->brlen[n])) return fail(nullptr, ELX_E_INVALID, "tree: branch length is not finite");
+  }
+  std::vector<double> w(C, 1.0);
+  if (model->is_mixture) {
+    double tot = 0;
+    for (int c = 0; c < C; ++c) {
+      w[c] = model->weights[c];
+      if (!(w[c] >= 0) || !std::isfinite(w[c])) return fail(nullptr, ELX_E_INVALID, "model: weights must be finite and >= 0");
+      tot += w[c];
+    }
+    if (!(tot > 0)) return fail(nullptr, ELX_E_BAD_WEIGHTS, "categorical: bad weights!");
+  }
+  for (int64_t i = 0; i < (int64_t)C * K; ++i)
+    if (!(model->pi[i] >= 0) || !std::isfinite(model->pi[i])) return fail(nullptr, ELX_E_INVALID, "model: pi must be finite and >= 0");
+
+  std::string msg;
+  WalkProgram walk;
+  int T = 0;
+  if (!compile_walk(N, tree->parent, tree->leaf_row, walk, T, msg)) return fail(nullptr, ELX_E_INVALID, msg);
+  if (walk.n_slots > MAX_SLOTS) return fail(nullptr, ELX_E_UNSUPPORTED, "tree: needs more than 32 live state slots");
+
+  std::vector<double> lambda((size_t)C * K), A((size_t)C * K * K), B((size_t)C * K * K);
+  for (int c = 0; c < C; ++c)
+    if (!eigen_reversible(K, model->pi + (size_t)c * K, model->exch + (size_t)c * K * K, &lambda[(size_t)c * K],
+                          &A[(size_t)c * K * K], &B[(size_t)c * K * K], msg))
+      return fail(nullptr, ELX_E_UNSUPPORTED, msg);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, ELX_E_CUDA, "no CUDA device available (elynx_b200 has no CPU fallback)");
+  int dev = opts && opts->device >= 0 ? opts->device : -1;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, ELX_E_CUDA, "cudaGetDevice failed"); }
+  if (dev >= ndev) return fail(nullptr, ELX_E_INVALID, "opts: device ordinal out of range");
+
+  elx_handle *h = new elx_handle();
+  h->N = N; h->K = K; h->C = C; h->T = T; h->is_mixture = model->is_mixture ? 1 : 0;
+  h->A = alias_bits(K); h->KP = 1 << h->A; h->device = dev; h->n_slots = walk.n_slots;
+  h->rounds = (opts && opts->philox_rounds == 7) ? 7 : 10;
+  h->flags = opts ? opts->flags : 0;
+  if (opts && opts->philox_rounds != 0 && opts->philox_rounds != 7 && opts->philox_rounds != 10) {
+    delete h;
+    return fail(nullptr, ELX_E_INVALID, "opts: philox_rounds must be 0, 7 or 10");
+  }
+  h->walk_host = walk.recs;
+  h->leaf_row_host.assign(tree->leaf_row, tree->leaf_row + N);
+  h->parent_host.assign(tree->parent, tree->parent + N);
+  h->brlen_host.assign(tree->brlen, tree->brlen + N);
+  auto bail = [&](int code, const std::string &m) { std::string mm = m; elx_destroy(h); return fail(nullptr, code, mm); };
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return bail(ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+  CT(cudaSetDevice(dev));
+  CT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t rows = (size_t)N * C * K;
+  CT(dalloc(&h->d_brlen, (size_t)N));
+  CT(dalloc(&h->d_lambda, (size_t)C * K));
+  CT(dalloc(&h->d_A, (size_t)C * K * K));
+  CT(dalloc(&h->d_B, (size_t)C * K * K));
+  CT(dalloc(&h->d_P, rows * K));
+  CT(dalloc(&h->d_cum, rows * K));
+  CT(dalloc(&h->d_e16, rows * h->KP));
+  CT(dalloc(&h->d_qlo, rows * h->KP));
+  CT(dalloc(&h->d_cumw, (size_t)C));
+  CT(dalloc(&h->d_cumpi, (size_t)C * K));
+  CT(dalloc(&h->d_walk, (size_t)N));
+  CT(dalloc(&h->d_error_flag, 1));
+  CT(cudaMemset(h->d_error_flag, 0, sizeof(int)));
+  // cumulative weights / stationary distributions: scanl1 (+) exactly as categorical does
+  std::vector<double> cumw(C), cumpi((size_t)C * K);
+  double acc = 0;
+  for (int c = 0; c < C; ++c) { acc = c ? acc + w[c] : w[0]; cumw[c] = acc; }
+  for (int c = 0; c < C; ++c) {
+    acc = 0;
+    for (int i = 0; i < K; ++i) { acc = i ? acc + model->pi[(size_t)c * K + i] : model->pi[(size_t)c * K]; cumpi[(size_t)c * K + i] = acc; }
+    if (!(acc > 0)) return bail(ELX_E_BAD_WEIGHTS, "categorical: bad weights!");
+  }
+  CT(cudaMemcpy(h->d_brlen, tree->brlen, sizeof(double) * N, cudaMemcpyHostToDevice));
+  CT(cudaMemcpy(h->d_lambda, lambda.data(), sizeof(double) * lambda.size(), cudaMemcpyHostToDevice));
+  CT(cudaMemcpy(h->d_A, A.data(), sizeof(double) * A.size(), cudaMemcpyHostToDevice));
+  CT(cudaMemcpy(h->d_B, B.data(), sizeof(double) * B.size(), cudaMemcpyHostToDevice));
+  CT(cudaMemcpy(h->d_cumw, cumw.data(), sizeof(double) * C, cudaMemcpyHostToDevice));
+  CT(cudaMemcpy(h->d_cumpi, cumpi.data(), sizeof(double) * cumpi.size(), cudaMemcpyHostToDevice));
+  CT(cudaMemcpy(h->d_walk, walk.recs.data(), sizeof(WalkRec) * N, cudaMemcpyHostToDevice));
+#undef CT
+  int rc = build_tables_from_p(h, false);
+  if (rc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, rc, m); }
+  *out = h;
+  return 0;
+}
+
+void elx_destroy(elx_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  fast_tables_free(h);
+  cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
+  cudaFree(h->d_e16); cudaFree(h->d_qlo); cudaFree(h->d_cumw); cudaFree(h->d_cumpi); cudaFree(h->d_walk);
+  cudaFree(h->d_error_flag); cudaFree(h->d_scratch); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
+  cudaFree(h->d_lut);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t elx_n_leaves(const elx_handle *h) { return h ? h->T : 0; }
+int32_t elx_n_nodes(const elx_handle *h) { return h ? h->N : 0; }
+int32_t elx_n_states(const elx_handle *h) { return h ? h->K : 0; }
+int32_t elx_n_components(const elx_handle *h) { return h ? h->C : 0; }
+int32_t elx_alias_columns(const elx_handle *h) { return h ? h->KP : 0; }
+void *elx_stream(const elx_handle *h) { return h ? (void *)h->stream : nullptr; }
+int64_t elx_launch_count(const elx_handle *h) { return h ? h->launches : 0; }
+
+int elx_ptables_get(elx_handle *h, double *out, int cumulative) {
+  if (!h || !out) return fail(h, ELX_E_INVALID, "elx_ptables_get: NULL argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  size_t n = (size_t)h->N * h->C * h->K * h->K;
+  CUDA_TRY(h, cudaMemcpyAsync(out, cumulative ? h->d_cum : h->d_P, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int elx_ptables_set(elx_handle *h, const double *p) {
+  if (!h || !p) return fail(h, ELX_E_INVALID, "elx_ptables_set: NULL argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  size_t n = (size_t)h->N * h->C * h->K * h->K;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_P, p, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return build_tables_from_p(h, true);
+}
+
+int elx_alias_get(elx_handle *h, uint16_t *e16, uint32_t *qlo) {
+  if (!h || !e16 || !qlo) return fail(h, ELX_E_INVALID, "elx_alias_get: NULL argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  size_t n = (size_t)h->N * h->C * h->K * h->KP;
+  CUDA_TRY(h, cudaMemcpyAsync(e16, h->d_e16, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(qlo, h->d_qlo, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves, int64_t leaves_pitch,
+                        int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch) {
+  int rc = check_sim_args(h, site0, nsites, d_leaves, leaves_pitch, d_internal, internal_pitch);
+  if (rc) return rc;
+  if (nsites == 0) return 0;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  SimArgs a = base_args(h);
+  a.leaves = d_leaves; a.leaves_pitch = leaves_pitch; a.comps = d_comps; a.internal = d_internal;
+  a.internal_pitch = internal_pitch; a.site0 = site0; a.nsites = nsites; a.seed = seed;
+  if (!(h->flags & ELX_FLAG_FORCE_GENERIC)) {
+    int used = 0;
+    rc = fast_simulate(h, a, &used);
+    if (rc) return rc;
+    if (used) return 0;
+  }
+  int64_t g0 = site0 >> 3, g1 = (site0 + nsites + 7) >> 3;
+  int64_t groups = g1 - g0;
+  const int threads = 128;
+  unsigned blocks = (unsigned)((groups + threads - 1) / threads);
+  if (h->rounds == 7) k2_freerun_generic<7><<<blocks, threads, 0, h->stream>>>(a);
+  else k2_freerun_generic<10><<<blocks, threads, 0, h->stream>>>(a);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int elx_simulate_injected_device(elx_handle *h, const double *d_U, int64_t u_pitch, int64_t nsites, uint8_t *d_leaves,
+                                 int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch) {
+  int rc = check_sim_args(h, 0, nsites, d_leaves, leaves_pitch, d_internal, internal_pitch);
+  if (rc) return rc;
+  if (!d_U && nsites > 0) return fail(h, ELX_E_INVALID, "simulate_injected: U is NULL");
+  if (u_pitch < nsites) return fail(h, ELX_E_INVALID, "simulate_injected: u_pitch < nsites");
+  if (nsites == 0) return 0;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  SimArgs a = base_args(h);
+  a.leaves = d_leaves; a.leaves_pitch = leaves_pitch; a.comps = d_comps; a.internal = d_internal;
+  a.internal_pitch = internal_pitch; a.site0 = 0; a.nsites = nsites; a.U = d_U; a.u_pitch = u_pitch;
+  const int threads = 128;
+  unsigned blocks = (unsigned)((nsites + threads - 1) / threads);
+  k2_injected<<<blocks, threads, 0, h->stream>>>(a);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+// host-buffer variants: device staging + copies, then synchronise
+static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int64_t site0, const double *U, int64_t u_pitch,
+                                int64_t nsites, uint8_t *leaves, int64_t lp, int32_t *comps, uint8_t *internal, int64_t ip) {
+  int rc = check_sim_args(h, site0, nsites, leaves, lp, internal, ip);
+  if (rc) return rc;
+  if (nsites == 0) return 0;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  // bounded batches keep the staging buffers small; column pitch of the staging buffers = batch size
+  const int64_t BATCH = 1 << 20;
+  uint8_t *d_leaves = nullptr, *d_internal = nullptr;
+  int32_t *d_comps = nullptr;
+  double *d_U = nullptr;
+  int64_t bmax = nsites < BATCH ? nsites : BATCH;
+  int64_t bpitch = (bmax + 15) & ~(int64_t)15;
+  int urows = h->N + (h->is_mixture ? 2 : 1);
+  auto cleanup = [&]() { cudaFree(d_leaves); cudaFree(d_internal); cudaFree(d_comps); cudaFree(d_U); };
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  CT(cudaMalloc((void **)&d_leaves, (size_t)h->T * bpitch));
+  if (internal) CT(cudaMalloc((void **)&d_internal, (size_t)h->N * bpitch));
+  if (comps) CT(cudaMalloc((void **)&d_comps, sizeof(int32_t) * (size_t)bpitch));
+  if (injected) CT(cudaMalloc((void **)&d_U, sizeof(double) * (size_t)urows * bpitch));
+  for (int64_t b0 = 0; b0 < nsites; b0 += BATCH) {
+    int64_t nb = nsites - b0 < BATCH ? nsites - b0 : BATCH;
+    if (injected) {
+      CT(cudaMemcpy2DAsync(d_U, sizeof(double) * bpitch, U + b0, sizeof(double) * u_pitch, sizeof(double) * nb, urows,
+                           cudaMemcpyHostToDevice, h->stream));
+      rc = elx_simulate_injected_device(h, d_U, bpitch, nb, d_leaves, bpitch, d_comps, d_internal, bpitch);
+    } else {
+      rc = elx_simulate_device(h, seed, site0 + b0, nb, d_leaves, bpitch, d_comps, d_internal, bpitch);
+    }
+    if (rc) { cleanup(); return rc; }
+    CT(cudaMemcpy2DAsync(leaves + b0, lp, d_leaves, bpitch, nb, h->T, cudaMemcpyDeviceToHost, h->stream));
+    if (internal) CT(cudaMemcpy2DAsync(internal + b0, ip, d_internal, bpitch, nb, h->N, cudaMemcpyDeviceToHost, h->stream));
+    if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream));
+    CT(cudaStreamSynchronize(h->stream));
+  }
+#undef CT
+  cleanup();
+  return check_error_flag(h);
+}
+
+int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch,
+                 int32_t *comps, uint8_t *internal, int64_t internal_pitch) {
+  return simulate_host_common(h, false, seed, site0, nullptr, 0, nsites, leaves, leaves_pitch, comps, internal, internal_pitch);
+}
+
+int elx_simulate_injected(elx_handle *h, const double *U, int64_t u_pitch, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch,
+                          int32_t *comps, uint8_t *internal, int64_t internal_pitch) {
+  if (!U && nsites > 0) return fail(h, ELX_E_INVALID, "simulate_injected: U is NULL");
+  if (u_pitch < nsites) return fail(h, ELX_E_INVALID, "simulate_injected: u_pitch < nsites");
+  return simulate_host_common(h, true, 0, 0, U, u_pitch, nsites, leaves, leaves_pitch, comps, internal, internal_pitch);
+}
+
+// ---- FASTA ------------------------------------------------------------------------------------
+static void leaf_names_in_row_order(const elx_handle *h, const char *const *names, std::vector<std::string> &out) {
+  out.assign(h->T, std::string());
+  for (int t = 0; t < h->T; ++t) out[t] = names && names[t] ? names[t] : "";
+}
+
+int64_t elx_fasta_size(const elx_handle *h, const char *const *names, int64_t total_sites) {
+  if (!h || total_sites < 0) return -1;
+  int64_t tot = 0;
+  for (int t = 0; t < h->T; ++t) tot += 1 + (int64_t)(names && names[t] ? strlen(names[t]) : 0) + 1 + total_sites + 1;
+  return tot;
+}
+
+static int fasta_upload_frame(elx_handle *h, const char *const *names, const char *alphabet, int64_t total_sites) {
+  std::vector<std::string> nm;
+  leaf_names_in_row_order(h, names, nm);
+  std::vector<int64_t> name_off(h->T + 1, 0), seq_off(h->T, 0);
+  std::string all;
+  int64_t pos = 0;
+  for (int t = 0; t < h->T; ++t) {
+    name_off[t] = (int64_t)all.size();
+    all += nm[t];
+    seq_off[t] = pos + 1 + (int64_t)nm[t].size() + 1;
+    pos = seq_off[t] + total_sites + 1;
+  }
+  name_off[h->T] = (int64_t)all.size();
+  if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
+  cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off); cudaFree(h->d_lut);
+  h->d_names = nullptr; h->d_name_off = nullptr; h->d_seq_off = nullptr; h->d_lut = nullptr;
+  CUDA_TRY(h, cudaMalloc((void **)&h->d_names, all.size() + 1));
+  CUDA_TRY(h, cudaMalloc((void **)&h->d_name_off, sizeof(int64_t) * (h->T + 1)));
+  CUDA_TRY(h, cudaMalloc((void **)&h->d_seq_off, sizeof(int64_t) * h->T));
+  CUDA_TRY(h, cudaMalloc((void **)&h->d_lut, 64));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_names, all.data(), all.size(), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_name_off, name_off.data(), sizeof(int64_t) * (h->T + 1), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_seq_off, seq_off.data(), sizeof(int64_t) * h->T, cudaMemcpyHostToDevice, h->stream));
+  uint8_t lut[64];
+  memset(lut, '?', sizeof lut);
+  memcpy(lut, alphabet, (size_t)h->K);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_lut, lut, 64, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+  h->fasta_total_sites = total_sites;
+  h->fasta_names_key = all + "\x01" + alphabet;
+  for (int t = 0; t < h->T; ++t) h->fasta_names_key += "\x02" + std::to_string(name_off[t]);
+  return 0;
+}
+
+int elx_fasta_pack_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t site0, int64_t nsites,
+                          int64_t total_sites, const char *const *names, const char *alphabet, uint8_t *d_out) {
+  if (!h || !d_out || !alphabet) return fail(h, ELX_E_INVALID, "fasta: NULL argument");
+  if (site0 < 0 || nsites < 0 || site0 + nsites > total_sites) return fail(h, ELX_E_INVALID, "fasta: site range outside the alignment");
+  if (nsites > 0 && (!d_leaves || leaves_pitch < nsites)) return fail(h, ELX_E_INVALID, "fasta: bad leaves buffer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  // (re)upload the frame description when the names / alphabet / length changed
+  std::string key;
+  {
+    std::vector<std::string> nm;
+    leaf_names_in_row_order(h, names, nm);
+    std::string all;
+    std::vector<size_t> offs;
+    for (auto &s : nm) { offs.push_back(all.size()); all += s; }
+    key = all + "\x01" + alphabet;
+    for (size_t o : offs) key += "\x02" + std::to_string(o);
+  }
+  if (!h->d_seq_off || h->fasta_total_sites != total_sites || key != h->fasta_names_key) {
+    int rc = fasta_upload_frame(h, names, alphabet, total_sites);
+    if (rc) return rc;
+  }
+  if (nsites > 0) {
+    const int threads = 256;
+    int64_t chunks = (nsites + 15) / 16 + 1;
+    dim3 grid((unsigned)((chunks + threads - 1) / threads), (unsigned)h->T);
+    k3_fasta_body<<<grid, threads, 0, h->stream>>>(d_leaves, leaves_pitch, site0, nsites, h->d_seq_off, h->d_lut, h->K, d_out);
+    h->launches++;
+  }
+  int head = site0 == 0, tail = site0 + nsites == total_sites;
+  if (head || tail) {
+    k3_fasta_frame<<<(h->T + 127) / 128, 128, 0, h->stream>>>(h->T, h->d_seq_off, h->d_name_off, h->d_names, total_sites, head,
+                                                                tail, d_out);
+    h->launches++;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const char *const *names, const char *alphabet,
+                       uint8_t *out, int64_t out_capacity, int32_t *comps) {
+  if (!h || !out || !alphabet) return fail(h, ELX_E_INVALID, "simulate_fasta: NULL argument");
+  int64_t need = elx_fasta_size(h, names, total_sites);
+  if (need < 0 || out_capacity < need) return fail(h, ELX_E_INVALID, "simulate_fasta: output buffer too small");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  uint8_t *d_out = nullptr, *d_leaves = nullptr;
+  int32_t *d_comps = nullptr;
+  const int64_t BATCH = 1 << 22;
+  int64_t bmax = total_sites < BATCH ? total_sites : BATCH;
+  int64_t bpitch = ((bmax > 0 ? bmax : 1) + 15) & ~(int64_t)15;
+  auto cleanup = [&]() { cudaFree(d_out); cudaFree(d_leaves); cudaFree(d_comps); };
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  CT(cudaMalloc((void **)&d_out, (size_t)need > 0 ? (size_t)need : 1));
+  CT(cudaMalloc((void **)&d_leaves, (size_t)h->T * bpitch));
+  if (comps) CT(cudaMalloc((void **)&d_comps, sizeof(int32_t) * (size_t)bpitch));
+  int rc = 0;
+  if (total_sites == 0) rc = elx_fasta_pack_device(h, nullptr, 0, 0, 0, 0, names, alphabet, d_out);
+  for (int64_t b0 = 0; b0 < total_sites && rc == 0; b0 += BATCH) {
+    int64_t nb = total_sites - b0 < BATCH ? total_sites - b0 : BATCH;
+    rc = elx_simulate_device(h, seed, b0, nb, d_leaves, bpitch, d_comps, nullptr, 0);
+    if (rc == 0) rc = elx_fasta_pack_device(h, d_leaves, bpitch, b0, nb, total_sites, names, alphabet, d_out);
+    if (rc == 0 && comps) CT(cudaMemcpyAsync(comps + b0, d_comps, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (rc) { cleanup(); return rc; }
+  CT(cudaMemcpyAsync(out, d_out, (size_t)need, cudaMemcpyDeviceToHost, h->stream));
+  CT(cudaStreamSynchronize(h->stream));
+#undef CT
+  cleanup();
+  return check_error_flag(h);
+}
+
+int elx_histogram_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t nsites, int64_t *d_state_counts,
+                         int64_t *d_pattern_counts) {
+  if (!h || !d_leaves) return fail(h, ELX_E_INVALID, "histogram: NULL argument");
+  if (nsites < 0 || leaves_pitch < nsites) return fail(h, ELX_E_INVALID, "histogram: bad site count / pitch");
+  if (nsites == 0) return 0;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (d_state_counts) {
+    int64_t bx = (nsites + 256 * 64 - 1) / (256 * 64);
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)h->T);
+    k_state_counts<<<grid, 256, 0, h->stream>>>(d_leaves, leaves_pitch, nsites, h->K, (unsigned long long *)d_state_counts);
+    h->launches++;
+  }
+  if (d_pattern_counts) {
+    double bins = pow((double)h->K, (double)h->T);
+    if (bins > (double)(1 << 24)) return fail(h, ELX_E_INVALID, "histogram: K^T exceeds 2^24 pattern bins");
+    int64_t bx = (nsites + 255) / 256;
+    if (bx > 148 * 16) bx = 148 * 16;
+    k_pattern_counts<<<(unsigned)bx, 256, 0, h->stream>>>(d_leaves, leaves_pitch, nsites, h->T, h->K,
+                                                           (unsigned long long *)d_pattern_counts);
+    h->launches++;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Device-side building blocks shared by the kernels: Philox4x32, the free-running draw spec,
+// and the table layout.  See DESIGN.md "free-running draw" for the specification these implement.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace elx {
+
+// Philox counter tags (ctr.w)
+constexpr uint32_t TAG_NODE = 0;    // ctr = (site>>3 lo, site>>3 hi, node, TAG_NODE): 8 x 16-bit draws, field = site & 7
+constexpr uint32_t TAG_REFINE = 1;  // ctr = (site lo, site hi, node, TAG_REFINE): word 0 = 32 refinement bits
+constexpr uint32_t TAG_COMP = 2;    // ctr = (site lo, site hi, 0, TAG_COMP): words 0,1 -> 53-bit uniform
+constexpr uint32_t TAG_ROOT = 3;    // ctr = (site lo, site hi, 0, TAG_ROOT)
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+template <int ROUNDS>
+__host__ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+    uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+#else
+    uint64_t p0 = (uint64_t)PHILOX_M0 * c.x, p1 = (uint64_t)PHILOX_M1 * c.z;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += PHILOX_W0;
+    k.y += PHILOX_W1;
+  }
+  return c;
+}
+
+__host__ __device__ __forceinline__ uint4 philox_rounds(uint4 c, uint2 k, int rounds) {
+  return rounds == 7 ? philox4x32<7>(c, k) : philox4x32<10>(c, k);
+}
+
+// 53-bit uniform in (0,1] from two Philox words (used for the component and root-state draws).
+__host__ __device__ __forceinline__ double u53_positive(uint32_t lo, uint32_t hi) {
+  uint64_t w = ((uint64_t)hi << 32) | lo;
+  return (double)((w >> 11) + 1) * 0x1p-53;
+}
+
+// Alias-table geometry.  KP = number of columns (power of two >= K), A = log2 KP.
+// 16-bit draw x = [r : 15-A bits][j : A bits][spare : 1 bit]; table entry e = [q_hi : 15-A][alias : A][0].
+// Full acceptance threshold q = q_hi * 2^32 + q_lo in [0, 2^(47-A)); accept column j iff r*2^32 + x_lo < q.
+__host__ __device__ __forceinline__ int alias_bits(int K) {
+  int a = 1;
+  while ((1 << a) < K) ++a;
+  return a < 2 ? 2 : a;
+}
+
+}  // namespace elx

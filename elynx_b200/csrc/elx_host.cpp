@@ -1,0 +1,174 @@
+// Host-side helpers: tree walk compilation and the per-component eigensystems.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "elx_internal.hpp"
+
+namespace elx {
+
+bool compile_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, WalkProgram &out, int &n_leaves,
+                  std::string &msg) {
+  const int N = n_nodes;
+  if (N < 1) { msg = "tree: no nodes"; return false; }
+  if (parent[0] != -1) { msg = "tree: parent[0] must be -1 (root first, preorder)"; return false; }
+  std::vector<int> n_child(N, 0), first_child(N, -1), next_sib(N, -1), last_child(N, -1);
+  {
+    // preorder check: parent[n] must lie on the path root..n-1
+    std::vector<int> path;
+    path.push_back(0);
+    for (int n = 1; n < N; ++n) {
+      int p = parent[n];
+      if (p < 0 || p >= n) { msg = "tree: parent[n] must be in [0, n) (preorder)"; return false; }
+      while (!path.empty() && path.back() != p) path.pop_back();
+      if (path.empty()) { msg = "tree: nodes are not in preorder"; return false; }
+      path.push_back(n);
+      if (first_child[p] < 0) first_child[p] = n; else next_sib[last_child[p]] = n;
+      last_child[p] = n;
+      n_child[p]++;
+    }
+  }
+  int T = 0;
+  for (int n = 0; n < N; ++n) if (n_child[n] == 0) ++T;
+  std::vector<char> seen(T, 0);
+  for (int n = 0; n < N; ++n) {
+    if (n_child[n] == 0) {
+      int r = leaf_row[n];
+      if (r < 0 || r >= T || seen[r]) { msg = "tree: leaf_row of the leaves must be a permutation of 0..T-1"; return false; }
+      seen[r] = 1;
+    } else if (leaf_row[n] != -1) {
+      msg = "tree: leaf_row must be -1 for internal nodes";
+      return false;
+    }
+  }
+  n_leaves = T;
+  std::vector<int64_t> size(N, 1);
+  for (int n = N - 1; n >= 1; --n) size[parent[n]] += size[n];
+
+  out.recs.clear();
+  out.recs.reserve(N);
+  std::vector<int> free_slots;
+  int high = 1;  // slot 0 = root states
+  auto alloc = [&]() {
+    if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
+    return high++;
+  };
+  struct Frame { int node, src, dst; std::vector<int> kids; size_t next; };
+  std::vector<Frame> st;
+  auto enter = [&](int v, int src, bool is_last) {
+    Frame f;
+    f.node = v; f.src = src; f.next = 0;
+    if (n_child[v] == 0) {
+      f.dst = -1;
+    } else {
+      f.dst = is_last ? src : alloc();
+      for (int c = first_child[v]; c >= 0; c = next_sib[c]) f.kids.push_back(c);
+      // heaviest child last (stable otherwise)
+      size_t h = 0;
+      for (size_t i = 1; i < f.kids.size(); ++i) if (size[f.kids[i]] > size[f.kids[h]]) h = i;
+      int heavy = f.kids[h];
+      f.kids.erase(f.kids.begin() + (long)h);
+      f.kids.push_back(heavy);
+    }
+    WalkRec r;
+    r.node = v; r.src = (int16_t)src; r.dst = (int16_t)f.dst; r.leaf_row = leaf_row[v]; r.pad = 0;
+    out.recs.push_back(r);
+    st.push_back(std::move(f));
+  };
+  enter(0, 0, true);
+  while (!st.empty()) {
+    Frame &f = st.back();
+    if (f.next < f.kids.size()) {
+      int c = f.kids[f.next];
+      bool last = (f.next + 1 == f.kids.size());
+      f.next++;
+      int src = f.dst;
+      enter(c, src, last);
+    } else {
+      // a slot allocated here (dst != src) is released unless the last child took it over: the last child
+      // writes into f.dst itself, so the slot is simply dead once this subtree is done.
+      if (f.dst >= 0 && f.dst != f.src) free_slots.push_back(f.dst);
+      st.pop_back();
+    }
+  }
+  out.n_slots = high;
+  if (high > 32000) { msg = "tree: too many live slots"; return false; }
+  return true;
+}
+
+bool eigen_reversible(int K, const double *pi, const double *exch, double *lambda, double *A, double *B,
+                      std::string &msg) {
+  std::vector<double> S((size_t)K * K), V((size_t)K * K, 0.0), sq(K);
+  double emax = 0;
+  for (int i = 0; i < K * K; ++i) emax = std::max(emax, std::fabs(exch[i]));
+  for (int i = 0; i < K; ++i) {
+    if (!(pi[i] > 0) || !std::isfinite(pi[i])) {
+      msg = "model: stationary frequencies must be > 0 for the eigen path (non-reversible models unsupported)";
+      return false;
+    }
+    sq[i] = std::sqrt(pi[i]);
+  }
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j) {
+      if (i == j) continue;
+      double a = exch[i * K + j], b = exch[j * K + i];
+      if (!std::isfinite(a) || a < 0) { msg = "model: exchangeabilities must be finite and >= 0"; return false; }
+      if (std::fabs(a - b) > 1e-10 * (emax > 0 ? emax : 1)) {
+        msg = "model: exchangeability matrix must be symmetric (non-reversible models unsupported)";
+        return false;
+      }
+    }
+  // Q = setDiagonal(E diag(pi)) (RateMatrix.hs:87-103); S = D^{1/2} Q D^{-1/2}
+  for (int i = 0; i < K; ++i) {
+    double rs = 0;
+    for (int j = 0; j < K; ++j)
+      if (j != i) rs += std::fabs(exch[i * K + j] * pi[j]);
+    for (int j = 0; j < K; ++j)
+      S[(size_t)i * K + j] = (i == j) ? -rs : sq[i] * 0.5 * (exch[i * K + j] + exch[j * K + i]) * sq[j];
+    V[(size_t)i * K + i] = 1.0;
+  }
+  // cyclic Jacobi
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) (i == j ? diag : off) += S[(size_t)i * K + j] * S[(size_t)i * K + j];
+    if (off <= 1e-34 * (diag > 0 ? diag : 1) || off == 0) break;
+    for (int p = 0; p < K - 1; ++p)
+      for (int q = p + 1; q < K; ++q) {
+        double apq = S[(size_t)p * K + q];
+        if (apq == 0) continue;
+        double app = S[(size_t)p * K + p], aqq = S[(size_t)q * K + q];
+        double theta = (aqq - app) / (2 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < K; ++k) {
+          double akp = S[(size_t)k * K + p], akq = S[(size_t)k * K + q];
+          S[(size_t)k * K + p] = c * akp - s * akq;
+          S[(size_t)k * K + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < K; ++k) {
+          double apk = S[(size_t)p * K + k], aqk = S[(size_t)q * K + k];
+          S[(size_t)p * K + k] = c * apk - s * aqk;
+          S[(size_t)q * K + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < K; ++k) {
+          double vkp = V[(size_t)k * K + p], vkq = V[(size_t)k * K + q];
+          V[(size_t)k * K + p] = c * vkp - s * vkq;
+          V[(size_t)k * K + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (int k = 0; k < K; ++k) {
+    double l = S[(size_t)k * K + k];
+    // a rate matrix has eigenvalues <= 0; clamp rounding noise on the zero eigenvalue
+    lambda[k] = l > 0 ? 0.0 : l;
+  }
+  for (int i = 0; i < K; ++i)
+    for (int k = 0; k < K; ++k) {
+      A[(size_t)i * K + k] = V[(size_t)i * K + k] / sq[i];
+      B[(size_t)k * K + i] = V[(size_t)i * K + k] * sq[i];
+    }
+  return true;
+}
+
+}  // namespace elx

@@ -1,0 +1,35 @@
+// Internal declarations shared by the host-side helpers and the CUDA translation units.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace elx {
+
+// One step of the tree walk.  Nodes are visited parent-before-child in "heavy child last" order so
+// that the last child can overwrite its parent's slot; at most floor(log2 N)+1 slots are ever live.
+struct WalkRec {
+  int32_t node;      // preorder index: selects the table, the uniform row and the Philox counter
+  int16_t src;       // slot holding the parent's states (slot 0 = root states for the root node)
+  int16_t dst;       // slot receiving this node's states, -1 for leaves (written to the output only)
+  int32_t leaf_row;  // output row or -1
+  int32_t pad;
+};
+static_assert(sizeof(WalkRec) == 16, "WalkRec must stay 16 bytes");
+
+struct WalkProgram {
+  std::vector<WalkRec> recs;
+  int n_slots = 0;
+};
+
+// Reference draw order is preorder (MarkovProcessAlongTree.hs:88-98); draws are keyed by node id, so
+// the visiting order is free.  Returns false (with msg) when the arrays do not describe a preorder tree.
+bool compile_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, WalkProgram &out, int &n_leaves,
+                  std::string &msg);
+
+// Symmetric eigen-decomposition (cyclic Jacobi) of S = D^{1/2} Q D^{-1/2}, Q = setDiagonal(E diag(pi)).
+// Produces lambda[K], A = D^{-1/2} V and B = V^T D^{1/2} so that exp(Qt) = I + A diag(expm1(lambda t)) B.
+bool eigen_reversible(int K, const double *pi, const double *exch, double *lambda, double *A, double *B,
+                      std::string &msg);
+
+}  // namespace elx

@@ -1,0 +1,64 @@
+// The opaque handle behind include/elynx_b200.h and the argument block shared by the simulation kernels.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "elx_internal.hpp"
+
+struct elx_handle {
+  int N = 0, K = 0, C = 0, T = 0, is_mixture = 0, A = 0, KP = 0, device = 0, n_slots = 0, rounds = 10, flags = 0;
+  cudaStream_t stream = nullptr;
+  double *d_brlen = nullptr, *d_lambda = nullptr, *d_A = nullptr, *d_B = nullptr;
+  double *d_P = nullptr, *d_cum = nullptr, *d_cumw = nullptr, *d_cumpi = nullptr;
+  uint16_t *d_e16 = nullptr;
+  uint32_t *d_qlo = nullptr;
+  elx::WalkRec *d_walk = nullptr;
+  int *d_error_flag = nullptr;
+  uint8_t *d_scratch = nullptr;
+  // FASTA frame (names, offsets, alphabet LUT)
+  uint8_t *d_names = nullptr, *d_lut = nullptr;
+  int64_t *d_name_off = nullptr, *d_seq_off = nullptr;
+  int64_t fasta_total_sites = -1;
+  std::string fasta_names_key;
+  // tiled ("fast") kernel tables, owned by elx_fast.cu
+  void *fast = nullptr;
+  std::vector<elx::WalkRec> walk_host;
+  std::vector<int32_t> leaf_row_host, parent_host;
+  std::vector<double> brlen_host;
+  int64_t launches = 0;
+  std::string last_error;
+};
+
+namespace elx {
+
+struct SimArgs {
+  int N, K, C, is_mixture, n_slots, A, rounds;
+  const WalkRec *walk;
+  const double *cum;    // [N][C][K][K]
+  const double *cumw;   // [C]
+  const double *cumpi;  // [C][K]
+  const uint16_t *e16;  // [N][C][K][KP]
+  const uint32_t *qlo;  // [N][C][K][KP]
+  uint8_t *leaves;      // [T][leaves_pitch]
+  int64_t leaves_pitch;
+  int32_t *comps;       // [nsites] or null
+  uint8_t *internal;    // [N][internal_pitch] or null
+  int64_t internal_pitch;
+  int64_t site0, nsites;
+  uint64_t seed;
+  const double *U;      // injected mode only
+  int64_t u_pitch;
+  int *error_flag;
+};
+
+int fail(elx_handle *h, int code, const std::string &msg);
+
+// elx_fast.cu: tiled shared-memory kernels for the shapes that fit (DNA / protein with few components)
+int fast_tables_build(elx_handle *h);
+void fast_tables_free(elx_handle *h);
+int fast_simulate(elx_handle *h, const SimArgs &a, int *used);
+
+}  // namespace elx

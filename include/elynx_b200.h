@@ -1,0 +1,161 @@
+/*
+ * elynx_b200 -- C ABI of the B200-native alignment simulator.
+ *
+ * This is the drop-in boundary for ONE path of dschrempf/elynx: the per-site continuous-time
+ * Markov process run along a phylogeny,
+ *
+ *   elynx-markov/src/ELynx/Simulate/MarkovProcessAlongTree.hs
+ *     simulateAndFlattenPar              :101-125   (single substitution model)
+ *     simulateAndFlattenMixtureModelPar  :238-262   (mixture model, returns component indices)
+ *     simulate / simulateMixtureModel    :130-155, :267-294  (same walk, keeps internal states)
+ *   elynx-markov/src/ELynx/Simulate/MarkovProcess.hs
+ *     probMatrix :33-41, jump :48-49
+ *
+ * called from slynx/src/SLynx/Simulate/Simulate.hs:100-127 (simulateAlignment).  The reference has
+ * no FFI today; INTEGRATION.md shows the `foreign import ccall` stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every array is caller-owned; the library owns its handle + device memory.
+ *   - every function returns 0 on success and a negative elx_status otherwise;
+ *     elx_last_error(h) (or elx_last_error(NULL) for a failed elx_create) gives the message.
+ *     The reference's convention is `error` (abort): MarkovProcess.hs:35-37, RateMatrix.hs:125.
+ *   - states are indices into the sorted alphabet (0..K-1) stored as uint8
+ *     (reference: `type State = Int`, MarkovProcess.hs:29).
+ *   - the tree arrives flattened in PREORDER (root first, children left to right), exactly the order
+ *     in which simulateAndFlatten' (:88-98) consumes random numbers:
+ *       parent[n] < n, parent[0] = -1; brlen[n] = length of the branch above n (root stem, 0 if
+ *       absent: elynx-tree Phylogeny.hs:374-381); leaf_row[n] = index of the leaf in DFS left-to-right
+ *       order (= `leaves`, Rooted.hs:244-248) or -1 for internal nodes.
+ *   - model inputs are used AS GIVEN, like the reference simulator does: pi[c] and exch[c] are
+ *     whatever SubstitutionModel/MixtureModel construction produced; Q_c = setDiagonal(exch_c * diag(pi_c))
+ *     (RateMatrix.hs:87-103).  Weights need not be normalised (mwc-random `categorical` rescales).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with ELX_E_CUDA.
+ */
+#ifndef ELYNX_B200_H
+#define ELYNX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct elx_handle elx_handle;
+
+typedef enum {
+  ELX_OK = 0,
+  ELX_E_INVALID = -1,     /* bad argument (what the reference rejects with `error`) */
+  ELX_E_CUDA = -2,        /* CUDA runtime failure / no device */
+  ELX_E_UNSUPPORTED = -3, /* e.g. non-reversible model (needs symmetric exch and pi > 0) */
+  ELX_E_NOMEM = -4,
+  ELX_E_BAD_WEIGHTS = -5  /* mwc-random "categorical: bad weights!" */
+} elx_status;
+
+/* (weights, stationary distributions, exchangeability matrices) -- the argument triple of
+ * simulateAndFlattenMixtureModelPar (:238-246); n_components = 1 and is_mixture = 0 gives the
+ * simulateAndFlattenPar (:101-108) flavour, which draws no component. */
+typedef struct {
+  int32_t n_states;      /* K: 4 (DNA) or 20 (Protein); any 2..64 accepted */
+  int32_t n_components;  /* C >= 1 */
+  int32_t is_mixture;    /* 0: single-Q API (C must be 1); 1: mixture API (component draw per site) */
+  const double *weights; /* [C]      (ignored when is_mixture == 0) */
+  const double *pi;      /* [C][K]   stationary distributions */
+  const double *exch;    /* [C][K][K] exchangeability matrices, row-major (hmatrix Matrix R layout) */
+} elx_model;
+
+/* `Data.Tree.Tree Double` of branch lengths (slynx Simulate.hs:101), flattened in preorder. */
+typedef struct {
+  int32_t n_nodes;         /* N */
+  const int32_t *parent;   /* [N] */
+  const double *brlen;     /* [N], >= 0 (negative -> ELX_E_INVALID, cf. MarkovProcess.hs:37) */
+  const int32_t *leaf_row; /* [N] */
+} elx_tree;
+
+typedef struct {
+  int32_t device;        /* CUDA device ordinal; -1 = current device */
+  int32_t philox_rounds; /* 0 = default (10) */
+  int32_t flags;         /* ELX_FLAG_* */
+  int32_t reserved;
+} elx_opts;
+
+#define ELX_FLAG_FORCE_GENERIC 1 /* always use the generic global-table kernel (cross-check of the tiled one) */
+
+int elx_version(void);
+const char *elx_last_error(const elx_handle *h);
+
+/* Builds the per-component eigensystems on the host, uploads the tree, and runs kernel K1
+ * (batched fp64 P(t) = I + A diag(expm1(lambda t)) B for every branch x component, stored as per-row
+ * cumulative tables + alias tables).  Replaces toProbTree / toProbTreeMixtureModel
+ * (MarkovProcessAlongTree.hs:54-55, :157-161). */
+int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opts, elx_handle **out);
+void elx_destroy(elx_handle *h);
+
+int32_t elx_n_leaves(const elx_handle *h);
+int32_t elx_n_nodes(const elx_handle *h);
+int32_t elx_n_states(const elx_handle *h);
+int32_t elx_n_components(const elx_handle *h);
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
+void *elx_stream(const elx_handle *h);
+
+/* Parity hook for probMatrix (MarkovProcess.hs:33-41): copy the [N][C][K][K] tables to the host,
+ * cumulative != 0 -> per-row cumulative sums (scanl1 (+)), else the probabilities themselves. */
+int elx_ptables_get(elx_handle *h, double *out, int cumulative);
+/* Parity hook: replace K1's tables by caller-supplied probability matrices [N][C][K][K]
+ * (e.g. the oracle's Pade tables) and rebuild the cumulative + alias tables from them on the device. */
+int elx_ptables_set(elx_handle *h, const double *p);
+/* Parity hook for the free-running sampler: alias tables derived from the P rows.
+ * e16 [N][C][K][KP] (uint16: threshold high bits | alias | 0), qlo [N][C][K][KP] (uint32 threshold low bits),
+ * KP = elx_alias_columns(h).  See DESIGN.md "free-running draw". */
+int32_t elx_alias_columns(const elx_handle *h);
+int elx_alias_get(elx_handle *h, uint16_t *e16, uint32_t *qlo);
+
+/* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
+ * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed); the result is a
+ * pure function of (seed, global site index, node), so any partition of the site range over calls,
+ * GPUs or processes yields the same alignment.
+ *   leaves   [T][leaves_pitch]   uint8, row = leaf_row, column = site - site0       (required)
+ *   comps    [nsites]            int32 component index per site, or NULL             (:257, `cs`)
+ *   internal [N][internal_pitch] uint8 states of every node in preorder, or NULL     (`simulate`, :130-155)
+ * The *_device variants take device pointers and only enqueue work on elx_stream(h);
+ * the host variants copy results back and synchronise. */
+int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch,
+                 int32_t *comps, uint8_t *internal, int64_t internal_pitch);
+int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves,
+                        int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch);
+
+/* Injected-uniforms mode: consumes the uniform matrix U[(is_mixture ? 2 : 1) + N][u_pitch] (doubles in
+ * (0,1]) in the reference's draw order -- [component row (mixtures)] [root-state row] [one row per node in
+ * preorder] -- with mwc-random `categorical` semantics (first i with cum[i] >= cum[K-1]*u, fp64).
+ * Must reproduce the reference algorithm bit for bit given the same tables. */
+int elx_simulate_injected(elx_handle *h, const double *U, int64_t u_pitch, int64_t nsites, uint8_t *leaves,
+                          int64_t leaves_pitch, int32_t *comps, uint8_t *internal, int64_t internal_pitch);
+int elx_simulate_injected_device(elx_handle *h, const double *d_U, int64_t u_pitch, int64_t nsites, uint8_t *d_leaves,
+                                 int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch);
+
+/* ---- FASTA emission (elynx-seq Export/Fasta.hs:24-36; slynx Simulate.hs:117-127) ---------------
+ * Layout: for each leaf in leaf_row order `>` name `\n` S characters `\n`.
+ * elx_fasta_size: total bytes for an alignment of total_sites columns.
+ * elx_fasta_pack_device: K3 -- maps states -> characters of `alphabet` (K chars) and writes the columns
+ *   [site0, site0+nsites) of every sequence line (plus the header lines when site0 == 0 and the trailing
+ *   newlines when site0 + nsites == total_sites) into d_out, a buffer holding the WHOLE file image.
+ * elx_simulate_fasta: simulate + pack + copy to the host buffer `out` (size >= elx_fasta_size). */
+int64_t elx_fasta_size(const elx_handle *h, const char *const *names, int64_t total_sites);
+int elx_fasta_pack_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t site0, int64_t nsites,
+                          int64_t total_sites, const char *const *names, const char *alphabet, uint8_t *d_out);
+int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const char *const *names, const char *alphabet,
+                       uint8_t *out, int64_t out_capacity, int32_t *comps);
+
+/* ---- validation histograms (new; the reference has none) ---------------------------------------
+ * d_state_counts [T][K] int64 += per-taxon state counts; d_pattern_counts [K^T] int64 += site-pattern counts
+ * (pattern index = sum_t state_t * K^(T-1-t); only when K^T <= 2^24; pass NULL to skip).  Device buffers are
+ * accumulated into, so per-GPU results can be summed with one NCCL all-reduce. */
+int elx_histogram_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t nsites,
+                         int64_t *d_state_counts, int64_t *d_pattern_counts);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t elx_launch_count(const elx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELYNX_B200_H */

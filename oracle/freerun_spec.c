@@ -1,0 +1,92 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- executable specification of the PRODUCT's free-running draw
+ * (DESIGN.md "free-running draw"), used to check the CUDA kernels bit for bit, including the rare
+ * refinement path that no statistical test can see.  It restates elynx_b200's own spec, not the
+ * reference: the reference-side semantics (inverse-CDF categorical on an injected uniform matrix) live
+ * in oracle/sim.c.  The walk itself is the reference's (MarkovProcessAlongTree.hs:88-98,195-208):
+ * every node draws from the row of its parent's state, root first.
+ *
+ * Spec:  key = (seed lo, seed hi); Philox4x32-R, R in {7,10}
+ *   component (mixtures): x = philox(site lo, site hi, 0, 2); u = ((x1:x0 >> 11) + 1) 2^-53;
+ *                         c = first i with cumw[i] >= cumw[C-1]*u      (mwc-random categorical)
+ *   root state:           x = philox(site lo, site hi, 0, 3); same rule on cumpi[c]
+ *   node n, site s:       x = philox(s>>3 lo, s>>3 hi, n, 0); x16 = 16-bit field (s & 7), low half of word (s&7)>>1 first
+ *                         j = (x16 >> 1) & (KP-1); r = x16 >> (A+1); e = e16[n][c][parent][j]
+ *                         r < e>>(A+1) -> j ;  r > e>>(A+1) -> alias = (e>>1)&(KP-1) ;
+ *                         tie -> y = philox(s lo, s hi, n, 1).x0 ;  y < qlo[n][c][parent][j] ? j : alias
+ */
+#include <stdint.h>
+#include <stdlib.h>
+
+static void philox(int rounds, uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < rounds; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+void spec_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  philox(rounds, c, key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+static int cat_cum(const double *cv, int k, double u) {
+  volatile double p = cv[k - 1] * u;
+  for (int i = 0; i < k; ++i)
+    if (cv[i] >= p) return i;
+  return -1;
+}
+
+int spec_freerun(int N, int K, int C, int is_mixture, int A, int rounds, const int32_t *parent, const int32_t *leaf_row,
+                 const double *cumw, const double *cumpi, const uint16_t *e16, const uint32_t *qlo, uint64_t seed,
+                 int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch, int32_t *comps, uint8_t *internal,
+                 int64_t internal_pitch) {
+  const int KP = 1 << A;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint8_t *st = (uint8_t *)malloc((size_t)N);
+  for (int64_t col = 0; col < nsites; ++col) {
+    uint64_t s = (uint64_t)(site0 + col);
+    int c = 0;
+    if (is_mixture) {
+      uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 2};
+      philox(rounds, x, k0, k1);
+      uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+      c = cat_cum(cumw, C, (double)((w >> 11) + 1) * 0x1p-53);
+      if (c < 0) { free(st); return -(N + 1); }
+    }
+    if (comps) comps[col] = c;
+    uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 3};
+    philox(rounds, x, k0, k1);
+    uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+    int root = cat_cum(cumpi + (int64_t)c * K, K, (double)((w >> 11) + 1) * 0x1p-53);
+    if (root < 0) { free(st); return -(N + 2); }
+    for (int n = 0; n < N; ++n) {
+      int par = parent[n] < 0 ? root : st[parent[n]];
+      uint64_t g = s >> 3;
+      uint32_t y[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)n, 0};
+      philox(rounds, y, k0, k1);
+      int f = (int)(s & 7);
+      uint32_t x16 = (y[f >> 1] >> ((f & 1) * 16)) & 0xffffu;
+      int j = (x16 >> 1) & (KP - 1);
+      uint32_t r = x16 >> (A + 1);
+      int64_t idx = (((int64_t)n * C + c) * K + par) * KP + j;
+      uint32_t e = e16[idx], qh = e >> (A + 1);
+      int al = (e >> 1) & (KP - 1), child;
+      if (r < qh) child = j;
+      else if (r > qh) child = al;
+      else {
+        uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)n, 1};
+        philox(rounds, z, k0, k1);
+        child = z[0] < qlo[idx] ? j : al;
+      }
+      st[n] = (uint8_t)child;
+      if (leaf_row[n] >= 0) leaves[(int64_t)leaf_row[n] * leaves_pitch + col] = (uint8_t)child;
+      if (internal) internal[(int64_t)n * internal_pitch + col] = (uint8_t)child;
+    }
+  }
+  free(st);
+  return 0;
+}

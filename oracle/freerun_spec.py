@@ -1,0 +1,67 @@
+"""ctypes loader for oracle/freerun_spec.c -- executable spec of the product's free-running draw (test infrastructure)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfreerun_spec.so")
+_SRC = os.path.join(_HERE, "freerun_spec.c")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO, _SRC])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.spec_freerun.restype = C.c_int
+    return _lib
+
+
+def philox4x32(ctr, key, rounds=10):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().spec_philox4x32(rounds, c, k, o)
+    return [int(x) for x in o]
+
+
+def alias_bits(k):
+    a = 1
+    while (1 << a) < k:
+        a += 1
+    return max(a, 2)
+
+
+def freerun(is_mixture, parent, leaf_row, ws, ds, e16, qlo, seed, site0, nsites, rounds=10, keep_internal=False):
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+    e16 = np.ascontiguousarray(e16, dtype=np.uint16)
+    qlo = np.ascontiguousarray(qlo, dtype=np.uint32)
+    n, c, k, kp = e16.shape
+    cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
+    cumpi = np.ascontiguousarray(np.cumsum(np.asarray(ds, dtype=np.float64).reshape(c, k), axis=1))
+    t = int((leaf_row >= 0).sum())
+    leaves = np.zeros((t, max(nsites, 1)), dtype=np.uint8)
+    comps = np.zeros(max(nsites, 1), dtype=np.int32)
+    internal = np.zeros((n, max(nsites, 1)), dtype=np.uint8) if keep_internal else None
+    vp = C.c_void_p
+    rc = lib().spec_freerun(n, k, c, int(bool(is_mixture)), alias_bits(k), rounds, vp(parent.ctypes.data), vp(leaf_row.ctypes.data),
+                            vp(cumw.ctypes.data), vp(cumpi.ctypes.data), vp(e16.ctypes.data), vp(qlo.ctypes.data),
+                            C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0), C.c_int64(nsites), vp(leaves.ctypes.data),
+                            C.c_int64(max(nsites, 1)), vp(comps.ctypes.data), vp(internal.ctypes.data) if keep_internal else None,
+                            C.c_int64(max(nsites, 1)))
+    if rc:
+        raise RuntimeError("spec_freerun rc=%d" % rc)
+    return leaves[:, :nsites], comps[:nsites], (internal[:, :nsites] if keep_internal else None)

@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for states/indices; P(t) within 1e-12 (max-norm relative) of the hmatrix-expm restatement."""
+import numpy as np
+import pytest
+
+import oracle.freerun_spec as spec
+import oracle.model as om
+import oracle.pruning as pruning
+import oracle.sim as osim
+from helpers import model_case, random_tree, tree_from_file, uniforms
+
+pytestmark = pytest.mark.gpu
+
+import elynx_b200 as eb  # noqa: E402
+
+
+def make_sim(model, tree, **kw):
+    is_mix, ws, ds, es, _ = model
+    return eb.Simulator(ws if is_mix else None, ds, es, tree, is_mixture=is_mix, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: P(t) tables
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,tree_file", [("jc", "Newick.tree"), ("hky_g4", "Newick.tree"), ("lg_g4", "Newick.tree"),
+                                            ("wag_g4", "UltraMetric.tree"), ("c10_g4", "UltraMetric.tree"), ("edm_lg", "Newick.tree")])
+def test_ptables_match_hmatrix_expm(name, tree_file):
+    model = model_case(name)
+    tree = tree_from_file(tree_file)
+    ref = om.prob_tables(model[2], model[3], tree.brlen)
+    with make_sim(model, tree) as sim:
+        p = sim.ptables()
+        cum = sim.ptables(cumulative=True)
+    assert p.shape == ref.shape
+    # north_star tolerance: 1e-12 relative (max-norm per matrix); element-wise reported in DESIGN.md
+    rel_maxnorm = np.max(np.abs(p - ref), axis=(2, 3)) / np.max(np.abs(ref), axis=(2, 3))
+    assert rel_maxnorm.max() < 1e-12, rel_maxnorm.max()
+    elementwise = np.max(np.abs(p - ref) / np.maximum(ref, 1e-300))
+    assert elementwise < 1e-9, elementwise
+    assert np.array_equal(p[tree.brlen == 0], np.broadcast_to(np.eye(p.shape[-1]), p[tree.brlen == 0].shape))
+    # the cumulative tables are the sequential left-to-right sums of the rows (scanl1 (+)), bit for bit
+    assert np.array_equal(cum, np.cumsum(p, axis=-1))
+    assert np.all(p >= 0) and np.allclose(p.sum(-1), 1.0, atol=1e-13)
+
+
+def test_ptables_short_and_long_branches():
+    model = model_case("lg")
+    tree = om.parse_newick("((a:1e-6,b:1e-4):1e-2,(c:0.1,d:1.0):5.0,e:20.0,f:0.0);")
+    ref = om.prob_tables(model[2], model[3], tree.brlen)
+    with make_sim(model, tree) as sim:
+        p = sim.ptables()
+    rel_maxnorm = np.max(np.abs(p - ref), axis=(2, 3)) / np.max(np.abs(ref), axis=(2, 3))
+    assert rel_maxnorm.max() < 1e-12
+    # the expm1 form keeps element-wise error ~1e-12 even at t = 1e-6
+    assert np.max(np.abs(p - ref) / np.maximum(ref, 1e-300)) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 injected-uniforms mode: bit-exact against the reference algorithm
+# ---------------------------------------------------------------------------------------------
+CASES = [("jc", "Newick.tree", 10000), ("hky", "Newick.tree", 3001), ("hky_g4", "Newick.tree", 4099),
+         ("gtr4_g4", "UltraMetric.tree", 2500), ("lg_g4", "Newick.tree", 1500), ("c10_g4", "UltraMetric.tree", 1203),
+         ("edm_lg", "Newick.tree", 1000), ("mixture_dna", "Multifurcating.tree", None)]
+
+
+@pytest.mark.parametrize("name,tree_file,s", CASES)
+def test_injected_bit_exact(name, tree_file, s):
+    rng = np.random.default_rng(abs(hash((name, tree_file))) % (2 ** 32))
+    model = model_case(name)
+    is_mix, ws, ds, es, _ = model
+    if tree_file == "Multifurcating.tree":
+        # that fixture has no branch lengths: give it some (toLengthTree would reject it otherwise)
+        tree = random_tree(37, rng, multifurcate=True, zero_frac=0.2)
+        s = 2000
+    else:
+        tree = tree_from_file(tree_file)
+    u = uniforms(rng, tree.n_nodes + (2 if is_mix else 1), s)
+    with make_sim(model, tree) as sim:
+        p_gpu = sim.ptables()
+        leaves, comps, internal = sim.simulate_injected(u, want_comps=True, keep_internal=True)
+        # (1) same tables on both sides -> byte-identical alignments
+        c0, l0, i0 = osim.simulate_injected(is_mix, tree.parent, tree.leaf_row, ws, ds, p_gpu, u, keep_internal=True)
+        assert np.array_equal(leaves, l0)
+        assert np.array_equal(comps, c0)
+        assert np.array_equal(internal, i0)
+        # (2) the oracle's own (Pade) tables uploaded to the device -> identical to the pure-oracle run
+        p_ref = om.prob_tables(ds, es, tree.brlen)
+        sim.set_ptables(p_ref)
+        leaves2, comps2, internal2 = sim.simulate_injected(u, want_comps=True, keep_internal=True)
+        c1, l1, i1 = osim.simulate_injected(is_mix, tree.parent, tree.leaf_row, ws, ds, p_ref, u, keep_internal=True)
+        assert np.array_equal(leaves2, l1) and np.array_equal(comps2, c1) and np.array_equal(internal2, i1)
+
+
+def test_injected_edge_uniforms():
+    """u = 1.0, u = 2^-65, and u landing exactly on cumulative thresholds."""
+    model = model_case("hky_g4")
+    is_mix, ws, ds, es, _ = model
+    tree = om.parse_newick("((a:0.1,b:0.0):0.05,(c:2.0,d:1e-9):0.3);")
+    with make_sim(model, tree) as sim:
+        p = sim.ptables()
+        cum = np.cumsum(p, axis=-1)
+        rows = tree.n_nodes + 2
+        specials = [1.0, 2.0 ** -65, 0.5, 0.25, 0.75, np.nextafter(1.0, 0)]
+        for n in range(tree.n_nodes):
+            for c in range(4):
+                for i in range(4):
+                    specials += list(cum[n, c, i] / cum[n, c, i, -1])
+        specials = np.array([x for x in specials if 0 < x <= 1.0])
+        rng = np.random.default_rng(1)
+        s = 4096
+        u = rng.choice(specials, size=(rows, s))
+        leaves, comps, internal = sim.simulate_injected(u, want_comps=True, keep_internal=True)
+        c0, l0, i0 = osim.simulate_injected(is_mix, tree.parent, tree.leaf_row, ws, ds, p, u, keep_internal=True)
+        assert np.array_equal(leaves, l0) and np.array_equal(comps, c0) and np.array_equal(internal, i0)
+
+
+def test_injected_single_node_and_empty():
+    model = model_case("jc")
+    tree = om.parse_newick("x;")
+    with make_sim(model, tree) as sim:
+        u = np.array([[0.5799093793674204], [0.9711]])  # KAT-1's stream
+        leaves, _, internal = sim.simulate_injected(u, keep_internal=True)
+        assert leaves.tolist() == [[2]] and internal.tolist() == [[2]]
+        leaves, _, _ = sim.simulate_injected(np.zeros((2, 0)))
+        assert leaves.shape == (1, 0)
+        assert sim.simulate(0, 0)[0].shape == (1, 0)
+
+
+def test_injected_bad_weights_is_an_error():
+    """mwc-random raises "bad weights" when no cumulative entry reaches p; u > 1 provokes it."""
+    model = model_case("jc")
+    tree = om.parse_newick("(a:0.1,b:0.1);")
+    with make_sim(model, tree) as sim:
+        u = np.full((tree.n_nodes + 1, 8), 0.5)
+        u[2, 3] = 1.5
+        with pytest.raises(eb.ElxError, match="bad weights"):
+            sim.simulate_injected(u)
+        sim.simulate_injected(np.full((tree.n_nodes + 1, 8), 0.5))  # handle still usable
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 free-running mode
+# ---------------------------------------------------------------------------------------------
+def check_alias_tables(p, e16, qlo, k):
+    """The alias tables encode integer masses m_i with sum 2^47 and m_i / 2^47 == p_i / sum(p) within 2^-45."""
+    a = spec.alias_bits(k)
+    kp = 1 << a
+    cap = 1 << (47 - a)
+    e = e16.astype(np.int64)
+    qh = e >> (a + 1)
+    al = (e >> 1) & (kp - 1)
+    q = (qh << 32) | qlo.astype(np.int64)
+    self_col = al == np.arange(kp)
+    q = np.where(self_col, cap, q)  # alias == self means "always accept"
+    mass = np.zeros(p.shape[:-1] + (kp,), dtype=np.int64)
+    for j in range(kp):
+        mass[..., j] += q[..., j]
+        np.put_along_axis(mass, al[..., j:j + 1], np.take_along_axis(mass, al[..., j:j + 1], -1) + (cap - q[..., j:j + 1]), -1)
+    assert np.all(mass.sum(-1) == 1 << 47)
+    assert np.all(mass[..., k:] == 0)
+    pn = p / p.sum(-1, keepdims=True)
+    assert np.max(np.abs(mass[..., :k] / float(1 << 47) - pn)) < 2.0 ** -44
+
+
+@pytest.mark.parametrize("name,tree_file,s", [("jc", "Newick.tree", 10000), ("hky_g4", "Newick.tree", 5000),
+                                             ("lg_g4", "UltraMetric.tree", 3000), ("c10", "UltraMetric.tree", 2000),
+                                             ("mixture_dna", "Newick.tree", 2000)])
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_freerun_matches_spec(name, tree_file, s, force_generic):
+    model = model_case(name)
+    is_mix, ws, ds, es, _ = model
+    tree = tree_from_file(tree_file)
+    with make_sim(model, tree, force_generic=force_generic) as sim:
+        e16, qlo = sim.alias_tables()
+        check_alias_tables(sim.ptables(), e16, qlo, ds.shape[1])
+        for seed, site0 in ((0, 0), (0xDEADBEEFCAFEF00D, 0), (7, 8 * 1000003), (7, 13)):
+            leaves, comps, internal = sim.simulate(seed, s, site0=site0, want_comps=True, keep_internal=True)
+            l0, c0, i0 = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, seed, site0, s, keep_internal=True)
+            assert np.array_equal(leaves, l0), (seed, site0)
+            assert np.array_equal(comps, c0) and np.array_equal(internal, i0)
+
+
+def test_freerun_refinement_path_is_exercised():
+    """Tables with many exact ties in the high bits: force r == q_hi often by using a tree of identical
+    short branches and a long run; compares against the spec which always takes the same path."""
+    model = model_case("hky")
+    is_mix, ws, ds, es, _ = model
+    tree = om.parse_newick("(" + ",".join("t%d:0.013" % i for i in range(64)) + ");")
+    with make_sim(model, tree) as sim:
+        e16, qlo = sim.alias_tables()
+        s = 200000
+        leaves, _, _ = sim.simulate(3, s)
+        l0, _, _ = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, 3, 0, s)
+        assert np.array_equal(leaves, l0)
+
+
+def test_freerun_partition_invariance():
+    """Output is a pure function of (seed, global site, node): any split of the site range gives the same bytes."""
+    model = model_case("hky_g4")
+    tree = tree_from_file("Newick.tree")
+    with make_sim(model, tree) as sim:
+        whole, cw, _ = sim.simulate(11, 5000, want_comps=True)
+        cuts = [0, 1, 17, 1024, 1031, 4096, 5000]
+        parts = [sim.simulate(11, b - a, site0=a, want_comps=True) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert np.array_equal(whole, np.concatenate([p[0] for p in parts], axis=1))
+        assert np.array_equal(cw, np.concatenate([p[1] for p in parts]))
+    with make_sim(model, tree, force_generic=True) as sim2:
+        assert np.array_equal(whole, sim2.simulate(11, 5000)[0])
+
+
+@pytest.mark.parametrize("name", ["jc", "hky_g4", "mixture_dna"])
+def test_freerun_chi_square_vs_exact_pattern_probabilities(name):
+    """Free-running output vs exact Felsenstein-pruning pattern probabilities on a 4-taxon tree (256 patterns)."""
+    from scipy import stats
+
+    model = model_case(name)
+    is_mix, ws, ds, es, _ = model
+    tree = om.parse_newick("((a:0.1,b:0.3):0.05,(c:0.02,d:0.7):0.2):0.15;")
+    s = 2_000_000
+    with make_sim(model, tree) as sim:
+        leaves, _, _ = sim.simulate(2024, s)
+        probs = pruning.pattern_probabilities(is_mix, ws, ds, sim.ptables(), tree.parent, tree.leaf_row)
+    assert abs(probs.sum() - 1) < 1e-12
+    idx = np.zeros(s, dtype=np.int64)
+    for t in range(4):
+        idx = idx * 4 + leaves[t]
+    obs = np.bincount(idx, minlength=256)
+    exp = probs * s
+    keep = exp >= 5
+    chi2 = float(((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum())
+    pval = stats.chi2.sf(chi2, int(keep.sum()) - 1)
+    assert pval > 1e-4, (chi2, pval)
+
+
+def test_freerun_chi_square_protein_marginals_and_pairs():
+    """LG+G4: per-taxon state frequencies vs pi and the pair pattern table of two leaves vs exact probabilities."""
+    from scipy import stats
+
+    model = model_case("lg_g4")
+    is_mix, ws, ds, es, _ = model
+    tree = om.parse_newick("(a:0.2,b:0.4);")
+    s = 1_000_000
+    with make_sim(model, tree) as sim:
+        leaves, comps, _ = sim.simulate(5, s, want_comps=True)
+        probs = pruning.pattern_probabilities(is_mix, ws, ds, sim.ptables(), tree.parent, tree.leaf_row)
+    obs = np.bincount(leaves[0].astype(np.int64) * 20 + leaves[1], minlength=400)
+    exp = probs * s
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    assert stats.chi2.sf(chi2, 399) > 1e-4, chi2
+    cc = np.bincount(comps, minlength=4)
+    assert stats.chisquare(cc).pvalue > 1e-4  # gamma categories are equiprobable (weights all 1.0)
+
+
+def test_freerun_two_sample_vs_oracle_stream():
+    """Free-running GPU output vs the oracle's free-running output on the reference's SplitMix stream
+    (two-sample chi-square on site patterns of a 3-taxon tree)."""
+    from scipy import stats
+
+    model = model_case("gtr4_g4")
+    is_mix, ws, ds, es, _ = model
+    tree = om.parse_newick("((a:0.3,b:0.1):0.2,c:0.5);")
+    s = 500_000
+    with make_sim(model, tree) as sim:
+        p = sim.ptables()
+        g = sim.simulate(99, s)[0]
+    o = osim.simulate_splitmix(is_mix, tree.parent, tree.leaf_row, ws, ds, p, s, 99, nchunks=4, nthreads=4)[1]
+
+    def hist(l):
+        return np.bincount((l[0].astype(np.int64) * 4 + l[1]) * 4 + l[2], minlength=64)
+
+    table = np.stack([hist(g), hist(o)])
+    assert stats.chi2_contingency(table)[1] > 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# public API mirror, K3 FASTA, histograms
+# ---------------------------------------------------------------------------------------------
+def test_reference_api_surface():
+    tree = tree_from_file("UltraMetric.tree")
+    sm = om.jc(om.DO_NORMALIZE)
+    leaves = eb.simulateAndFlattenPar(100, sm.stationary_distribution, sm.exchangeability_matrix, tree, 1)
+    assert leaves.shape == (10, 100) and leaves.max() < 4
+    internal = eb.simulate(10, sm.stationary_distribution, sm.exchangeability_matrix, tree, 1)
+    assert internal.shape == (tree.n_nodes, 10)  # MarkovProcessAlongTreeSpec.hs:49-52 (length 10 at every node)
+    _, ws, ds, es, _ = model_case("c10")
+    comps, leaves = eb.simulateAndFlattenMixtureModelPar(64, ws, ds, es, tree, 2)
+    assert comps.shape == (64,) and comps.max() < 10 and leaves.shape == (10, 64)
+    assert eb.simulateMixtureModel(5, ws, ds, es, tree, 2).shape == (tree.n_nodes, 5)
+
+
+@pytest.mark.parametrize("name,s", [("hky_g4", 1000), ("lg", 777), ("jc", 0), ("jc", 1)])
+def test_fasta_matches_reference_layout(name, s):
+    model = model_case(name)
+    tree = tree_from_file("Newick.tree")
+    names = tree.leaf_names()
+    alphabet = om.ALPHABET_CHARS[model[4]]
+    with make_sim(model, tree) as sim:
+        fasta, _ = sim.simulate_fasta(42, s, names, alphabet)
+        leaves, _, _ = sim.simulate(42, s)
+    assert fasta == om.sequences_to_fasta(names, leaves, model[4])
+
+
+def test_histograms_device():
+    torch = pytest.importorskip("torch")
+    model = model_case("hky")
+    tree = om.parse_newick("((a:0.1,b:0.3):0.05,(c:0.02,d:0.7):0.2);")
+    s = 100003
+    with make_sim(model, tree) as sim:
+        leaves, _, _ = sim.simulate(1, s)
+        d = torch.from_numpy(leaves).cuda()
+        sc = torch.zeros((4, 4), dtype=torch.int64, device="cuda")
+        pc = torch.zeros(256, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        sim.histogram_device(d.data_ptr(), s, s, sc.data_ptr(), pc.data_ptr())
+        torch.cuda.current_stream().synchronize()
+        import ctypes
+        torch.cuda.synchronize()
+        sc, pc = sc.cpu().numpy(), pc.cpu().numpy()
+    for t in range(4):
+        assert np.array_equal(sc[t], np.bincount(leaves[t], minlength=4))
+    idx = ((leaves[0].astype(np.int64) * 4 + leaves[1]) * 4 + leaves[2]) * 4 + leaves[3]
+    assert np.array_equal(pc, np.bincount(idx, minlength=256))
