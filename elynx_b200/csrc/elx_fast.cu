@@ -25,22 +25,24 @@
 
 namespace elx {
 
-constexpr int NPS = 64;      // nodes per TMA stage
-constexpr int NSTAGE = 3;    // stages in flight
+constexpr int MAX_NSTAGE = 3;  // TMA stages in flight
 constexpr int FAST_THREADS = 128;
 
 struct FastTables {
-  int kind = 0;  // 0 = none, 1 = DNA tiled
+  int kind = 0;  // 0 = none (generic kernel), 1 = DNA layout, 2 = protein layout
   uint8_t *d_ftab = nullptr;
   int tb = 0;           // table bytes per node
-  int stage_bytes = 0;  // NPS * (16 + tb)
+  int nps = 0;          // nodes per TMA stage
+  int nstage = 0;       // stages in flight (2 or 3)
+  int stage_bytes = 0;  // nps * (16 + tb)
   int n_stages = 0;
+  size_t smem = 0;
 };
 
 struct FastArgs {
   SimArgs s;
   const uint8_t *ftab;
-  int tb, stage_bytes, n_stages;
+  int tb, stage_bytes, n_stages, nps, nstage;
 };
 
 // ---- PTX helpers --------------------------------------------------------------------------------
@@ -90,55 +92,55 @@ __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, dou
   return -1;
 }
 
-// One pair of draws (two sites sharing one Philox word).  P = packed parent offsets of the quad, dA/dB = byte index.
-// Returns the packed min (child bits at 1..2 of each half) and the tie detector t = w ^ ee.
-template <int DA, int DB>
-__device__ __forceinline__ void draw_pair(uint32_t tbl, uint32_t P, uint32_t w, uint32_t &c2, uint32_t &t) {
-  uint32_t offA = __byte_perm(P, 0u, 0x4440u | DA);
-  uint32_t offB = __byte_perm(P, 0u, 0x4440u | DB);
-  uint32_t aA = offA | (w & 6u);
-  uint32_t aB = offB | ((w >> 16) & 6u);
-  uint32_t eA = lds_u16(tbl + aA);
-  uint32_t eB = lds_u16(tbl + aB);
-  uint32_t ee = __byte_perm(eA, eB, 0x5410u);
-  c2 = __vminu2(w, ee);
-  t = w ^ ee;
-}
+// ---------------------------------------------------------------------------------------------------
+// Tiled kernel.  AA = false: DNA layout (K = 4, KP = 4, C <= 8; per-site byte = comp*32 + state*8, 4 packed regs).
+//                AA = true : protein layout (K <= 32 > 4, KP = 32, rows of 64 B; per-site 16-bit lane =
+//                            (comp*K + state)*64, 8 packed regs; C*K*64 <= 65535).
+// ---------------------------------------------------------------------------------------------------
+template <bool AA>
+struct Lay {
+  static constexpr int NREG = AA ? 8 : 4;            // packed parent registers per thread (16 sites)
+  static constexpr uint32_t JMASK = AA ? 0x3eu : 6u;  // j*2 bits of a 16-bit draw
+  static constexpr uint32_t TIE = AA ? 64u : 8u;      // lane of (x ^ e) below this <=> high bits equal
+  static constexpr int A = AA ? 5 : 2;
+};
 
-// Exact resolution of a tie in the 13 high bits (DNA layout): 32 more random bits against the low threshold word.
-template <int ROUNDS>
+// Exact resolution of a tie in the high bits: 32 more random bits against the low threshold word.
+template <int ROUNDS, bool AA>
 __device__ __noinline__ uint32_t refine_draw(const SimArgs &a, uint32_t tbl, uint32_t off, uint32_t x16, uint64_t site,
                                              uint32_t node, uint2 key) {
-  const uint32_t j = (x16 >> 1) & 3u;
+  constexpr uint32_t KPm1 = (1u << Lay<AA>::A) - 1u;
+  const uint32_t j = (x16 >> 1) & KPm1;
   const uint32_t e = lds_u16(tbl + (off | (j << 1)));
   const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)site, (uint32_t)(site >> 32), node, TAG_REFINE), key);
-  const int64_t idx = (((int64_t)node * a.C + (off >> 5)) * 4 + ((off >> 3) & 3u)) * 4 + j;
-  return z.x < __ldg(a.qlo + idx) ? j : ((e >> 1) & 3u);
+  // off / rowbytes = comp*K + state ; e16/qlo index = ((node*C + comp)*K + state)*KP + j
+  const uint32_t row = AA ? (off >> 6) : (off >> 3);
+  const int64_t idx = (((int64_t)node * a.C * a.K) + row) * (KPm1 + 1) + j;
+  return z.x < __ldg(a.qlo + idx) ? j : ((e >> 1) & KPm1);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// DNA tiled kernel
-// ---------------------------------------------------------------------------------------------------
-template <int ROUNDS>
-__global__ void __launch_bounds__(FAST_THREADS) k2_dna_tiled(FastArgs fa) {
+template <int ROUNDS, bool AA>
+__global__ void __launch_bounds__(FAST_THREADS) k2_tiled(FastArgs fa) {
+  using L = Lay<AA>;
+  constexpr int NREG = L::NREG;
   extern __shared__ __align__(128) uint8_t smem[];
   const SimArgs &a = fa.s;
   const int tid = threadIdx.x;
+  const int nstage = fa.nstage, nps = fa.nps;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-  uint8_t *stage0 = smem + 128;
-  const uint32_t stage_smem = smem_u32(stage0);
-  const uint32_t slots_smem = stage_smem + (uint32_t)(NSTAGE * fa.stage_bytes);
-  const uint32_t my_slot0 = slots_smem + (uint32_t)tid * 16u;
-  const uint32_t slot_stride = FAST_THREADS * 16u;
+  const uint32_t stage_smem = smem_u32(smem + 128);
+  const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
+  const uint32_t my_slot0 = slots_smem + (uint32_t)tid * (NREG * 4u);
+  const uint32_t slot_stride = FAST_THREADS * (NREG * 4u);
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < nstage; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   __syncthreads();
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE && i < fa.n_stages; ++i) {
+    for (int i = 0; i < nstage && i < fa.n_stages; ++i) {
       mbar_expect_tx(smem_u32(&bars[i]), (uint32_t)fa.stage_bytes);
       tma_bulk_g2s(stage_smem + (uint32_t)(i * fa.stage_bytes), fa.ftab + (size_t)i * fa.stage_bytes, (uint32_t)fa.stage_bytes,
                    smem_u32(&bars[i]));
@@ -156,41 +158,43 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_dna_tiled(FastArgs fa) {
   const uint32_t G0lo = (uint32_t)G0, Ghi = (uint32_t)(G0 >> 32), G1lo = G0lo | 1u;
 
   // component and root-state draws (once per site; exact fp64 inverse-CDF, as in the generic kernel)
-  uint32_t cmask[4], par[4];
+  uint32_t cbase[NREG], par[NREG];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t cm = 0, pr = 0;
+  for (int q = 0; q < NREG; ++q) { cbase[q] = 0; par[q] = 0; }
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      uint64_t s = (uint64_t)sbase + q * 4 + d;
-      int c = 0;
-      if (a.is_mixture) {
-        uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_COMP), key);
-        c = cat_cum(a.cumw, a.C, u53_positive(x.x, x.y));
-        if (c < 0) { atomicExch(a.error_flag, a.N + 1); c = 0; }
-      }
-      uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_ROOT), key);
-      int root = cat_cum(a.cumpi + c * 4, 4, u53_positive(x.x, x.y));
-      if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
-      cm |= (uint32_t)(c * 32) << (8 * d);
-      pr |= (uint32_t)(c * 32 + root * 8) << (8 * d);
-      int64_t col = col0 + q * 4 + d;
-      if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = c;
+  for (int i = 0; i < 16; ++i) {
+    uint64_t s = (uint64_t)sbase + i;
+    int c = 0;
+    if (a.is_mixture) {
+      uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_COMP), key);
+      c = cat_cum(a.cumw, a.C, u53_positive(x.x, x.y));
+      if (c < 0) { atomicExch(a.error_flag, a.N + 1); c = 0; }
     }
-    cmask[q] = cm;
-    par[q] = pr;
+    uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_ROOT), key);
+    int root = cat_cum(a.cumpi + c * a.K, a.K, u53_positive(x.x, x.y));
+    if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
+    if (AA) {
+      cbase[i >> 1] |= (uint32_t)(c * a.K * 64) << (16 * (i & 1));
+      par[i >> 1] |= (uint32_t)((c * a.K + root) * 64) << (16 * (i & 1));
+    } else {
+      cbase[i >> 2] |= (uint32_t)(c * 32) << (8 * (i & 3));
+      par[i >> 2] |= (uint32_t)(c * 32 + root * 8) << (8 * (i & 3));
+    }
+    int64_t col = col0 + i;
+    if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = c;
   }
-  sts_v4(my_slot0, make_uint4(par[0], par[1], par[2], par[3]));
+#pragma unroll
+  for (int q = 0; q < NREG; q += 4) sts_v4(my_slot0 + q * 4u, make_uint4(par[q], par[q + 1], par[q + 2], par[q + 3]));
   int reg_slot = 0;  // slot whose contents are mirrored in par[]
 
   const bool vec_store = full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
                          ((col0 & 15) == 0);
 
   for (int st = 0; st < fa.n_stages; ++st) {
-    const int buf = st % NSTAGE;
-    mbar_wait(smem_u32(&bars[buf]), (uint32_t)((st / NSTAGE) & 1));
+    const int buf = st % nstage;
+    mbar_wait(smem_u32(&bars[buf]), (uint32_t)((st / nstage) & 1));
     const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
-    const int nn = min(NPS, a.N - st * NPS);
+    const int nn = min(nps, a.N - st * nps);
     for (int k = 0; k < nn; ++k) {
       const uint4 rec = lds_v4(sbuf + (uint32_t)k * 16u);
       const uint32_t node = rec.x;
@@ -198,57 +202,76 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_dna_tiled(FastArgs fa) {
       const int dst = (int)(int16_t)(rec.y >> 16);
       const int leaf_row = (int)rec.z;
       if (src != reg_slot) {
-        uint4 v = lds_v4(my_slot0 + (uint32_t)src * slot_stride);
-        par[0] = v.x; par[1] = v.y; par[2] = v.z; par[3] = v.w;
+#pragma unroll
+        for (int q = 0; q < NREG; q += 4) {
+          uint4 v = lds_v4(my_slot0 + (uint32_t)src * slot_stride + q * 4u);
+          par[q] = v.x; par[q + 1] = v.y; par[q + 2] = v.z; par[q + 3] = v.w;
+        }
         reg_slot = src;
       }
       const uint4 x0 = philox4x32<ROUNDS>(make_uint4(G0lo, Ghi, node, TAG_NODE), key);
       const uint4 x1 = philox4x32<ROUNDS>(make_uint4(G1lo, Ghi, node, TAG_NODE), key);
-      const uint32_t tbl = sbuf + (uint32_t)(NPS * 16) + (uint32_t)k * (uint32_t)fa.tb;
+      const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const uint32_t tbl = sbuf + (uint32_t)(nps * 16) + (uint32_t)k * (uint32_t)fa.tb;
       uint32_t c2[8], t[8];
-      draw_pair<0, 1>(tbl, par[0], x0.x, c2[0], t[0]);
-      draw_pair<2, 3>(tbl, par[0], x0.y, c2[1], t[1]);
-      draw_pair<0, 1>(tbl, par[1], x0.z, c2[2], t[2]);
-      draw_pair<2, 3>(tbl, par[1], x0.w, c2[3], t[3]);
-      draw_pair<0, 1>(tbl, par[2], x1.x, c2[4], t[4]);
-      draw_pair<2, 3>(tbl, par[2], x1.y, c2[5], t[5]);
-      draw_pair<0, 1>(tbl, par[3], x1.z, c2[6], t[6]);
-      draw_pair<2, 3>(tbl, par[3], x1.w, c2[7], t[7]);
-      uint32_t raw[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) raw[q] = __byte_perm(c2[2 * q], c2[2 * q + 1], 0x6420u);
-      // tie detection: some 16-bit lane of t has all 13 high bits zero  <=>  lane < 8
+      for (int pr = 0; pr < 8; ++pr) {  // pair pr = sites 2pr, 2pr+1 share Philox word pr
+        uint32_t offA, offB;
+        if (AA) {
+          offA = par[pr] & 0xffffu;
+          offB = par[pr] >> 16;
+        } else {
+          offA = __byte_perm(par[pr >> 1], 0u, 0x4440u | ((pr & 1) * 2));
+          offB = __byte_perm(par[pr >> 1], 0u, 0x4440u | ((pr & 1) * 2 + 1));
+        }
+        uint32_t aA = offA | (w[pr] & L::JMASK);
+        uint32_t aB = offB | ((w[pr] >> 16) & L::JMASK);
+        uint32_t eA = lds_u16(tbl + aA);
+        uint32_t eB = lds_u16(tbl + aB);
+        uint32_t ee = __byte_perm(eA, eB, 0x5410u);
+        c2[pr] = __vminu2(w[pr], ee);
+        t[pr] = w[pr] ^ ee;
+      }
+      // tie detection: some 16-bit lane of t has all its high (threshold) bits zero
       uint32_t m01 = __vimin3_u16x2(t[0], t[1], t[2]);
       uint32_t m23 = __vimin3_u16x2(t[3], t[4], t[5]);
       uint32_t m = __vimin3_u16x2(m01, m23, __vminu2(t[6], t[7]));
-      if (((m & 0xffffu) < 8u) || ((m >> 16) < 8u)) {
-        // exact path (rare: 16 * 2^-13 per thread-node): redo the tied draws with the 32-bit refinement.
-        // Fully unrolled with static indices so that par[] / raw[] stay in registers on the fast path.
-        const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (((m & 0xffffu) < L::TIE) || ((m >> 16) < L::TIE)) {
+        // exact path (rare): redo the tied draws with the 32-bit refinement.  Fully unrolled with static indices
+        // so that the packed registers stay in registers on the fast path.
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const uint32_t tl = (t[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-          if (tl < 8u) {
-            const uint32_t x16 = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-            const uint32_t off = (par[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-            const uint32_t child = refine_draw<ROUNDS>(a, tbl, off, x16, (uint64_t)sbase + i, node, key);
-            const uint32_t sh = (i & 3) * 8;
-            raw[i >> 2] = (raw[i >> 2] & ~(0xffu << sh)) | ((child << 1) << sh);
+          const uint32_t sh = (i & 1) * 16;
+          const uint32_t tl = (t[i >> 1] >> sh) & 0xffffu;
+          if (tl < L::TIE) {
+            const uint32_t x16 = (w[i >> 1] >> sh) & 0xffffu;
+            const uint32_t off = AA ? ((par[i >> 1] >> sh) & 0xffffu) : ((par[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+            const uint32_t child = refine_draw<ROUNDS, AA>(a, tbl, off, x16, (uint64_t)sbase + i, node, key);
+            c2[i >> 1] = (c2[i >> 1] & ~(0xffffu << sh)) | ((child << 1) << sh);
           }
         }
       }
       if (dst >= 0) {
+        if (AA) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) par[q] = ((raw[q] & 0x06060606u) << 2) | cmask[q];
-        sts_v4(my_slot0 + (uint32_t)dst * slot_stride, make_uint4(par[0], par[1], par[2], par[3]));
+          for (int q = 0; q < 8; ++q) par[q] = ((c2[q] & 0x003e003eu) << 5) + cbase[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            par[q] = ((__byte_perm(c2[2 * q], c2[2 * q + 1], 0x6420u) & 0x06060606u) << 2) | cbase[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NREG; q += 4)
+          sts_v4(my_slot0 + (uint32_t)dst * slot_stride + q * 4u, make_uint4(par[q], par[q + 1], par[q + 2], par[q + 3]));
         reg_slot = dst;
       }
       if (leaf_row >= 0 && any) {
+        constexpr uint32_t SM = AA ? 0x1f1f1f1fu : 0x03030303u;
         uint4 o;
-        o.x = (raw[0] >> 1) & 0x03030303u;
-        o.y = (raw[1] >> 1) & 0x03030303u;
-        o.z = (raw[2] >> 1) & 0x03030303u;
-        o.w = (raw[3] >> 1) & 0x03030303u;
+        o.x = (__byte_perm(c2[0], c2[1], 0x6420u) >> 1) & SM;
+        o.y = (__byte_perm(c2[2], c2[3], 0x6420u) >> 1) & SM;
+        o.z = (__byte_perm(c2[4], c2[5], 0x6420u) >> 1) & SM;
+        o.w = (__byte_perm(c2[6], c2[7], 0x6420u) >> 1) & SM;
         uint8_t *dstp = a.leaves + (int64_t)leaf_row * a.leaves_pitch + col0;
         if (vec_store) {
           stg_cs_v4(dstp, o);
@@ -262,30 +285,31 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_dna_tiled(FastArgs fa) {
       }
     }
     __syncthreads();  // every warp is done with this stage buffer
-    if (tid == 0 && st + NSTAGE < fa.n_stages) {
+    if (tid == 0 && st + nstage < fa.n_stages) {
       fence_async_smem();
       mbar_expect_tx(smem_u32(&bars[buf]), (uint32_t)fa.stage_bytes);
-      tma_bulk_g2s(sbuf, fa.ftab + (size_t)(st + NSTAGE) * fa.stage_bytes, (uint32_t)fa.stage_bytes, smem_u32(&bars[buf]));
+      tma_bulk_g2s(sbuf, fa.ftab + (size_t)(st + nstage) * fa.stage_bytes, (uint32_t)fa.stage_bytes, smem_u32(&bars[buf]));
     }
   }
 }
 
-// Gather the per-node alias tables into walk order, interleaved with the walk records, one stage per NPS nodes:
-// stage = [NPS x WalkRec (16 B)] [NPS x tb table bytes].
-__global__ void k_build_ftab(int N, int tb, int stage_bytes, const WalkRec *__restrict__ walk, const uint16_t *__restrict__ e16,
-                             uint8_t *__restrict__ ftab) {
+// Gather the per-node alias tables into walk order, interleaved with the walk records, one stage per nps nodes:
+// stage = [nps x WalkRec (16 B)] [nps x tb table bytes].  The e16 layout [node][comp][state][column] u16 already is the
+// row layout both kernels address (DNA: comp*32 + state*8 + j*2; protein: (comp*K + state)*64 + j*2).
+__global__ void k_build_ftab(int N, int nps, int tb, int stage_bytes, const WalkRec *__restrict__ walk,
+                             const uint16_t *__restrict__ e16, uint8_t *__restrict__ ftab) {
   const int chunks_per_node = (16 + tb) / 16;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * chunks_per_node) return;
   int k = (int)(i / chunks_per_node), ch = (int)(i % chunks_per_node);
-  int st = k / NPS, kk = k % NPS;
+  int st = k / nps, kk = k % nps;
   uint8_t *stage = ftab + (size_t)st * stage_bytes;
   if (ch == 0) {
     *reinterpret_cast<uint4 *>(stage + kk * 16) = *reinterpret_cast<const uint4 *>(&walk[k]);
   } else {
     int node = walk[k].node;
     const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(e16) + (size_t)node * tb) + (ch - 1);
-    *reinterpret_cast<uint4 *>(stage + NPS * 16 + (size_t)kk * tb + (ch - 1) * 16) = *src;
+    *reinterpret_cast<uint4 *>(stage + nps * 16 + (size_t)kk * tb + (ch - 1) * 16) = *src;
   }
 }
 
@@ -295,25 +319,41 @@ int fast_tables_build(elx_handle *h) {
     ft = new FastTables();
     h->fast = ft;
   }
-  if (h->K == 4 && h->C <= 8 && h->KP == 4) {
-    ft->kind = 1;
-    ft->tb = h->C * 32;
-    ft->stage_bytes = NPS * (16 + ft->tb);
-    ft->n_stages = (h->N + NPS - 1) / NPS;
+  int kind = 0, tb = 0, slot_bytes = 0;
+  if (h->K == 4 && h->KP == 4 && h->C <= 8) {
+    kind = 1; tb = h->C * 32; slot_bytes = 16;
+  } else if (h->KP == 32 && (int64_t)h->C * h->K * 64 <= 65535) {
+    kind = 2; tb = h->C * h->K * 64; slot_bytes = 32;
+  }
+  if (kind) {
+    // stage geometry: about 24 KB per stage, 3 stages; shrink to 2 stages / 1 node when the tables are big
+    const size_t slots = (size_t)h->n_slots * FAST_THREADS * slot_bytes;
+    int nps = (24 * 1024) / (16 + tb);
+    if (nps > 64) nps = 64;
+    if (nps < 1) nps = 1;
+    int nstage = MAX_NSTAGE;
+    size_t smem = 128 + (size_t)nstage * nps * (16 + tb) + slots;
+    if (smem > 100 * 1024 && nps == 1) { nstage = 2; smem = 128 + (size_t)nstage * (16 + tb) + slots; }
+    if (smem > 220 * 1024) kind = 0;
+    ft->nps = nps; ft->nstage = nstage; ft->smem = smem;
+  }
+  ft->kind = kind;
+  if (kind) {
+    ft->tb = tb;
+    ft->stage_bytes = ft->nps * (16 + tb);
+    ft->n_stages = (h->N + ft->nps - 1) / ft->nps;
     size_t bytes = (size_t)ft->n_stages * ft->stage_bytes;
     if (!ft->d_ftab) {
       cudaError_t e = cudaMalloc((void **)&ft->d_ftab, bytes);
       if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("cudaMalloc(ftab): ") + cudaGetErrorString(e));
       cudaMemsetAsync(ft->d_ftab, 0, bytes, h->stream);
     }
-    int chunks = (16 + ft->tb) / 16;
+    int chunks = (16 + tb) / 16;
     int64_t n = (int64_t)h->N * chunks;
-    k_build_ftab<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, ft->tb, ft->stage_bytes, h->d_walk, h->d_e16, ft->d_ftab);
+    k_build_ftab<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, ft->nps, tb, ft->stage_bytes, h->d_walk, h->d_e16, ft->d_ftab);
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("k_build_ftab: ") + cudaGetErrorString(e));
-  } else {
-    ft->kind = 0;
   }
   return 0;
 }
@@ -326,6 +366,14 @@ void fast_tables_free(elx_handle *h) {
   h->fast = nullptr;
 }
 
+template <int ROUNDS, bool AA>
+static cudaError_t launch_tiled(const FastArgs &fa, unsigned blocks, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(k2_tiled<ROUNDS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k2_tiled<ROUNDS, AA><<<blocks, FAST_THREADS, smem, stream>>>(fa);
+  return cudaGetLastError();
+}
+
 int fast_simulate(elx_handle *h, const SimArgs &a, int *used) {
   *used = 0;
   FastTables *ft = static_cast<FastTables *>(h->fast);
@@ -336,23 +384,17 @@ int fast_simulate(elx_handle *h, const SimArgs &a, int *used) {
   fa.tb = ft->tb;
   fa.stage_bytes = ft->stage_bytes;
   fa.n_stages = ft->n_stages;
-  size_t smem = 128 + (size_t)NSTAGE * ft->stage_bytes + (size_t)h->n_slots * FAST_THREADS * 16;
-  if (smem > 200 * 1024) return 0;  // fall back to the generic kernel
+  fa.nps = ft->nps;
+  fa.nstage = ft->nstage;
   int64_t g0 = a.site0 >> 4, g1 = (a.site0 + a.nsites + 15) >> 4;
-  int64_t groups = g1 - g0;
-  unsigned blocks = (unsigned)((groups + FAST_THREADS - 1) / FAST_THREADS);
+  unsigned blocks = (unsigned)((g1 - g0 + FAST_THREADS - 1) / FAST_THREADS);
   cudaError_t e;
-  if (h->rounds == 7) {
-    e = cudaFuncSetAttribute(k2_dna_tiled<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k2_dna_tiled<7><<<blocks, FAST_THREADS, smem, h->stream>>>(fa);
-  } else {
-    e = cudaFuncSetAttribute(k2_dna_tiled<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k2_dna_tiled<10><<<blocks, FAST_THREADS, smem, h->stream>>>(fa);
-  }
-  if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("k2_dna_tiled attribute: ") + cudaGetErrorString(e));
+  if (ft->kind == 1)
+    e = h->rounds == 7 ? launch_tiled<7, false>(fa, blocks, ft->smem, h->stream) : launch_tiled<10, false>(fa, blocks, ft->smem, h->stream);
+  else
+    e = h->rounds == 7 ? launch_tiled<7, true>(fa, blocks, ft->smem, h->stream) : launch_tiled<10, true>(fa, blocks, ft->smem, h->stream);
+  if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("k2_tiled launch: ") + cudaGetErrorString(e));
   h->launches++;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("k2_dna_tiled launch: ") + cudaGetErrorString(e));
   *used = 1;
   return 0;
 }
