@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libelynx_b200.so")
+LIB_PATH = os.environ.get("ELX_LIB") or os.path.join(_HERE, "libelynx_b200.so")  # ELX_LIB: A/B builds of the same ABI
 
 ELX_OK = 0
 ELX_E_INVALID = -1

@@ -93,13 +93,13 @@ __global__ void k1_cum_from_p(int64_t rows, int K, const double *__restrict__ P,
 }
 
 // Alias tables for the free-running sampler, built in exact integer arithmetic (one thread per row).
-// Row masses m_i = round(p_i / sum p * 2^47) (residual added to the largest), column capacity 2^(47-A).
+// Row masses m_i = round(p_i / sum p * 2^48) (residual added to the largest), column capacity 2^(48-A).
 __global__ void k1_alias(int64_t rows, int K, int A, const double *__restrict__ P, uint16_t *__restrict__ e16,
                          uint32_t *__restrict__ qlo) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int KP = 1 << A;
-  const int QB = 47 - A;
+  const int QB = 48 - A;
   const int64_t CAP = (int64_t)1 << QB;
   int64_t m[64];
   int alias[64];
@@ -116,12 +116,12 @@ __global__ void k1_alias(int64_t rows, int K, int A, const double *__restrict__ 
   for (int j = 0; j < KP; ++j) {
     double p = 0.0;
     if (j < K) { p = P[r * K + j]; if (!(p > 0.0)) p = 0.0; }
-    int64_t v = sum > 0.0 ? (int64_t)llrint(p / sum * 0x1p47) : (j == 0 ? ((int64_t)1 << 47) : 0);
+    int64_t v = sum > 0.0 ? (int64_t)llrint(p / sum * 0x1p48) : (j == 0 ? ((int64_t)1 << 48) : 0);
     m[j] = v;
     tot += v;
     if (v > m[big]) big = j;
   }
-  m[big] += ((int64_t)1 << 47) - tot;
+  m[big] += ((int64_t)1 << 48) - tot;
   int ns = 0, nl = 0;
   for (int j = KP - 1; j >= 0; --j) {
     alias[j] = j;
@@ -141,7 +141,7 @@ __global__ void k1_alias(int64_t rows, int K, int A, const double *__restrict__ 
     int64_t qq = q[j];
     int al = alias[j];
     if (qq >= CAP) { qq = CAP - 1; al = j; }
-    e16[r * KP + j] = (uint16_t)(((qq >> 32) << (A + 1)) | ((int64_t)al << 1));
+    e16[r * KP + j] = (uint16_t)(((qq >> 32) << A) | (int64_t)al);
     qlo[r * KP + j] = (uint32_t)(qq & 0xffffffffu);
   }
 }
@@ -200,12 +200,12 @@ template <int ROUNDS>
 __device__ __forceinline__ int draw_child(const SimArgs &a, int node, int comp, int par, uint32_t x16, uint64_t site,
                                           uint2 key) {
   const int KP = 1 << a.A;
-  int j = (x16 >> 1) & (KP - 1);
-  uint32_t r = x16 >> (a.A + 1);
+  int j = x16 & (KP - 1);
+  uint32_t r = x16 >> a.A;
   int64_t idx = (((int64_t)node * a.C + comp) * a.K + par) * KP + j;
   uint32_t e = __ldg(a.e16 + idx);
-  uint32_t qh = e >> (a.A + 1);
-  int al = (e >> 1) & (KP - 1);
+  uint32_t qh = e >> a.A;
+  int al = e & (KP - 1);
   if (r < qh) return j;
   if (r > qh) return al;
   uint4 c = philox4x32<ROUNDS>(make_uint4((uint32_t)site, (uint32_t)(site >> 32), (uint32_t)node, TAG_REFINE), key);

@@ -44,8 +44,8 @@ __host__ __device__ __forceinline__ double u53_positive(uint32_t lo, uint32_t hi
 }
 
 // Alias-table geometry.  KP = number of columns (power of two >= K), A = log2 KP.
-// 16-bit draw x = [r : 15-A bits][j : A bits][spare : 1 bit]; table entry e = [q_hi : 15-A][alias : A][0].
-// Full acceptance threshold q = q_hi * 2^32 + q_lo in [0, 2^(47-A)); accept column j iff r*2^32 + x_lo < q.
+// 16-bit draw x = [r : 16-A bits][j : A bits]; table entry e = [q_hi : 16-A][alias : A].
+// Full acceptance threshold q = q_hi * 2^32 + q_lo in [0, 2^(48-A)); accept column j iff r*2^32 + x_lo < q.
 __host__ __device__ __forceinline__ int alias_bits(int K) {
   int a = 1;
   while ((1 << a) < K) ++a;

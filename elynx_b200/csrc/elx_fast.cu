@@ -9,7 +9,7 @@
 //   * live internal-node states sit in a shared-memory slot stack [slot][thread] (128-bit, conflict free); the
 //     walk order (heavy child last) bounds the number of slots by floor(log2 N)+1;
 //   * a draw is: PRMT (parent offset) + LOP3 (address) + LDS.U16 + half a PRMT/VIMNMX.U16x2/LOP3 -- the alias
-//     decision is a packed 16-bit min: child bits = low bits of min(random, entry); ties in the high bits (2^-13)
+//     decision is a packed 16-bit min: child bits = low bits of min(random, entry); ties in the high bits (2^-14)
 //     fall to an exact 32-bit refinement path.
 //
 // DNA kernel: K = 4, KP = 4, C <= 8.  Per-site state byte = comp*32 + state*8 = byte offset of the table row.
@@ -25,8 +25,9 @@
 
 namespace elx {
 
-constexpr int MAX_NSTAGE = 3;  // TMA stages in flight
-constexpr int FAST_THREADS = 128;
+constexpr int MAX_NSTAGE = 3;       // TMA stages in flight
+constexpr int FAST_THREADS = 128;    // threads per CTA (4 warps); lane 0 of warp 0 doubles as the TMA producer
+constexpr int FAST_CTA = FAST_THREADS;
 
 struct FastTables {
   int kind = 0;  // 0 = none (generic kernel), 1 = DNA layout, 2 = protein layout
@@ -57,6 +58,17 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -97,55 +109,94 @@ __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, dou
 //                AA = true : protein layout (K <= 32 > 4, KP = 32, rows of 64 B; per-site 16-bit lane =
 //                            (comp*K + state)*64, 8 packed regs; C*K*64 <= 65535).
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_leaf(const SimArgs &a, uint8_t *leaf_base, int leaf_row, int64_t col0, int store_mode,
+                                           uint4 o) {
+  uint8_t *dstp = leaf_base + (int64_t)leaf_row * a.leaves_pitch;
+  if (store_mode == 1) {
+    stg_cs_v4(dstp, o);  // 32 lanes x 16 B = 512 contiguous bytes of the [taxon][site] row, streaming (evict-first)
+  } else {
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+    for (int i = 0; i < 16; ++i) {
+      int64_t col = col0 + i;
+      if (col >= 0 && col < a.nsites) dstp[i] = (uint8_t)(ow[i >> 2] >> ((i & 3) * 8));
+    }
+  }
+}
+
 template <bool AA>
 struct Lay {
   static constexpr int NREG = AA ? 8 : 4;            // packed parent registers per thread (16 sites)
-  static constexpr uint32_t JMASK = AA ? 0x3eu : 6u;  // j*2 bits of a 16-bit draw
-  static constexpr uint32_t TIE = AA ? 64u : 8u;      // lane of (x ^ e) below this <=> high bits equal
+  static constexpr uint32_t JMASK = AA ? 31u : 3u;   // column bits of a 16-bit draw x = [r : 16-A][j : A]
+  static constexpr uint32_t TIE = AA ? 32u : 4u;      // lane of (x ^ e) below this <=> threshold bits equal
   static constexpr int A = AA ? 5 : 2;
 };
 
-// Exact resolution of a tie in the high bits: 32 more random bits against the low threshold word.
-template <int ROUNDS, bool AA>
-__device__ __noinline__ uint32_t refine_draw(const SimArgs &a, uint32_t tbl, uint32_t off, uint32_t x16, uint64_t site,
-                                             uint32_t node, uint2 key) {
-  constexpr uint32_t KPm1 = (1u << Lay<AA>::A) - 1u;
-  const uint32_t j = (x16 >> 1) & KPm1;
-  const uint32_t e = lds_u16(tbl + (off | (j << 1)));
-  const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)site, (uint32_t)(site >> 32), node, TAG_REFINE), key);
-  // off / rowbytes = comp*K + state ; e16/qlo index = ((node*C + comp)*K + state)*KP + j
-  const uint32_t row = AA ? (off >> 6) : (off >> 3);
-  const int64_t idx = (((int64_t)node * a.C * a.K) + row) * (KPm1 + 1) + j;
-  return z.x < __ldg(a.qlo + idx) ? j : ((e >> 1) & KPm1);
+// Component and root-state draws of one site (once per site; exact fp64 inverse-CDF on 53-bit uniforms, identical
+// to the generic kernel).  Out of line: it runs 16 times per thread in the prologue and must not inflate the
+// register budget of the node loop.  Returns comp | root << 16.
+template <int ROUNDS>
+__device__ __noinline__ uint32_t draw_comp_root(const SimArgs &a, uint64_t s, uint32_t k0, uint32_t k1) {
+  const uint2 key = make_uint2(k0, k1);
+  int c = 0;
+  if (a.is_mixture) {
+    uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_COMP), key);
+    c = cat_cum(a.cumw, a.C, u53_positive(x.x, x.y));
+    if (c < 0) { atomicExch(a.error_flag, a.N + 1); c = 0; }
+  }
+  uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_ROOT), key);
+  int root = cat_cum(a.cumpi + c * a.K, a.K, u53_positive(x.x, x.y));
+  if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
+  return (uint32_t)c | ((uint32_t)root << 16);
 }
 
+#ifndef ELX_MIN_CTAS
+#define ELX_MIN_CTAS 4
+#endif
 template <int ROUNDS, bool AA>
-__global__ void __launch_bounds__(FAST_THREADS) k2_tiled(FastArgs fa) {
+__global__ void __launch_bounds__(FAST_CTA, ELX_MIN_CTAS) k2_tiled(FastArgs fa) {
   using L = Lay<AA>;
   constexpr int NREG = L::NREG;
   extern __shared__ __align__(128) uint8_t smem[];
   const SimArgs &a = fa.s;
   const int tid = threadIdx.x;
   const int nstage = fa.nstage, nps = fa.nps;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);        // [nstage] TMA bytes have landed
+  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(smem) + 4;   // [nstage] all consumer warps are done with the buffer
   const uint32_t stage_smem = smem_u32(smem + 128);
   const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
-  const uint32_t my_slot0 = slots_smem + (uint32_t)tid * (NREG * 4u);
-  const uint32_t slot_stride = FAST_THREADS * (NREG * 4u);
+  const uint32_t my_slot0 = slots_smem + (uint32_t)tid * 16u;  // slot stack [slot][thread] x 16 B
+  const uint32_t slot_stride = FAST_THREADS * 16u;
 
   if (tid == 0) {
-    for (int i = 0; i < nstage; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < nstage; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), FAST_THREADS / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 0; i < nstage && i < fa.n_stages; ++i) {
-      mbar_expect_tx(smem_u32(&bars[i]), (uint32_t)fa.stage_bytes);
-      tma_bulk_g2s(stage_smem + (uint32_t)(i * fa.stage_bytes), fa.ftab + (size_t)i * fa.stage_bytes, (uint32_t)fa.stage_bytes,
-                   smem_u32(&bars[i]));
+  __syncthreads();  // the only CTA-wide barrier: roles split below
+
+  // ---- in-band TMA producer (thread 0): streams [walk records | alias tables] stage by stage into the ring.
+  // Buffers are released per warp (empty_bar, count = #warps), so no CTA-wide barrier is needed; thread 0 tops the
+  // ring up whenever a buffer is free and only blocks when it needs a stage that has not been issued yet.
+  int next_fill = 0;
+  auto topup = [&](int st) {
+    while (next_fill < fa.n_stages && next_fill < st + nstage) {
+      const int buf = next_fill % nstage, use = next_fill / nstage;
+      if (use > 0) {
+        const uint32_t par = (uint32_t)((use - 1) & 1);
+        if (next_fill <= st) mbar_wait(smem_u32(&empty_bar[buf]), par);
+        else if (!mbar_test(smem_u32(&empty_bar[buf]), par)) break;
+      }
+      fence_async_smem();
+      mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
+      tma_bulk_g2s(stage_smem + (uint32_t)(buf * fa.stage_bytes), fa.ftab + (size_t)next_fill * fa.stage_bytes,
+                   (uint32_t)fa.stage_bytes, smem_u32(&full_bar[buf]));
+      ++next_fill;
     }
-  }
+  };
+  if (tid == 0) topup(0);  // fills the whole ring: stages 0..nstage-1
 
   // 16 sites per thread, aligned on global site index multiples of 16
   const int64_t g16 = (a.site0 >> 4) + (int64_t)blockIdx.x * FAST_THREADS + tid;
@@ -163,16 +214,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_tiled(FastArgs fa) {
   for (int q = 0; q < NREG; ++q) { cbase[q] = 0; par[q] = 0; }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    uint64_t s = (uint64_t)sbase + i;
-    int c = 0;
-    if (a.is_mixture) {
-      uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_COMP), key);
-      c = cat_cum(a.cumw, a.C, u53_positive(x.x, x.y));
-      if (c < 0) { atomicExch(a.error_flag, a.N + 1); c = 0; }
-    }
-    uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_ROOT), key);
-    int root = cat_cum(a.cumpi + c * a.K, a.K, u53_positive(x.x, x.y));
-    if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
+    const uint32_t cr = draw_comp_root<ROUNDS>(a, (uint64_t)sbase + i, key.x, key.y);
+    const int c = (int)(cr & 0xffffu), root = (int)(cr >> 16);
     if (AA) {
       cbase[i >> 1] |= (uint32_t)(c * a.K * 64) << (16 * (i & 1));
       par[i >> 1] |= (uint32_t)((c * a.K + root) * 64) << (16 * (i & 1));
@@ -183,29 +226,62 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_tiled(FastArgs fa) {
     int64_t col = col0 + i;
     if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = c;
   }
+  // Pin the loop invariants into single registers: without this ptxas keeps the per-site pieces of cbase[] apart and
+  // re-ORs them (and re-derives the slot address and the store predicates) on every node.
 #pragma unroll
-  for (int q = 0; q < NREG; q += 4) sts_v4(my_slot0 + q * 4u, make_uint4(par[q], par[q + 1], par[q + 2], par[q + 3]));
+  for (int q = 0; q < NREG; ++q) asm volatile("" : "+r"(cbase[q]));
+  uint32_t slot_base = my_slot0;
+  asm volatile("" : "+r"(slot_base));
+  // slot 0 = root states.  DNA slots hold the packed offset bytes (= par[]); protein slots hold state bytes
+  // (the leaf output format) and are expanded to 16-bit offset lanes on reload.
+  if (AA) {
+    uint32_t b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t lo = (par[2 * q] - cbase[2 * q]) >> 6, hi = (par[2 * q + 1] - cbase[2 * q + 1]) >> 6;  // state lanes
+      b[q] = __byte_perm(lo, hi, 0x6420u);
+    }
+    sts_v4(my_slot0, make_uint4(b[0], b[1], b[2], b[3]));
+  } else {
+    sts_v4(my_slot0, make_uint4(par[0], par[1], par[2], par[3]));
+  }
   int reg_slot = 0;  // slot whose contents are mirrored in par[]
 
-  const bool vec_store = full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
-                         ((col0 & 15) == 0);
+  // store mode: 0 = nothing to store (thread past the site range), 1 = 128-bit row stores, 2 = byte stores (ragged / unaligned)
+  int store_mode = !any ? 0
+                        : (full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) && ((col0 & 15) == 0)) ? 1 : 2;
+  asm volatile("" : "+r"(store_mode));
+  uint8_t *leaf_base = a.leaves + col0;
+  asm volatile("" : "+l"(leaf_base));
 
   for (int st = 0; st < fa.n_stages; ++st) {
     const int buf = st % nstage;
-    mbar_wait(smem_u32(&bars[buf]), (uint32_t)((st / nstage) & 1));
+#ifndef ELX_CTA_SYNC
+    if (tid == 0) topup(st);
+#endif
+    mbar_wait(smem_u32(&full_bar[buf]), (uint32_t)((st / nstage) & 1));
     const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
     const int nn = min(nps, a.N - st * nps);
     for (int k = 0; k < nn; ++k) {
+#ifndef ELX_CTA_SYNC
+      if (tid == 0 && k == (nn >> 1)) topup(st);
+#endif
       const uint4 rec = lds_v4(sbuf + (uint32_t)k * 16u);
       const uint32_t node = rec.x;
       const int src = (int)(int16_t)(rec.y & 0xffffu);
       const int dst = (int)(int16_t)(rec.y >> 16);
       const int leaf_row = (int)rec.z;
       if (src != reg_slot) {
+        const uint4 v = lds_v4(slot_base + (uint32_t)src * slot_stride);
+        if (AA) {
+          const uint32_t b[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int q = 0; q < NREG; q += 4) {
-          uint4 v = lds_v4(my_slot0 + (uint32_t)src * slot_stride + q * 4u);
-          par[q] = v.x; par[q + 1] = v.y; par[q + 2] = v.z; par[q + 3] = v.w;
+          for (int q = 0; q < 4; ++q) {  // state bytes -> 16-bit lanes -> row offsets (state*64 + comp*K*64)
+            par[2 * q] = __byte_perm(b[q], 0u, 0x4140u) * 64u + cbase[2 * q];
+            par[2 * q + 1] = __byte_perm(b[q], 0u, 0x4342u) * 64u + cbase[2 * q + 1];
+          }
+        } else {
+          par[0] = v.x; par[1] = v.y; par[2] = v.z; par[3] = v.w;
         }
         reg_slot = src;
       }
@@ -224,8 +300,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_tiled(FastArgs fa) {
           offA = __byte_perm(par[pr >> 1], 0u, 0x4440u | ((pr & 1) * 2));
           offB = __byte_perm(par[pr >> 1], 0u, 0x4440u | ((pr & 1) * 2 + 1));
         }
-        uint32_t aA = offA | (w[pr] & L::JMASK);
-        uint32_t aB = offB | ((w[pr] >> 16) & L::JMASK);
+        // entry address = row offset + 2*j (IMAD: the multiply-add runs on the FMA pipe, the ALU pipe is the bottleneck)
+        uint32_t aA = (w[pr] & L::JMASK) * 2u + offA;
+        uint32_t aB = ((w[pr] >> 16) & L::JMASK) * 2u + offB;
         uint32_t eA = lds_u16(tbl + aA);
         uint32_t eB = lds_u16(tbl + aB);
         uint32_t ee = __byte_perm(eA, eB, 0x5410u);
@@ -237,59 +314,86 @@ __global__ void __launch_bounds__(FAST_THREADS) k2_tiled(FastArgs fa) {
       uint32_t m23 = __vimin3_u16x2(t[3], t[4], t[5]);
       uint32_t m = __vimin3_u16x2(m01, m23, __vminu2(t[6], t[7]));
       if (((m & 0xffffu) < L::TIE) || ((m >> 16) < L::TIE)) {
-        // exact path (rare): redo the tied draws with the 32-bit refinement.  Fully unrolled with static indices
-        // so that the packed registers stay in registers on the fast path.
+        // exact path (rare): a draw tied in its threshold bits; resolve it with 32 more random bits.
+        // No calls and no arrays here: either would make ptxas spill / re-materialise state on the FAST path.
+        // The tied pairs are picked one by one out of the registers with a switch.
+        uint32_t mask = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t sh = (i & 1) * 16;
-          const uint32_t tl = (t[i >> 1] >> sh) & 0xffffu;
-          if (tl < L::TIE) {
-            const uint32_t x16 = (w[i >> 1] >> sh) & 0xffffu;
-            const uint32_t off = AA ? ((par[i >> 1] >> sh) & 0xffffu) : ((par[i >> 2] >> ((i & 3) * 8)) & 0xffu);
-            const uint32_t child = refine_draw<ROUNDS, AA>(a, tbl, off, x16, (uint64_t)sbase + i, node, key);
-            c2[i >> 1] = (c2[i >> 1] & ~(0xffffu << sh)) | ((child << 1) << sh);
+        for (int pr = 0; pr < 8; ++pr)
+          if (((t[pr] & 0xffffu) < L::TIE) || ((t[pr] >> 16) < L::TIE)) mask |= 1u << pr;
+        constexpr uint32_t KPm1 = (1u << L::A) - 1u;
+#pragma unroll 1
+        while (mask) {
+          const int pr = __ffs(mask) - 1;
+          mask &= mask - 1;
+          uint32_t tt = 0, ww = 0, cc = 0, oo = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q == pr) {
+              tt = t[q]; ww = w[q]; cc = c2[q];
+              oo = AA ? par[q] : (__byte_perm(par[q >> 1], 0u, 0x4440u | ((q & 1) * 2)) |
+                                  (__byte_perm(par[q >> 1], 0u, 0x4440u | ((q & 1) * 2 + 1)) << 16));
+            }
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t sh = (uint32_t)hh * 16u;
+            if (((tt >> sh) & 0xffffu) < L::TIE) {
+              const uint32_t x16 = (ww >> sh) & 0xffffu, off = (oo >> sh) & 0xffffu, j = x16 & KPm1;
+              const uint32_t e = lds_u16(tbl + off + 2u * j);
+              const uint64_t s = (uint64_t)sbase + 2 * pr + hh;
+              const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), node, TAG_REFINE), key);
+              // off / rowbytes = comp*K + state ; e16/qlo index = ((node*C + comp)*K + state)*KP + j
+              const uint32_t row = AA ? (off >> 6) : (off >> 3);
+              const int64_t idx = ((int64_t)node * (a.C * a.K) + row) * (KPm1 + 1) + j;
+              const uint32_t child = z.x < __ldg(a.qlo + idx) ? j : (e & KPm1);
+              cc = (cc & ~(0xffffu << sh)) | (child << sh);
+            }
           }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q == pr) c2[q] = cc;
         }
       }
-      if (dst >= 0) {
-        if (AA) {
+      if (AA) {
+        constexpr uint32_t SM = 0x1f1f1f1fu;
+        uint4 o;  // state bytes of the 16 sites: leaf output format = slot format
+        o.x = __byte_perm(c2[0], c2[1], 0x6420u) & SM;
+        o.y = __byte_perm(c2[2], c2[3], 0x6420u) & SM;
+        o.z = __byte_perm(c2[4], c2[5], 0x6420u) & SM;
+        o.w = __byte_perm(c2[6], c2[7], 0x6420u) & SM;
+        if (dst >= 0) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) par[q] = ((c2[q] & 0x003e003eu) << 5) + cbase[q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            par[q] = ((__byte_perm(c2[2 * q], c2[2 * q + 1], 0x6420u) & 0x06060606u) << 2) | cbase[q];
+          for (int q = 0; q < 8; ++q) par[q] = (c2[q] & 0x001f001fu) * 64u + cbase[q];
+          sts_v4(slot_base + (uint32_t)dst * slot_stride, o);
+          reg_slot = dst;
         }
+        if (leaf_row >= 0 && store_mode) store_leaf(a, leaf_base, leaf_row, col0, store_mode, o);
+      } else {
+        constexpr uint32_t SM = 0x03030303u;
+        uint32_t raw[4];  // state bytes of the 16 sites (leaf output format)
 #pragma unroll
-        for (int q = 0; q < NREG; q += 4)
-          sts_v4(my_slot0 + (uint32_t)dst * slot_stride + q * 4u, make_uint4(par[q], par[q + 1], par[q + 2], par[q + 3]));
-        reg_slot = dst;
-      }
-      if (leaf_row >= 0 && any) {
-        constexpr uint32_t SM = AA ? 0x1f1f1f1fu : 0x03030303u;
-        uint4 o;
-        o.x = (__byte_perm(c2[0], c2[1], 0x6420u) >> 1) & SM;
-        o.y = (__byte_perm(c2[2], c2[3], 0x6420u) >> 1) & SM;
-        o.z = (__byte_perm(c2[4], c2[5], 0x6420u) >> 1) & SM;
-        o.w = (__byte_perm(c2[6], c2[7], 0x6420u) >> 1) & SM;
-        uint8_t *dstp = a.leaves + (int64_t)leaf_row * a.leaves_pitch + col0;
-        if (vec_store) {
-          stg_cs_v4(dstp, o);
-        } else {
-          const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-          for (int i = 0; i < 16; ++i) {
-            int64_t col = col0 + i;
-            if (col >= 0 && col < a.nsites) dstp[i] = (uint8_t)(ow[i >> 2] >> ((i & 3) * 8));
-          }
+        for (int q = 0; q < 4; ++q) raw[q] = __byte_perm(c2[2 * q], c2[2 * q + 1], 0x6420u) & SM;
+        if (dst >= 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) par[q] = raw[q] * 8u + cbase[q];
+          sts_v4(slot_base + (uint32_t)dst * slot_stride, make_uint4(par[0], par[1], par[2], par[3]));
+          reg_slot = dst;
         }
+        if (leaf_row >= 0 && store_mode) store_leaf(a, leaf_base, leaf_row, col0, store_mode, make_uint4(raw[0], raw[1], raw[2], raw[3]));
       }
     }
-    __syncthreads();  // every warp is done with this stage buffer
+    // this warp is done with the stage buffer: hand it back to the producer
+#ifdef ELX_CTA_SYNC
+    __syncthreads();
     if (tid == 0 && st + nstage < fa.n_stages) {
       fence_async_smem();
-      mbar_expect_tx(smem_u32(&bars[buf]), (uint32_t)fa.stage_bytes);
-      tma_bulk_g2s(sbuf, fa.ftab + (size_t)(st + nstage) * fa.stage_bytes, (uint32_t)fa.stage_bytes, smem_u32(&bars[buf]));
+      mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
+      tma_bulk_g2s(sbuf, fa.ftab + (size_t)(st + nstage) * fa.stage_bytes, (uint32_t)fa.stage_bytes, smem_u32(&full_bar[buf]));
     }
+#else
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[buf]));
+#endif
   }
 }
 
@@ -323,7 +427,7 @@ int fast_tables_build(elx_handle *h) {
   if (h->K == 4 && h->KP == 4 && h->C <= 8) {
     kind = 1; tb = h->C * 32; slot_bytes = 16;
   } else if (h->KP == 32 && (int64_t)h->C * h->K * 64 <= 65535) {
-    kind = 2; tb = h->C * h->K * 64; slot_bytes = 32;
+    kind = 2; tb = h->C * h->K * 64; slot_bytes = 16;
   }
   if (kind) {
     // stage geometry: about 24 KB per stage, 3 stages; shrink to 2 stages / 1 node when the tables are big
@@ -370,7 +474,7 @@ template <int ROUNDS, bool AA>
 static cudaError_t launch_tiled(const FastArgs &fa, unsigned blocks, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(k2_tiled<ROUNDS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k2_tiled<ROUNDS, AA><<<blocks, FAST_THREADS, smem, stream>>>(fa);
+  k2_tiled<ROUNDS, AA><<<blocks, FAST_CTA, smem, stream>>>(fa);
   return cudaGetLastError();
 }
 

@@ -11,8 +11,8 @@
  *                         c = first i with cumw[i] >= cumw[C-1]*u      (mwc-random categorical)
  *   root state:           x = philox(site lo, site hi, 0, 3); same rule on cumpi[c]
  *   node n, site s:       x = philox(s>>3 lo, s>>3 hi, n, 0); x16 = 16-bit field (s & 7), low half of word (s&7)>>1 first
- *                         j = (x16 >> 1) & (KP-1); r = x16 >> (A+1); e = e16[n][c][parent][j]
- *                         r < e>>(A+1) -> j ;  r > e>>(A+1) -> alias = (e>>1)&(KP-1) ;
+ *                         j = x16 & (KP-1); r = x16 >> A; e = e16[n][c][parent][j]
+ *                         r < e>>A -> j ;  r > e>>A -> alias = e & (KP-1) ;
  *                         tie -> y = philox(s lo, s hi, n, 1).x0 ;  y < qlo[n][c][parent][j] ? j : alias
  */
 #include <stdint.h>
@@ -70,11 +70,11 @@ int spec_freerun(int N, int K, int C, int is_mixture, int A, int rounds, const i
       philox(rounds, y, k0, k1);
       int f = (int)(s & 7);
       uint32_t x16 = (y[f >> 1] >> ((f & 1) * 16)) & 0xffffu;
-      int j = (x16 >> 1) & (KP - 1);
-      uint32_t r = x16 >> (A + 1);
+      int j = x16 & (KP - 1);
+      uint32_t r = x16 >> A;
       int64_t idx = (((int64_t)n * C + c) * K + par) * KP + j;
-      uint32_t e = e16[idx], qh = e >> (A + 1);
-      int al = (e >> 1) & (KP - 1), child;
+      uint32_t e = e16[idx], qh = e >> A;
+      int al = e & (KP - 1), child;
       if (r < qh) child = j;
       else if (r > qh) child = al;
       else {

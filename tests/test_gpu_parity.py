@@ -142,13 +142,13 @@ def test_injected_bad_weights_is_an_error():
 # K2 free-running mode
 # ---------------------------------------------------------------------------------------------
 def check_alias_tables(p, e16, qlo, k):
-    """The alias tables encode integer masses m_i with sum 2^47 and m_i / 2^47 == p_i / sum(p) within 2^-45."""
+    """The alias tables encode integer masses m_i with sum 2^48 and m_i / 2^48 == p_i / sum(p) within 2^-45."""
     a = spec.alias_bits(k)
     kp = 1 << a
-    cap = 1 << (47 - a)
+    cap = 1 << (48 - a)
     e = e16.astype(np.int64)
-    qh = e >> (a + 1)
-    al = (e >> 1) & (kp - 1)
+    qh = e >> a
+    al = e & (kp - 1)
     q = (qh << 32) | qlo.astype(np.int64)
     self_col = al == np.arange(kp)
     q = np.where(self_col, cap, q)  # alias == self means "always accept"
@@ -156,10 +156,10 @@ def check_alias_tables(p, e16, qlo, k):
     for j in range(kp):
         mass[..., j] += q[..., j]
         np.put_along_axis(mass, al[..., j:j + 1], np.take_along_axis(mass, al[..., j:j + 1], -1) + (cap - q[..., j:j + 1]), -1)
-    assert np.all(mass.sum(-1) == 1 << 47)
+    assert np.all(mass.sum(-1) == 1 << 48)
     assert np.all(mass[..., k:] == 0)
     pn = p / p.sum(-1, keepdims=True)
-    assert np.max(np.abs(mass[..., :k] / float(1 << 47) - pn)) < 2.0 ** -44
+    assert np.max(np.abs(mass[..., :k] / float(1 << 48) - pn)) < 2.0 ** -44
 
 
 @pytest.mark.parametrize("name,tree_file,s", [("jc", "Newick.tree", 10000), ("hky_g4", "Newick.tree", 5000),
