@@ -1,0 +1,138 @@
+"""`python -m elynx_b200.cli simulate ...` -- thin native driver with the `slynx simulate` surface.
+
+Mirrors slynx/src/SLynx/Simulate/Options.hs:65-204 (arguments) and Simulate.hs:239-306 (simulateCmd): reads a Newick
+tree, assembles the phylogenetic model from the model string (+ EDM / site-profile files, weights, gamma rate
+heterogeneity), simulates the alignment on the GPU and writes `<base>.fasta` (and `<base>.sitedists` for mixture
+models, PAML order, Simulate.hs:79-89).  Out of scope: `.elynx` reproduction files,
+`.model.gz`, the ELynx logger; a GPU counter-based stream replaces SplitMix, so the bytes differ from the Haskell
+binary for the same seed."""
+from __future__ import annotations
+
+import argparse
+import gzip
+import re
+import sys
+import time
+
+import numpy as np
+
+from . import model as pm
+from .simulate import Simulator
+
+AA_PAML_ORDER = "ARNDCQEGHILKMFPSTWYV"  # AminoAcid.hs:74-99
+
+
+def _parse_weights(s):
+    """`-w "[0.9,0.05,...]"` (Options.hs mixture-model-weights: a Haskell list literal)"""
+    s = s.strip()
+    if not (s.startswith("[") and s.endswith("]")):
+        raise SystemExit("mixture weights must look like [w1,w2,...]")
+    return [float(x) for x in s[1:-1].split(",")]
+
+
+def _parse_gamma(s):
+    """`-g "(4,0.5)"` (Options.hs gamma-rate-heterogeneity: (number of categories, alpha))"""
+    m = re.fullmatch(r"\(\s*(\d+)\s*,\s*([0-9.eE+-]+)\s*\)", s.strip())
+    if not m:
+        raise SystemExit("gamma rate heterogeneity must look like (n,alpha)")
+    return int(m.group(1)), float(m.group(2))
+
+
+def _parse_seed(s):
+    """`-S [0]` / `-S 0`: the reference takes an Int since random-1.2"""
+    return int(s.strip().strip("[]").split(",")[0])
+
+
+def double_dec(x: float) -> str:
+    """ByteString.Builder.doubleDec = Haskell `show`: shortest round-trip digits, scientific outside [0.1, 10^7)."""
+    if x == 0:
+        return "0.0"
+    r = repr(abs(float(x)))
+    sign = "-" if x < 0 else ""
+    mant, ex = (r.lower().split("e") + ["0"])[:2]
+    ex = int(ex)
+    ip, fp = (mant.split(".") + [""])[:2]
+    digits = (ip + fp).lstrip("0")
+    lead = len(ip.lstrip("0"))
+    e10 = (lead - 1 + ex) if lead else (-(len(fp) - len(fp.lstrip("0"))) - 1 + ex)
+    digits = digits.rstrip("0") or "0"
+    if 0.1 <= abs(x) < 1e7:
+        if e10 >= 0:
+            return sign + digits[: e10 + 1].ljust(e10 + 1, "0") + "." + (digits[e10 + 1:] or "0")
+        return sign + "0." + "0" * (-e10 - 1) + digits
+    return sign + digits[0] + "." + (digits[1:] or "0") + "e" + str(e10)
+
+
+def site_dists(comps, model) -> bytes:
+    """writeSiteDists (Simulate.hs:79-89): `i pi...` per site, 1-based, component pi in PAML order."""
+    alpha = "ACDEFGHIKLMNPQRSTVWY"
+    if model.alphabet == pm.PROTEIN:
+        perm = [alpha.index(c) for c in AA_PAML_ORDER]
+    else:
+        raise SystemExit("site distributions are written in PAML order and only make sense for protein models")
+    rows = [" ".join(double_dec(v) for v in model.pi[c][perm]) for c in range(model.n_components)]
+    return "\n".join("%d %s" % (i + 1, rows[c]) for i, c in enumerate(comps)).encode()
+
+
+def simulate_cmd(args) -> int:
+    t0 = time.time()
+    log = (lambda *a: None) if args.verbosity == "Quiet" else (lambda *a: print(*a, file=sys.stderr))
+    log("Read tree from file '%s'." % args.tree_file)
+    tree = pm.parse_newick(open(args.tree_file).read())
+    log("Number of leaves: %d" % tree.n_leaves)
+    if args.edm_file and args.siteprofile_files:
+        raise SystemExit("Got both: --edm-file and --siteprofile-files.")
+    comps = None
+    if args.edm_file:
+        comps = pm.parse_edm_phylobayes(open(args.edm_file).read())
+    if args.siteprofile_files:
+        comps = sum((pm.parse_siteprofiles_phylobayes(open(f).read()) for f in args.siteprofile_files), [])
+    if comps is not None:
+        log("Empiricial distribution mixture model with %d components." % len(comps))
+    model = pm.get_phylo_model(args.substitution_model, args.mixture_model, args.global_normalization,
+                               _parse_weights(args.mixture_model_weights) if args.mixture_model_weights else None, comps,
+                               _parse_gamma(args.gamma_rate_heterogeneity) if args.gamma_rate_heterogeneity else None)
+    log("%s model '%s': %d states, %d component(s)." % (model.alphabet, model.name, model.n_states, model.n_components))
+    log("Simulate alignment.")
+    log("Length: %d." % args.length)
+    seed = _parse_seed(args.seed) if args.seed is not None else int(time.time_ns() & (2 ** 63 - 1))
+    with Simulator(model.weights if model.is_mixture else None, model.pi, model.exch, tree, is_mixture=model.is_mixture,
+                   device=args.device) as sim:
+        fasta, cs = sim.simulate_fasta(seed, args.length, tree.leaf_names(), model.alphabet_chars, want_comps=model.is_mixture)
+    if args.output_file_basename:
+        fn = args.output_file_basename + ".fasta"
+        (gzip.open if fn.endswith(".gz") else open)(fn, "wb").write(fasta)
+        log("Wrote simulated multi sequence alignment to '%s'." % fn)
+        if model.is_mixture and model.alphabet == pm.PROTEIN:
+            open(args.output_file_basename + ".sitedists", "wb").write(site_dists(cs, model))
+    else:
+        sys.stdout.buffer.write(fasta)
+    log("Done in %.2f s." % (time.time() - t0))
+    return 0
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="slynx-b200", description="B200-native `slynx simulate` (alignment simulation on the GPU)")
+    ap.add_argument("-v", "--verbosity", default="Info", choices=["Quiet", "Warn", "Info", "Debug"])
+    ap.add_argument("-o", "--output-file-basename")
+    ap.add_argument("-f", "--force", action="store_true", help="accepted for compatibility (outputs are always overwritten)")
+    ap.add_argument("--no-elynx-file", action="store_true", help="accepted for compatibility (no .elynx file is written)")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    s = sub.add_parser("simulate", help="Simulate multi sequence alignments (slynx/src/SLynx/Simulate/Options.hs)")
+    s.add_argument("-t", "--tree-file", required=True)
+    s.add_argument("-s", "--substitution-model")
+    s.add_argument("-m", "--mixture-model")
+    s.add_argument("-e", "--edm-file")
+    s.add_argument("-p", "--siteprofile-files", nargs="+")
+    s.add_argument("-w", "--mixture-model-weights")
+    s.add_argument("-n", "--global-normalization", action="store_true")
+    s.add_argument("-g", "--gamma-rate-heterogeneity")
+    s.add_argument("-l", "--length", type=int, required=True)
+    s.add_argument("-S", "--seed")
+    s.add_argument("--device", type=int, default=-1)
+    args = ap.parse_args(argv)
+    return simulate_cmd(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

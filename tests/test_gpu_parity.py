@@ -320,3 +320,78 @@ def test_histograms_device():
         assert np.array_equal(sc[t], np.bincount(leaves[t], minlength=4))
     idx = ((leaves[0].astype(np.int64) * 4 + leaves[1]) * 4 + leaves[2]) * 4 + leaves[3]
     assert np.array_equal(pc, np.bincount(idx, minlength=256))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size runs checked through size-independent properties
+# ---------------------------------------------------------------------------------------------
+def _device_run(sim, seed, site0, n, t, torch):
+    pitch = (n + 127) // 128 * 128
+    buf = torch.empty((t, pitch), dtype=torch.uint8, device="cuda")
+    sim.simulate_device(seed, site0, n, buf.data_ptr(), pitch)
+    return buf, pitch
+
+
+@pytest.mark.parametrize("spec_str,gamma,taxa,sites", [("HKY[6.0]{0.2,0.3,0.3,0.2}", (4, 0.5), 1000, 10_000_000),
+                                                       ("LG", (4, 0.5), 1000, 2_000_000)])
+def test_full_size_stationarity_and_partition_checksums(spec_str, gamma, taxa, sites):
+    """BASELINE configs 2/3 at (near) full size on the device: (1) the process is stationary, so every taxon's state
+    frequencies must match pi (chi-square per taxon, device histograms); (2) checksum of checksums: the state-count
+    histogram of the whole run equals the sum over an uneven 3-way split of the site range (pure function of
+    (seed, site, node))."""
+    torch = pytest.importorskip("torch")
+    from scipy import stats
+    from elynx_b200 import model as pm
+
+    tree = pm.birth_death_tree(taxa, 1.0, 0.5, seed=1)
+    model = pm.get_phylo_model(spec_str, gamma=gamma)
+    k = model.n_states
+    with eb.Simulator(model.weights, model.pi, model.exch, tree, is_mixture=True) as sim:
+        stream = torch.cuda.ExternalStream(sim.stream)
+        buf, pitch = _device_run(sim, 5, 0, sites, taxa, torch)
+        whole = torch.zeros((taxa, k), dtype=torch.int64, device="cuda")
+        sim.histogram_device(buf.data_ptr(), pitch, sites, whole.data_ptr())
+        stream.synchronize()
+        whole = whole.cpu().numpy()
+        del buf
+        parts = np.zeros_like(whole)
+        cuts = [0, 16 * 1001, sites // 3 + 5, sites]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            pbuf, ppitch = _device_run(sim, 5, a, b - a, taxa, torch)
+            h = torch.zeros((taxa, k), dtype=torch.int64, device="cuda")
+            sim.histogram_device(pbuf.data_ptr(), ppitch, b - a, h.data_ptr())
+            stream.synchronize()
+            parts += h.cpu().numpy()
+            del pbuf
+    assert np.array_equal(whole, parts)
+    assert np.all(whole.sum(1) == sites)
+    pi = model.pi[0]  # gamma categories share pi
+    pvals = np.array([stats.chisquare(whole[t], pi * sites).pvalue for t in range(taxa)])
+    # 1000 independent-ish tests: no catastrophic p-value, and the p-values are not piled up near zero
+    assert pvals.min() > 1e-7, pvals.min()
+    assert (pvals < 0.01).mean() < 0.05
+
+
+def test_cli_slynx_test_matrix(tmp_path, ref_data):
+    """scripts/slynx-test:25-50: the model spellings the reference's smoke script runs must parse and run."""
+    import os
+
+    from elynx_b200 import cli
+
+    tree = os.path.join(ref_data, "Newick.tree")
+    edm = os.path.join(ref_data, "EDMDistsPhylobayes.txt")
+    prof = os.path.join(ref_data, "HSSPMany.siteprofiles")
+    cases = [["-s", "HKY[6.0]{0.2,0.3,0.3,0.2}"], ["-s", "GTR4[1,2,3,4,5,6]{0.2,0.3,0.4,0.1}"], ["-e", edm, "-m", "EDM(LG-Custom)"],
+             ["-e", edm, "-m", "EDM(LG-Custom)", "-w", "[0.9,0.05,0.03,0.02]"], ["-m", "C20", "-n"],
+             ["-g", "(4,0.2)", "-s", "HKY[6.0]{0.2,0.3,0.3,0.2}"], ["-m", "C10", "-n", "-g", "(4,0.2)"],
+             ["-m", "MIXTURE(JC,HKY[6.0]{0.25,0.25,0.25,0.25})", "-w", "[0.4,0.6]"], ["-m", "EDM(Poisson-Custom)", "-p", prof]]
+    for i, c in enumerate(cases):
+        base = str(tmp_path / ("out%d" % i))
+        assert cli.main(["-v", "Quiet", "-o", base, "simulate", "-t", tree] + c + ["-l", "1000", "-S", "[0]"]) == 0
+        lines = open(base + ".fasta", "rb").read().split(b"\n")
+        assert len(lines) == 81 and lines[-1] == b"" and lines[0] == b">Aeropyrum0"
+        assert all(len(l) == 1000 for l in lines[1::2][:40])
+        alphabet = b"ACGT" if ("HKY" in " ".join(c) or "GTR4" in " ".join(c) or "JC" in " ".join(c)) else b"ACDEFGHIKLMNPQRSTVWY"
+        assert set(b"".join(lines[1::2])) <= set(alphabet)
+    sd = open(str(tmp_path / "out2") + ".sitedists").read().split("\n")
+    assert len(sd) == 1000 and sd[0].startswith("1 ") and len(sd[0].split()) == 21
