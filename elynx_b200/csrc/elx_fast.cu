@@ -4,8 +4,8 @@
 // the machine:
 //   * one thread owns 16 consecutive sites (two Philox4x32 calls per node = 16 x 16-bit draws) and writes each leaf
 //     row with one 128-bit streaming store (a warp covers 512 contiguous bytes of the [taxon][site] row);
-//   * the per-branch alias tables and the walk records are streamed through shared memory in stages of NPS nodes
-//     by TMA bulk copies (cp.async.bulk + mbarrier, 3 stages in flight);
+//   * the per-branch alias tables and the walk records are streamed through shared memory in stages of `nps` nodes
+//     by TMA bulk copies (cp.async.bulk + mbarrier, up to 3 stages in flight; one CTA barrier per stage retires a buffer);
 //   * live internal-node states sit in a shared-memory slot stack [slot][thread] (128-bit, conflict free); the
 //     walk order (heavy child last) bounds the number of slots by floor(log2 N)+1;
 //   * a draw is: PRMT (parent offset) + LOP3 (address) + LDS.U16 + half a PRMT/VIMNMX.U16x2/LOP3 -- the alias
@@ -26,7 +26,7 @@
 namespace elx {
 
 constexpr int MAX_NSTAGE = 3;       // TMA stages in flight
-constexpr int FAST_THREADS = 128;    // threads per CTA (4 warps); lane 0 of warp 0 doubles as the TMA producer
+constexpr int FAST_THREADS = 128;    // threads per CTA (4 warps); thread 0 also issues the TMA refills
 constexpr int FAST_CTA = FAST_THREADS;
 
 struct FastTables {
@@ -135,17 +135,20 @@ struct Lay {
 // to the generic kernel).  Out of line: it runs 16 times per thread in the prologue and must not inflate the
 // register budget of the node loop.  Returns comp | root << 16.
 template <int ROUNDS>
-__device__ __noinline__ uint32_t draw_comp_root(const SimArgs &a, uint64_t s, uint32_t k0, uint32_t k1) {
+__device__ __noinline__ uint32_t draw_comp_root(const double *__restrict__ cumw, const double *__restrict__ cumpi, int C, int K,
+                                                int N, int is_mixture, int *error_flag, uint64_t s, uint32_t k0, uint32_t k1) {
+  // scalars by value: taking the address of the kernel parameter block would move it to local memory and turn every
+  // later read of a launch constant into a per-thread (non-uniform) load
   const uint2 key = make_uint2(k0, k1);
   int c = 0;
-  if (a.is_mixture) {
+  if (is_mixture) {
     uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_COMP), key);
-    c = cat_cum(a.cumw, a.C, u53_positive(x.x, x.y));
-    if (c < 0) { atomicExch(a.error_flag, a.N + 1); c = 0; }
+    c = cat_cum(cumw, C, u53_positive(x.x, x.y));
+    if (c < 0) { atomicExch(error_flag, N + 1); c = 0; }
   }
   uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), 0u, TAG_ROOT), key);
-  int root = cat_cum(a.cumpi + c * a.K, a.K, u53_positive(x.x, x.y));
-  if (root < 0) { atomicExch(a.error_flag, a.N + 2); root = 0; }
+  int root = cat_cum(cumpi + c * K, K, u53_positive(x.x, x.y));
+  if (root < 0) { atomicExch(error_flag, N + 2); root = 0; }
   return (uint32_t)c | ((uint32_t)root << 16);
 }
 
@@ -160,43 +163,30 @@ __global__ void __launch_bounds__(FAST_CTA, ELX_MIN_CTAS) k2_tiled(FastArgs fa) 
   const SimArgs &a = fa.s;
   const int tid = threadIdx.x;
   const int nstage = fa.nstage, nps = fa.nps;
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);        // [nstage] TMA bytes have landed
-  uint64_t *empty_bar = reinterpret_cast<uint64_t *>(smem) + 4;   // [nstage] all consumer warps are done with the buffer
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);  // [nstage] mbarriers: the stage's TMA bytes have landed
   const uint32_t stage_smem = smem_u32(smem + 128);
   const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
   const uint32_t my_slot0 = slots_smem + (uint32_t)tid * 16u;  // slot stack [slot][thread] x 16 B
   const uint32_t slot_stride = FAST_THREADS * 16u;
 
   if (tid == 0) {
-    for (int i = 0; i < nstage; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), FAST_THREADS / 32);
-    }
+    for (int i = 0; i < nstage; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  __syncthreads();  // the only CTA-wide barrier: roles split below
+  __syncthreads();
 
-  // ---- in-band TMA producer (thread 0): streams [walk records | alias tables] stage by stage into the ring.
-  // Buffers are released per warp (empty_bar, count = #warps), so no CTA-wide barrier is needed; thread 0 tops the
-  // ring up whenever a buffer is free and only blocks when it needs a stage that has not been issued yet.
-  int next_fill = 0;
-  auto topup = [&](int st) {
-    while (next_fill < fa.n_stages && next_fill < st + nstage) {
-      const int buf = next_fill % nstage, use = next_fill / nstage;
-      if (use > 0) {
-        const uint32_t par = (uint32_t)((use - 1) & 1);
-        if (next_fill <= st) mbar_wait(smem_u32(&empty_bar[buf]), par);
-        else if (!mbar_test(smem_u32(&empty_bar[buf]), par)) break;
-      }
-      fence_async_smem();
-      mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
-      tma_bulk_g2s(stage_smem + (uint32_t)(buf * fa.stage_bytes), fa.ftab + (size_t)next_fill * fa.stage_bytes,
-                   (uint32_t)fa.stage_bytes, smem_u32(&full_bar[buf]));
-      ++next_fill;
+  // Fill the ring: stages 0..nstage-1.  Refills happen at the end of each stage, after the CTA barrier that
+  // retires the buffer, in straight-line code.  (Measured: per-warp release with an in-band producer loop was no
+  // faster, and any data-dependent loop under `tid == 0` makes ptxas drop uniform-register addressing for the whole
+  // node loop, which costs one extra ALU-pipe IADD3 per draw.)
+  if (tid == 0) {
+    for (int i = 0; i < nstage && i < fa.n_stages; ++i) {
+      mbar_expect_tx(smem_u32(&full_bar[i]), (uint32_t)fa.stage_bytes);
+      tma_bulk_g2s(stage_smem + (uint32_t)(i * fa.stage_bytes), fa.ftab + (size_t)i * fa.stage_bytes, (uint32_t)fa.stage_bytes,
+                   smem_u32(&full_bar[i]));
     }
-  };
-  if (tid == 0) topup(0);  // fills the whole ring: stages 0..nstage-1
+  }
 
   // 16 sites per thread, aligned on global site index multiples of 16
   const int64_t g16 = (a.site0 >> 4) + (int64_t)blockIdx.x * FAST_THREADS + tid;
@@ -214,7 +204,7 @@ __global__ void __launch_bounds__(FAST_CTA, ELX_MIN_CTAS) k2_tiled(FastArgs fa) 
   for (int q = 0; q < NREG; ++q) { cbase[q] = 0; par[q] = 0; }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const uint32_t cr = draw_comp_root<ROUNDS>(a, (uint64_t)sbase + i, key.x, key.y);
+    const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag, (uint64_t)sbase + i, key.x, key.y);
     const int c = (int)(cr & 0xffffu), root = (int)(cr >> 16);
     if (AA) {
       cbase[i >> 1] |= (uint32_t)(c * a.K * 64) << (16 * (i & 1));
@@ -254,18 +244,15 @@ __global__ void __launch_bounds__(FAST_CTA, ELX_MIN_CTAS) k2_tiled(FastArgs fa) 
   uint8_t *leaf_base = a.leaves + col0;
   asm volatile("" : "+l"(leaf_base));
 
+  // ring position kept incrementally (a runtime % / would run on the vector pipes and make every shared-memory
+  // address below non-uniform)
+  int buf = 0;
+  uint32_t phase = 0;
   for (int st = 0; st < fa.n_stages; ++st) {
-    const int buf = st % nstage;
-#ifndef ELX_CTA_SYNC
-    if (tid == 0) topup(st);
-#endif
-    mbar_wait(smem_u32(&full_bar[buf]), (uint32_t)((st / nstage) & 1));
+    mbar_wait(smem_u32(&full_bar[buf]), phase);
     const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
     const int nn = min(nps, a.N - st * nps);
     for (int k = 0; k < nn; ++k) {
-#ifndef ELX_CTA_SYNC
-      if (tid == 0 && k == (nn >> 1)) topup(st);
-#endif
       const uint4 rec = lds_v4(sbuf + (uint32_t)k * 16u);
       const uint32_t node = rec.x;
       const int src = (int)(int16_t)(rec.y & 0xffffu);
@@ -300,9 +287,10 @@ __global__ void __launch_bounds__(FAST_CTA, ELX_MIN_CTAS) k2_tiled(FastArgs fa) 
           offA = __byte_perm(par[pr >> 1], 0u, 0x4440u | ((pr & 1) * 2));
           offB = __byte_perm(par[pr >> 1], 0u, 0x4440u | ((pr & 1) * 2 + 1));
         }
-        // entry address = row offset + 2*j (IMAD: the multiply-add runs on the FMA pipe, the ALU pipe is the bottleneck)
-        uint32_t aA = (w[pr] & L::JMASK) * 2u + offA;
-        uint32_t aB = ((w[pr] >> 16) & L::JMASK) * 2u + offB;
+        // entry address = row offset | 2*j.  Written as an OR: with an ADD ptxas folds the (warp-uniform) table base into a
+        // 3-input IADD3 per draw instead of using [R + UR] addressing.
+        uint32_t aA = ((w[pr] & L::JMASK) << 1) | offA;
+        uint32_t aB = (((w[pr] >> 16) & L::JMASK) << 1) | offB;
         uint32_t eA = lds_u16(tbl + aA);
         uint32_t eB = lds_u16(tbl + aB);
         uint32_t ee = __byte_perm(eA, eB, 0x5410u);
@@ -383,17 +371,13 @@ __global__ void __launch_bounds__(FAST_CTA, ELX_MIN_CTAS) k2_tiled(FastArgs fa) 
       }
     }
     // this warp is done with the stage buffer: hand it back to the producer
-#ifdef ELX_CTA_SYNC
-    __syncthreads();
+    __syncthreads();  // every warp is done with this stage buffer
     if (tid == 0 && st + nstage < fa.n_stages) {
       fence_async_smem();
       mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
       tma_bulk_g2s(sbuf, fa.ftab + (size_t)(st + nstage) * fa.stage_bytes, (uint32_t)fa.stage_bytes, smem_u32(&full_bar[buf]));
     }
-#else
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[buf]));
-#endif
+    if (++buf == nstage) { buf = 0; phase ^= 1u; }
   }
 }
 
@@ -430,15 +414,18 @@ int fast_tables_build(elx_handle *h) {
     kind = 2; tb = h->C * h->K * 64; slot_bytes = 16;
   }
   if (kind) {
-    // stage geometry: about 24 KB per stage, 3 stages; shrink to 2 stages / 1 node when the tables are big
+    // stage geometry: keep a CTA under ~44 KB of shared memory so that 5 CTAs (20 warps) fit an SM; small tables
+    // (DNA) stream 3 stages of up to 64 nodes, bigger ones 2 stages of a few nodes; tables that do not fit that
+    // budget fall back to 2 stages x 1 node with fewer CTAs per SM, and to the generic kernel beyond 200 KB.
     const size_t slots = (size_t)h->n_slots * FAST_THREADS * slot_bytes;
-    int nps = (24 * 1024) / (16 + tb);
+    const size_t per_node = 16 + (size_t)tb;
+    int nstage = tb <= 1024 ? MAX_NSTAGE : 2;
+    const size_t budget = 44 * 1024;
+    int nps = budget > slots + 128 ? (int)((budget - slots - 128) / nstage / per_node) : 0;
     if (nps > 64) nps = 64;
-    if (nps < 1) nps = 1;
-    int nstage = MAX_NSTAGE;
-    size_t smem = 128 + (size_t)nstage * nps * (16 + tb) + slots;
-    if (smem > 100 * 1024 && nps == 1) { nstage = 2; smem = 128 + (size_t)nstage * (16 + tb) + slots; }
-    if (smem > 220 * 1024) kind = 0;
+    if (nps < 1) { nps = 1; nstage = 2; }
+    size_t smem = 128 + (size_t)nstage * nps * per_node + slots;
+    if (smem > 200 * 1024) kind = 0;
     ft->nps = nps; ft->nstage = nstage; ft->smem = smem;
   }
   ft->kind = kind;
