@@ -123,6 +123,13 @@ __device__ __forceinline__ void store_leaf(const SimArgs &a, uint8_t *leaf_base,
   }
 }
 
+// w >> 15 computed as the high word of w * 2^17: a multiply runs on the FMA pipe, a shift on the (binding) ALU pipe.
+__device__ __forceinline__ uint32_t hi15(uint32_t w) {
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, 131072;" : "=r"(r) : "r"(w));
+  return r;
+}
+
 template <bool AA>
 struct Lay {
   static constexpr int NREG = AA ? 8 : 4;            // packed parent registers per thread (16 sites)
