@@ -15,6 +15,7 @@
 // DNA kernel: K = 4, KP = 4, C <= 8.  Per-site state byte = comp*32 + state*8 = byte offset of the table row.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include <cuda_runtime.h>
@@ -427,7 +428,8 @@ int fast_tables_build(elx_handle *h) {
     const size_t slots = (size_t)h->n_slots * FAST_THREADS * slot_bytes;
     const size_t per_node = 16 + (size_t)tb;
     int nstage = tb <= 1024 ? MAX_NSTAGE : 2;
-    const size_t budget = 44 * 1024;
+    size_t budget = 44 * 1024;
+    if (const char *e = getenv("ELX_SMEM_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;  // tuning knob
     int nps = budget > slots + 128 ? (int)((budget - slots - 128) / nstage / per_node) : 0;
     if (nps > 64) nps = 64;
     if (nps < 1) { nps = 1; nstage = 2; }
