@@ -164,7 +164,8 @@ def check_alias_tables(p, e16, qlo, k):
 
 @pytest.mark.parametrize("name,tree_file,s", [("jc", "Newick.tree", 10000), ("hky_g4", "Newick.tree", 5000),
                                              ("lg_g4", "UltraMetric.tree", 3000), ("c10", "UltraMetric.tree", 2000),
-                                             ("mixture_dna", "Newick.tree", 2000)])
+                                             ("mixture_dna", "Newick.tree", 2000), ("c60", "UltraMetric.tree", 9000),
+                                             ("c60", "Newick.tree", 1000)])
 @pytest.mark.parametrize("force_generic", [True, False])
 def test_freerun_matches_spec(name, tree_file, s, force_generic):
     model = model_case(name)
