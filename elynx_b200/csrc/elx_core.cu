@@ -624,35 +624,60 @@ static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int
   if (rc) return rc;
   if (nsites == 0) return 0;
   CUDA_TRY(h, cudaSetDevice(h->device));
-  // bounded batches keep the staging buffers small; column pitch of the staging buffers = batch size
+  // Site batches through two device staging sets: the kernels of batch b+1 (compute stream) overlap the device-to-host
+  // copies of batch b (copy stream).  The result path is PCIe-bound: 1 byte per cell has to cross to the host.
   const int64_t BATCH = 1 << 20;
-  uint8_t *d_leaves = nullptr, *d_internal = nullptr;
-  int32_t *d_comps = nullptr;
-  double *d_U = nullptr;
+  const int NB = 2;
+  uint8_t *d_leaves[NB] = {nullptr, nullptr}, *d_internal[NB] = {nullptr, nullptr};
+  int32_t *d_comps[NB] = {nullptr, nullptr};
+  double *d_U[NB] = {nullptr, nullptr};
+  cudaEvent_t sim_done[NB] = {nullptr, nullptr}, copy_done[NB] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
   int64_t bmax = nsites < BATCH ? nsites : BATCH;
   int64_t bpitch = (bmax + 15) & ~(int64_t)15;
   int urows = h->N + (h->is_mixture ? 2 : 1);
-  auto cleanup = [&]() { cudaFree(d_leaves); cudaFree(d_internal); cudaFree(d_comps); cudaFree(d_U); };
+  const int nbuf = nsites > BATCH ? NB : 1;
+  auto cleanup = [&]() {
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < NB; ++i) {
+      cudaFree(d_leaves[i]); cudaFree(d_internal[i]); cudaFree(d_comps[i]); cudaFree(d_U[i]);
+      if (sim_done[i]) cudaEventDestroy(sim_done[i]);
+      if (copy_done[i]) cudaEventDestroy(copy_done[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  };
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
-  CT(cudaMalloc((void **)&d_leaves, (size_t)h->T * bpitch));
-  if (internal) CT(cudaMalloc((void **)&d_internal, (size_t)h->N * bpitch));
-  if (comps) CT(cudaMalloc((void **)&d_comps, sizeof(int32_t) * (size_t)bpitch));
-  if (injected) CT(cudaMalloc((void **)&d_U, sizeof(double) * (size_t)urows * bpitch));
-  for (int64_t b0 = 0; b0 < nsites; b0 += BATCH) {
+  CT(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < nbuf; ++i) {
+    CT(cudaMalloc((void **)&d_leaves[i], (size_t)h->T * bpitch));
+    if (internal) CT(cudaMalloc((void **)&d_internal[i], (size_t)h->N * bpitch));
+    if (comps) CT(cudaMalloc((void **)&d_comps[i], sizeof(int32_t) * (size_t)bpitch));
+    if (injected) CT(cudaMalloc((void **)&d_U[i], sizeof(double) * (size_t)urows * bpitch));
+    CT(cudaEventCreateWithFlags(&sim_done[i], cudaEventDisableTiming));
+    CT(cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming));
+  }
+  int64_t batch = 0;
+  for (int64_t b0 = 0; b0 < nsites; b0 += BATCH, ++batch) {
+    const int i = (int)(batch % nbuf);
     int64_t nb = nsites - b0 < BATCH ? nsites - b0 : BATCH;
+    if (batch >= nbuf) CT(cudaStreamWaitEvent(h->stream, copy_done[i], 0));  // staging set i is free again
     if (injected) {
-      CT(cudaMemcpy2DAsync(d_U, sizeof(double) * bpitch, U + b0, sizeof(double) * u_pitch, sizeof(double) * nb, urows,
+      CT(cudaMemcpy2DAsync(d_U[i], sizeof(double) * bpitch, U + b0, sizeof(double) * u_pitch, sizeof(double) * nb, urows,
                            cudaMemcpyHostToDevice, h->stream));
-      rc = elx_simulate_injected_device(h, d_U, bpitch, nb, d_leaves, bpitch, d_comps, d_internal, bpitch);
+      rc = elx_simulate_injected_device(h, d_U[i], bpitch, nb, d_leaves[i], bpitch, d_comps[i], d_internal[i], bpitch);
     } else {
-      rc = elx_simulate_device(h, seed, site0 + b0, nb, d_leaves, bpitch, d_comps, d_internal, bpitch);
+      rc = elx_simulate_device(h, seed, site0 + b0, nb, d_leaves[i], bpitch, d_comps[i], d_internal[i], bpitch);
     }
     if (rc) { cleanup(); return rc; }
-    CT(cudaMemcpy2DAsync(leaves + b0, lp, d_leaves, bpitch, nb, h->T, cudaMemcpyDeviceToHost, h->stream));
-    if (internal) CT(cudaMemcpy2DAsync(internal + b0, ip, d_internal, bpitch, nb, h->N, cudaMemcpyDeviceToHost, h->stream));
-    if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream));
-    CT(cudaStreamSynchronize(h->stream));
+    CT(cudaEventRecord(sim_done[i], h->stream));
+    CT(cudaStreamWaitEvent(copy_stream, sim_done[i], 0));
+    CT(cudaMemcpy2DAsync(leaves + b0, lp, d_leaves[i], bpitch, nb, h->T, cudaMemcpyDeviceToHost, copy_stream));
+    if (internal) CT(cudaMemcpy2DAsync(internal + b0, ip, d_internal[i], bpitch, nb, h->N, cudaMemcpyDeviceToHost, copy_stream));
+    if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps[i], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, copy_stream));
+    CT(cudaEventRecord(copy_done[i], copy_stream));
   }
+  CT(cudaStreamSynchronize(copy_stream));
 #undef CT
   cleanup();
   return check_error_flag(h);
