@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -141,8 +141,11 @@ def cpu_reference_rate(tree, model, target_seconds, cores, steps=1, warmup=0):
 
     probe = max(cores * 64, 2048)
     dt = run(probe)
+    while dt < 2.0 and probe < 16_000_000:  # grow the probe until per-chunk overheads no longer dominate the estimate
+        probe *= 4
+        dt = run(probe)
     rate = t * probe / dt
-    s = int(max(probe, min(rate * target_seconds / t, 4_000_000)))
+    s = int(max(probe, min(rate * target_seconds / t, 50_000_000)))
     for _ in range(warmup):
         run(s)
     times = [run(s) for _ in range(max(steps, 1))]
@@ -213,12 +216,12 @@ def run_product(args):
     def step():
         sim.simulate_device(seed, site0, sites, d_leaves.data_ptr(), pitch)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = sim.launch_count
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t0 = time.perf_counter()
@@ -228,8 +231,15 @@ def run_product(args):
         b.record(stream)
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
     launches = sim.launch_count - launches0
+    # the timed region (K x ~12 ms) is shorter than nvidia-smi's sampling period: keep the GPU under the identical load
+    # for a short post-roll so that the clock / throttle-reason record has samples taken under this very kernel
+    t_roll = time.perf_counter()
+    while time.perf_counter() - t_roll < 0.6:
+        step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps + 0.6 s post-roll of identical steps"
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
     dev_total_ms = evs[0][0].elapsed_time(evs[-1][1])
     # max over ranks of the device time for the K steps
