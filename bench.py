@@ -286,6 +286,11 @@ def run_product(args):
         del host
 
     peak, peak_src = measured_peak_gbs()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("%s:%d" % (args.config, sites), {}).get("traffic_bytes")
+    except Exception:
+        pass
     kms = float(np.mean(kernel_ms))
     achieved = T * sites / (kms * 1e-3) / 1e9
     line = {
@@ -296,9 +301,11 @@ def run_product(args):
                    "components": model.n_components, "parallelism": "site-range sharding x%d, no data-path collective" % world,
                    "l2": "output %d MB per step >> 126 MB L2, no flush needed" % (T * sites // 2 ** 20),
                    "kernel": "generic" if args.force_generic else "auto", "philox_rounds": args.philox_rounds or 10},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": T * sites, "kernel_ms": kms,
-                     "note": "1 byte per alignment cell (uint8 leaf state written once); CUDA events on the handle's stream"},
+                     "note": "1 byte per alignment cell (uint8 leaf state written once); CUDA events on the handle's stream; "
+                             "traffic = DRAM read+write bytes per launch from the committed ncu --set full capture of this workload "
+                             "(profiles/r1_traffic.json), null when none was taken"},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall / args.steps * 1e3,
