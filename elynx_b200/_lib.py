@@ -67,6 +67,8 @@ SIGNATURES = {
     "elx_fasta_size": (_I64, [_VP, _CSTRS, _I64]),
     "elx_fasta_pack_device": (C.c_int, [_VP, _VP, _I64, _I64, _I64, _I64, _CSTRS, C.c_char_p, _VP]),
     "elx_simulate_fasta": (C.c_int, [_VP, _U64, _I64, _CSTRS, C.c_char_p, _VP, _I64, _VP]),
+    "elx_fasta_pack_slice_device": (C.c_int, [_VP, _VP, _I64, _I64, C.c_char_p, _VP, _I64]),
+    "elx_fasta_row_offset": (_I64, [_VP, _CSTRS, _I64, _I32]),
     "elx_histogram_device": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _VP]),
     "elx_launch_count": (_I64, [_VP]),
 }

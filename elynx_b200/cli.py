@@ -96,6 +96,32 @@ def simulate_cmd(args) -> int:
     log("Simulate alignment.")
     log("Length: %d." % args.length)
     seed = _parse_seed(args.seed) if args.seed is not None else int(time.time_ns() & (2 ** 63 - 1))
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # torchrun: one process per GPU, every rank packs its site range into its own pinned buffer (K3 slice mode) and
+        # writes its row segments of <base>.fasta; no data-path collective (elynx_b200/distributed.py)
+        import torch
+        import torch.distributed as dist
+
+        from .distributed import simulate_fasta_to_file
+
+        if not args.output_file_basename:
+            raise SystemExit("multi-GPU runs need -o/--output-file-basename")
+        if args.seed is None:
+            raise SystemExit("multi-GPU runs need -S/--seed (every rank must use the same seed)")
+        rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with Simulator(model.weights if model.is_mixture else None, model.pi, model.exch, tree, is_mixture=model.is_mixture,
+                       device=local) as sim:
+            simulate_fasta_to_file(sim, seed, args.length, tree.leaf_names(), model.alphabet_chars,
+                                   args.output_file_basename + ".fasta", rank=rank, world=world, barrier=dist.barrier)
+        dist.destroy_process_group()
+        if rank == 0:
+            log("Wrote simulated multi sequence alignment to '%s.fasta' with %d GPUs." % (args.output_file_basename, world))
+        return 0
     with Simulator(model.weights if model.is_mixture else None, model.pi, model.exch, tree, is_mixture=model.is_mixture,
                    device=args.device) as sim:
         fasta, cs = sim.simulate_fasta(seed, args.length, tree.leaf_names(), model.alphabet_chars, want_comps=model.is_mixture)

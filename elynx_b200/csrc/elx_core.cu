@@ -312,6 +312,32 @@ __global__ void k3_fasta_body(const uint8_t *__restrict__ leaves, int64_t pitch,
   }
 }
 
+// slice mode: [T][out_pitch] characters, no frame
+__global__ void k3_fasta_slice(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, const uint8_t *__restrict__ lut,
+                               int K, uint8_t *__restrict__ out, int64_t out_pitch) {
+  __shared__ uint8_t slut[64];
+  if (threadIdx.x < 64) slut[threadIdx.x] = threadIdx.x < K ? lut[threadIdx.x] : (uint8_t)'?';
+  __syncthreads();
+  int t = blockIdx.y;
+  const uint8_t *src = leaves + (int64_t)t * pitch;
+  uint8_t *dst = out + (int64_t)t * out_pitch;
+  int64_t lo = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16, hi = lo + 16;
+  if (hi > nsites) hi = nsites;
+  if (lo >= hi) return;
+  if (hi - lo == 16 && ((reinterpret_cast<uintptr_t>(dst + lo) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src + lo) & 15) == 0)) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + lo);
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      wv[q] = (uint32_t)slut[in[q] & 63] | ((uint32_t)slut[(in[q] >> 8) & 63] << 8) | ((uint32_t)slut[(in[q] >> 16) & 63] << 16) |
+              ((uint32_t)slut[(in[q] >> 24) & 63] << 24);
+    *reinterpret_cast<uint4 *>(dst + lo) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+  } else {
+    for (int64_t i = lo; i < hi; ++i) dst[i] = slut[src[i] & 63];
+  }
+}
+
 __global__ void k3_fasta_frame(int T, const int64_t *__restrict__ seq_off, const int64_t *__restrict__ name_off,
                                const uint8_t *__restrict__ names, int64_t total_sites, int write_head, int write_tail,
                                uint8_t *__restrict__ out) {
@@ -776,6 +802,38 @@ int elx_fasta_pack_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves
                                                                 tail, d_out);
     h->launches++;
   }
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+int64_t elx_fasta_row_offset(const elx_handle *h, const char *const *names, int64_t total_sites, int32_t t) {
+  if (!h || total_sites < 0 || t < 0 || t >= h->T) return -1;
+  int64_t pos = 0;
+  for (int i = 0; i <= t; ++i) {
+    int64_t len = (int64_t)(names && names[i] ? strlen(names[i]) : 0);
+    if (i == t) return pos + 1 + len + 1;
+    pos += 1 + len + 1 + total_sites + 1;
+  }
+  return -1;
+}
+
+int elx_fasta_pack_slice_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t nsites, const char *alphabet,
+                                uint8_t *d_out, int64_t out_pitch) {
+  if (!h || !d_out || !alphabet || !d_leaves) return fail(h, ELX_E_INVALID, "fasta slice: NULL argument");
+  if (nsites < 0 || leaves_pitch < nsites || out_pitch < nsites) return fail(h, ELX_E_INVALID, "fasta slice: bad site count / pitch");
+  if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
+  if (nsites == 0) return 0;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->d_lut) CUDA_TRY(h, cudaMalloc((void **)&h->d_lut, 64));
+  uint8_t lut[64];
+  memset(lut, '?', sizeof lut);
+  memcpy(lut, alphabet, (size_t)h->K);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_lut, lut, 64, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // `lut` is a stack buffer
+  h->fasta_names_key.clear();                     // the frame cache shares d_lut
+  dim3 grid((unsigned)((nsites + 16 * 256 - 1) / (16 * 256)), (unsigned)h->T);
+  k3_fasta_slice<<<grid, 256, 0, h->stream>>>(d_leaves, leaves_pitch, nsites, h->d_lut, h->K, d_out, out_pitch);
+  h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return 0;
 }

@@ -49,3 +49,69 @@ def simulate_sharded(sim, seed: int, n_sites: int, rank: int, world: int, want_c
     site0, n = site_range(rank, world, n_sites, align=16)
     leaves, comps, _ = sim.simulate(seed, n, site0=site0, want_comps=want_comps)
     return site0, leaves, comps
+
+
+def simulate_fasta_to_file(sim, seed: int, total_sites: int, names, alphabet: str, path: str, rank: int = 0, world: int = 1,
+                           batch_sites: int = 1 << 22, barrier=None):
+    """Write the FASTA file of a `total_sites`-column alignment with `world` GPUs (one process each).
+
+    Rank r owns the columns site_range(r, world, total_sites, align=16) of every sequence line.  Kernel K3 (slice
+    mode) of every GPU packs the characters of its columns STRAIGHT into that rank's pinned host buffer over PCIe
+    (no device-side file image, no host-side interleaving, no collective); the host then writes each row segment at
+    its byte offset in the file (one pwrite per row and batch).  Rank 0 creates the file at its final size and writes
+    the `>name` lines and the newlines.  `barrier` orders file creation before the other ranks open it
+    (torch.distributed.barrier under torchrun)."""
+    import os
+
+    import torch
+
+    size = sim.fasta_size(names, total_sites)
+    t = sim.n_leaves
+    row_off = [sim.fasta_row_offset(names, total_sites, i) for i in range(t)]
+    if rank == 0:
+        with open(path, "wb") as f:
+            f.truncate(size)
+            for i in range(t):
+                f.seek(row_off[i] - len(names[i].encode()) - 2)
+                f.write(b">" + names[i].encode() + b"\n")
+                f.seek(row_off[i] + total_sites)
+                f.write(b"\n")
+    if barrier is not None:
+        barrier()
+    site0, n = site_range(rank, world, total_sites, align=16)
+    if n > 0:
+        nb = max(16, min(batch_sites, n))
+        pitch = (nb + 127) // 128 * 128
+        d_leaves = torch.empty((t, pitch), dtype=torch.uint8, device="cuda")
+        host = [torch.empty((t, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(2)]  # double-buffered pinned slices
+        stream = torch.cuda.ExternalStream(sim.stream)
+        torch.cuda.synchronize()
+        fd = os.open(path, os.O_RDWR)
+        try:
+            pending = None
+            done = 0
+            b = 0
+            while done < n or pending is not None:
+                cur = None
+                if done < n:
+                    k = min(nb, n - done)
+                    hb = host[b & 1]
+                    sim.simulate_device(seed, site0 + done, k, d_leaves.data_ptr(), pitch)
+                    sim.fasta_pack_slice_device(d_leaves.data_ptr(), pitch, k, alphabet, hb.data_ptr(), pitch)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    cur = (ev, hb, site0 + done, k)
+                    done += k
+                    b += 1
+                if pending is not None:  # write batch b-1 while the GPU works on batch b
+                    ev, hb, s0, k = pending
+                    ev.synchronize()
+                    arr = hb.numpy()
+                    for i in range(t):
+                        os.pwrite(fd, arr[i, :k].tobytes(), row_off[i] + s0)
+                pending = cur
+        finally:
+            os.close(fd)
+    if barrier is not None:
+        barrier()
+    return site0, n

@@ -172,6 +172,14 @@ class Simulator:
         L.check(L.lib().elx_fasta_pack_device(self._h, C.c_void_p(d_leaves), leaves_pitch, site0, nsites, total_sites,
                                               self._names(names), alphabet.encode(), C.c_void_p(d_out)), self._h)
 
+    def fasta_pack_slice_device(self, d_leaves: int, leaves_pitch: int, nsites: int, alphabet: str, d_out: int, out_pitch: int):
+        """K3 slice mode: [T][out_pitch] characters into any device-accessible buffer (e.g. pinned host memory)."""
+        L.check(L.lib().elx_fasta_pack_slice_device(self._h, C.c_void_p(d_leaves), leaves_pitch, nsites, alphabet.encode(),
+                                                    C.c_void_p(d_out), out_pitch), self._h)
+
+    def fasta_row_offset(self, names: Sequence[str], total_sites: int, t: int) -> int:
+        return int(L.lib().elx_fasta_row_offset(self._h, self._names(names), total_sites, t))
+
     def histogram_device(self, d_leaves: int, leaves_pitch: int, nsites: int, d_state_counts: int = 0, d_pattern_counts: int = 0):
         L.check(L.lib().elx_histogram_device(self._h, C.c_void_p(d_leaves), leaves_pitch, nsites,
                                              C.c_void_p(d_state_counts or None), C.c_void_p(d_pattern_counts or None)), self._h)

@@ -104,7 +104,7 @@ int elx_ptables_get(elx_handle *h, double *out, int cumulative);
  * (e.g. the oracle's Pade tables) and rebuild the cumulative + alias tables from them on the device. */
 int elx_ptables_set(elx_handle *h, const double *p);
 /* Parity hook for the free-running sampler: alias tables derived from the P rows.
- * e16 [N][C][K][KP] (uint16: threshold high bits | alias | 0), qlo [N][C][K][KP] (uint32 threshold low bits),
+ * e16 [N][C][K][KP] (uint16: [threshold high bits : 16-A][alias : A], A = log2 KP), qlo [N][C][K][KP] (uint32 threshold low bits),
  * KP = elx_alias_columns(h).  See DESIGN.md "free-running draw". */
 int32_t elx_alias_columns(const elx_handle *h);
 int elx_alias_get(elx_handle *h, uint16_t *e16, uint32_t *qlo);
@@ -144,6 +144,14 @@ int elx_fasta_pack_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves
                           int64_t total_sites, const char *const *names, const char *alphabet, uint8_t *d_out);
 int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const char *const *names, const char *alphabet,
                        uint8_t *out, int64_t out_capacity, int32_t *comps);
+/* K3 in slice mode: the characters of columns [0, nsites) of every sequence as a plain [T][out_pitch] matrix (no header
+ * lines, no newlines).  d_out may be any device-accessible pointer, in particular pinned host memory: with several GPUs
+ * every rank packs its site range straight into its own pinned buffer and the host writes each row segment into the
+ * file at elx_fasta_row_offset(t) + site0. */
+int elx_fasta_pack_slice_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t nsites,
+                                const char *alphabet, uint8_t *d_out, int64_t out_pitch);
+/* byte offset of the first sequence character of leaf row t in the FASTA image of a total_sites-column alignment */
+int64_t elx_fasta_row_offset(const elx_handle *h, const char *const *names, int64_t total_sites, int32_t t);
 
 /* ---- validation histograms (new; the reference has none) ---------------------------------------
  * d_state_counts [T][K] int64 += per-taxon state counts; d_pattern_counts [K^T] int64 += site-pattern counts

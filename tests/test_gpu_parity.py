@@ -396,3 +396,24 @@ def test_cli_slynx_test_matrix(tmp_path, ref_data):
         assert set(b"".join(lines[1::2])) <= set(alphabet)
     sd = open(str(tmp_path / "out2") + ".sitedists").read().split("\n")
     assert len(sd) == 1000 and sd[0].startswith("1 ") and len(sd[0].split()) == 21
+
+
+def test_fasta_straight_to_pinned_file_image(tmp_path):
+    """K3 packs into a cudaHostRegister'ed mmap of the output file; emulating 3 ranks one after the other on one GPU
+    must give the bytes of the single-call FASTA path (site ranges are disjoint, counters use global site indices)."""
+    pytest.importorskip("torch")
+    from elynx_b200.distributed import simulate_fasta_to_file
+
+    model = model_case("lg_g4")
+    tree = tree_from_file("Newick.tree")
+    names = tree.leaf_names()
+    s = 10007
+    with make_sim(model, tree) as sim:
+        ref, _ = sim.simulate_fasta(9, s, names, om.ALPHABET_CHARS[model[4]])
+        path = str(tmp_path / "aln.fasta")
+        for rank in range(3):
+            simulate_fasta_to_file(sim, 9, s, names, om.ALPHABET_CHARS[model[4]], path, rank=rank, world=3, batch_sites=2048)
+        assert open(path, "rb").read() == ref
+        one = str(tmp_path / "one.fasta")
+        simulate_fasta_to_file(sim, 9, s, names, om.ALPHABET_CHARS[model[4]], one)
+        assert open(one, "rb").read() == ref
