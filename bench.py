@@ -232,6 +232,7 @@ def run_product(args):
     barrier()
     wall = time.perf_counter() - t0
     launches = sim.launch_count - launches0
+    sim.synchronize()  # raises if any kernel flagged an error (e.g. "categorical: bad weights!")
     # the timed region (K x ~12 ms) is shorter than nvidia-smi's sampling period: keep the GPU under the identical load
     # for a short post-roll so that the clock / throttle-reason record has samples taken under this very kernel
     t_roll = time.perf_counter()

@@ -62,6 +62,7 @@ SIGNATURES = {
     "elx_alias_get": (C.c_int, [_VP, _VP, _VP]),
     "elx_simulate": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
+    "elx_synchronize": (C.c_int, [_VP]),
     "elx_simulate_injected": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_injected_device": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_fasta_size": (_I64, [_VP, _CSTRS, _I64]),

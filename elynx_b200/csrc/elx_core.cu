@@ -624,6 +624,12 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   return 0;
 }
 
+int elx_synchronize(elx_handle *h) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return check_error_flag(h);
+}
+
 int elx_simulate_injected_device(elx_handle *h, const double *d_U, int64_t u_pitch, int64_t nsites, uint8_t *d_leaves,
                                  int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch) {
   int rc = check_sim_args(h, 0, nsites, d_leaves, leaves_pitch, d_internal, internal_pitch);

@@ -256,6 +256,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) k2_tiled(Fast
       const int leaf_row = (int)rec.z;
       const uint32_t tbl = sbuf + (uint32_t)(nps * 16) + (uint32_t)k * (uint32_t)fa.tb;
       const bool reload = src != reg_slot;
+#ifdef ELX_DEBUG_BOUNDS
+      if (src < 0 || src >= a.n_slots || dst >= a.n_slots || node >= (uint32_t)a.N || k * fa.tb + fa.tb + nps * 16 > fa.stage_bytes)
+        atomicExch(a.error_flag, -8);
+#endif
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (reload) {
@@ -293,6 +297,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) k2_tiled(Fast
           // into a 3-input IADD3 per draw instead of using [R + UR] addressing.
           uint32_t aA = ((w[pr] & L::JMASK) << 1) | offA;
           uint32_t aB = (((w[pr] >> 16) & L::JMASK) << 1) | offB;
+#ifdef ELX_DEBUG_BOUNDS  // compute-sanitizer is closed on the GPU pool: self-check every shared-memory table access
+          if (aA + 2 > (uint32_t)fa.tb || aB + 2 > (uint32_t)fa.tb || (aA & 1) || (aB & 1)) atomicExch(a.error_flag, -7);
+#endif
           uint32_t eA = lds_u16(tbl + aA);
           uint32_t eB = lds_u16(tbl + aB);
           uint32_t ee = __byte_perm(eA, eB, 0x5410u);

@@ -148,6 +148,10 @@ class Simulator:
                                             leaves_pitch, C.c_void_p(d_comps or None), C.c_void_p(d_internal or None),
                                             internal_pitch), self._h)
 
+    def synchronize(self):
+        """Wait for the enqueued device work and raise what the kernels flagged (elx_synchronize)."""
+        L.check(L.lib().elx_synchronize(self._h), self._h)
+
     # -- FASTA -----------------------------------------------------------------------------------
     @staticmethod
     def _names(names: Sequence[str]):

@@ -123,6 +123,10 @@ int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, ui
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves,
                         int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch);
 
+/* Waits for the work enqueued by the *_device entry points on elx_stream(h) and reports what the kernels flagged
+ * ("categorical: bad weights!", ELX_E_BAD_WEIGHTS); the host variants do this themselves. */
+int elx_synchronize(elx_handle *h);
+
 /* Injected-uniforms mode: consumes the uniform matrix U[(is_mixture ? 2 : 1) + N][u_pitch] (doubles in
  * (0,1]) in the reference's draw order -- [component row (mixtures)] [root-state row] [one row per node in
  * preorder] -- with mwc-random `categorical` semantics (first i with cum[i] >= cum[K-1]*u, fp64).
