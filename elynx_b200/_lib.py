@@ -51,6 +51,7 @@ SIGNATURES = {
     "elx_last_error": (C.c_char_p, [_VP]),
     "elx_create": (C.c_int, [C.POINTER(elx_model), C.POINTER(elx_tree), C.POINTER(elx_opts), C.POINTER(_VP)]),
     "elx_destroy": (None, [_VP]),
+    "elx_tree_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
     "elx_n_leaves": (_I32, [_VP]),
     "elx_n_nodes": (_I32, [_VP]),
     "elx_n_states": (_I32, [_VP]),

@@ -550,6 +550,19 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   return 0;
 }
 
+int elx_tree_walk_info(const elx_tree *tree, int32_t *n_leaves, int32_t *n_slots, int32_t *walk_nodes) {
+  if (!tree || tree->n_nodes < 1 || !tree->parent || !tree->leaf_row) return fail(nullptr, ELX_E_INVALID, "tree: empty or NULL arrays");
+  WalkProgram walk;
+  int T = 0;
+  std::string msg;
+  if (!compile_walk(tree->n_nodes, tree->parent, tree->leaf_row, walk, T, msg)) return fail(nullptr, ELX_E_INVALID, msg);
+  if (n_leaves) *n_leaves = T;
+  if (n_slots) *n_slots = walk.n_slots;
+  if (walk_nodes)
+    for (int i = 0; i < tree->n_nodes; ++i) walk_nodes[i] = walk.recs[i].node;
+  return 0;
+}
+
 void elx_destroy(elx_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);

@@ -90,6 +90,11 @@ const char *elx_last_error(const elx_handle *h);
 int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opts, elx_handle **out);
 void elx_destroy(elx_handle *h);
 
+/* Host-only: validates the preorder arrays and compiles the tree walk (heavy child last); reports the number of leaves
+ * and of live state slots the walk needs (<= floor(log2 N) + 1 for any tree).  walk_nodes (optional, [N]) receives the
+ * visiting order as preorder node indices. */
+int elx_tree_walk_info(const elx_tree *tree, int32_t *n_leaves, int32_t *n_slots, int32_t *walk_nodes);
+
 int32_t elx_n_leaves(const elx_handle *h);
 int32_t elx_n_nodes(const elx_handle *h);
 int32_t elx_n_states(const elx_handle *h);

@@ -82,3 +82,56 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(eb.ElxError) as ei:
         eb.simulateAndFlattenPar(10, d, e, T3, 0)
     assert ei.value.code == L.ELX_E_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def _walk_info(parent, leaf_row):
+    import ctypes as C
+
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+    brlen = np.zeros(len(parent))
+    t = L.elx_tree(len(parent), parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
+                   leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
+    nl, ns = C.c_int32(), C.c_int32()
+    order = np.empty(len(parent), dtype=np.int32)
+    L.check(L.lib().elx_tree_walk_info(C.byref(t), C.byref(nl), C.byref(ns), C.c_void_p(order.ctypes.data)))
+    return nl.value, ns.value, order
+
+
+def test_walk_program_slot_bound():
+    """Heavy-child-last walk: parents before children, every node once, and at most floor(log2 N)+1 live slots for ANY
+    tree -- ladders of 10^4 taxa included (no HBM scratch needed for deep trees)."""
+    import math
+
+    from elynx_b200 import model as pm
+
+    def ladder(n, left):  # caterpillar with the internal child first (left) or last (right), in preorder
+        m = n - 1  # internal nodes
+        if left:
+            parent = [-1] + list(range(m - 1)) + [m - 1, m - 1] + list(range(m - 2, -1, -1))
+            leaf_row = [-1] * m + list(range(n))
+        else:
+            parent, leaf_row = [-1], [-1]
+            cur = 0
+            for i in range(m - 1):
+                parent += [cur, cur]
+                leaf_row += [i, -1]
+                cur = len(parent) - 1
+            parent += [cur, cur]
+            leaf_row += [m - 1, m]
+        return np.array(parent), np.array(leaf_row)
+
+    cases = [ladder(10000, True), ladder(10000, False)]
+    for n, seed in ((1000, 1), (10000, 3), (3, 0), (2, 0)):
+        t = pm.birth_death_tree(n, 1.0, 0.5, seed=seed)
+        cases.append((t.parent, t.leaf_row))
+    cases.append((np.array([-1]), np.array([0])))  # single node
+    for parent, leaf_row in cases:
+        n = len(parent)
+        nl, ns, order = _walk_info(parent, leaf_row)
+        assert nl == int((np.asarray(leaf_row) >= 0).sum())
+        assert sorted(order.tolist()) == list(range(n))
+        pos = np.empty(n, dtype=np.int64)
+        pos[order] = np.arange(n)
+        assert all(pos[parent[i]] < pos[i] for i in range(1, n))
+        assert ns <= int(math.floor(math.log2(n))) + 1 if n > 1 else ns == 1, (n, ns)
