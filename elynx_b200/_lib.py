@@ -17,6 +17,7 @@ ELX_E_UNSUPPORTED = -3
 ELX_E_NOMEM = -4
 ELX_E_BAD_WEIGHTS = -5
 ELX_FLAG_FORCE_GENERIC = 1
+ELX_FLAG_PADE = 2
 
 
 class ElxError(RuntimeError):

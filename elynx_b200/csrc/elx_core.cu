@@ -92,6 +92,122 @@ __global__ void k1_cum_from_p(int64_t rows, int K, const double *__restrict__ P,
   }
 }
 
+// K1 (general path): P = expm(t Q) by scaled diagonal Pade of order 7 with squaring -- the algorithm hmatrix `expm`
+// runs (Golub & Van Loan 11.3.1: j = max 0 (floor (log2 ||tQ||_inf)), A = tQ/2^j, F = D^-1 N, square j times), one CTA
+// per (branch, component) matrix, everything in shared memory.  Used when a component is not reversible (asymmetric
+// exchangeabilities or a zero stationary frequency: no symmetric eigensystem) or when ELX_FLAG_PADE asks for it.
+__global__ void k1_pade(int N, int C, int K, const double *__restrict__ brlen, const double *__restrict__ Q, double *__restrict__ P) {
+  extern __shared__ double sm[];
+  const int KK = K * K;
+  double *A = sm, *X = sm + KK, *Nn = sm + 2 * KK, *D = sm + 3 * KK, *T = sm + 4 * KK;
+  __shared__ double red[32];
+  __shared__ int s_piv;
+  const int m = blockIdx.x, n = m / C, c = m % C;
+  const double t = brlen[n];
+  double *out = P + (int64_t)m * KK;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (t == 0.0) {
+    for (int e = tid; e < KK; e += nt) out[e] = (e / K == e % K) ? 1.0 : 0.0;
+    return;
+  }
+  const double *Qc = Q + (int64_t)c * KK;
+  for (int e = tid; e < KK; e += nt) A[e] = t * Qc[e];
+  __syncthreads();
+  // infinity norm = max row sum of |a_ij|
+  double rmax = 0.0;
+  for (int i = tid; i < K; i += nt) {
+    double r = 0.0;
+    for (int j = 0; j < K; ++j) r += fabs(A[i * K + j]);
+    rmax = fmax(rmax, r);
+  }
+  for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  if ((tid & 31) == 0) red[tid >> 5] = rmax;
+  __syncthreads();
+  double nrm = 0.0;
+  for (int w = 0; w < (nt + 31) / 32; ++w) nrm = fmax(nrm, red[w]);
+  int jsq = nrm > 0.0 ? (int)floor(log2(nrm)) : 0;
+  if (jsq < 0) jsq = 0;
+  const double scale = ldexp(1.0, -jsq);
+  for (int e = tid; e < KK; e += nt) {
+    A[e] *= scale;
+    double id = (e / K == e % K) ? 1.0 : 0.0;
+    X[e] = id; Nn[e] = id; D[e] = id;
+  }
+  __syncthreads();
+  const int q = 7;
+  double cf = 1.0;
+  for (int k = 1; k <= q; ++k) {
+    cf = cf * (double)(q - k + 1) / (double)((2 * q - k + 1) * k);
+    for (int e = tid; e < KK; e += nt) {  // T = A X
+      const int i = e / K, j = e % K;
+      double acc = 0.0;
+      for (int l = 0; l < K; ++l) acc = fma(A[i * K + l], X[l * K + j], acc);
+      T[e] = acc;
+    }
+    __syncthreads();
+    const double sgn = (k & 1) ? -1.0 : 1.0;
+    for (int e = tid; e < KK; e += nt) {
+      const double x = T[e];
+      X[e] = x;
+      Nn[e] += cf * x;
+      D[e] += sgn * cf * x;
+    }
+    __syncthreads();
+  }
+  // solve D F = N by Gaussian elimination with partial pivoting (in place: D -> U, N -> F)
+  for (int p = 0; p < K; ++p) {
+    if (tid == 0) {
+      int best = p;
+      double bv = fabs(D[p * K + p]);
+      for (int i = p + 1; i < K; ++i) { double v = fabs(D[i * K + p]); if (v > bv) { bv = v; best = i; } }
+      s_piv = best;
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv != p)
+      for (int j = tid; j < 2 * K; j += nt) {
+        double *M = j < K ? D : Nn;
+        const int jj = j < K ? j : j - K;
+        double a = M[p * K + jj]; M[p * K + jj] = M[piv * K + jj]; M[piv * K + jj] = a;
+      }
+    __syncthreads();
+    const double dinv = 1.0 / D[p * K + p];
+    for (int i = p + 1 + tid; i < K; i += nt) T[i] = D[i * K + p] * dinv;  // multipliers
+    __syncthreads();
+    for (int e = tid; e < (K - p - 1) * 2 * K; e += nt) {
+      const int i = p + 1 + e / (2 * K), j = e % (2 * K);
+      double *M = j < K ? D : Nn;
+      const int jj = j < K ? j : j - K;
+      if (j < K && jj <= p) continue;
+      M[i * K + jj] -= T[i] * M[p * K + jj];
+    }
+    __syncthreads();
+  }
+  for (int p = K - 1; p >= 0; --p) {  // back substitution, column-parallel
+    for (int j = tid; j < K; j += nt) {
+      double acc = Nn[p * K + j];
+      for (int l = p + 1; l < K; ++l) acc -= D[p * K + l] * Nn[l * K + j];
+      Nn[p * K + j] = acc / D[p * K + p];
+    }
+    __syncthreads();
+  }
+  double *F = Nn, *G = X;
+  for (int it = 0; it < jsq; ++it) {
+    for (int e = tid; e < KK; e += nt) {
+      const int i = e / K, j = e % K;
+      double acc = 0.0;
+      for (int l = 0; l < K; ++l) acc = fma(F[i * K + l], F[l * K + j], acc);
+      G[e] = acc;
+    }
+    __syncthreads();
+    double *tmp = F; F = G; G = tmp;
+  }
+  for (int e = tid; e < KK; e += nt) {
+    double p = F[e];
+    out[e] = p > 0.0 ? p : 0.0;  // rounding noise on vanishing entries
+  }
+}
+
 // Alias tables for the free-running sampler, built in exact integer arithmetic (one thread per row).
 // Row masses m_i = round(p_i / sum p * 2^48) (residual added to the largest), column capacity 2^(48-A).
 __global__ void k1_alias(int64_t rows, int K, int A, const double *__restrict__ P, uint16_t *__restrict__ e16,
@@ -385,7 +501,13 @@ static int build_tables_from_p(elx_handle *h, bool have_p) {
   const int64_t rows = (int64_t)h->N * h->C * h->K;
   const int threads = 128;
   const unsigned blocks = (unsigned)((rows + threads - 1) / threads);
-  if (!have_p) {
+  if (!have_p && h->use_pade) {
+    const size_t smem = sizeof(double) * 5 * h->K * h->K;
+    cudaFuncSetAttribute(k1_pade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k1_pade<<<(unsigned)(h->N * h->C), 128, smem, h->stream>>>(h->N, h->C, h->K, h->d_brlen, h->d_Q, h->d_P);
+    h->launches++;
+    k1_cum_from_p<<<blocks, threads, 0, h->stream>>>(rows, h->K, h->d_P, h->d_cum);
+  } else if (!have_p) {
     k1_ptables<<<blocks, threads, 0, h->stream>>>(h->N, h->C, h->K, h->d_brlen, h->d_lambda, h->d_A, h->d_B, h->d_P, h->d_cum);
   } else {
     k1_cum_from_p<<<blocks, threads, 0, h->stream>>>(rows, h->K, h->d_P, h->d_cum);
@@ -483,11 +605,31 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   if (!compile_walk(N, tree->parent, tree->leaf_row, walk, T, msg)) return fail(nullptr, ELX_E_INVALID, msg);
   if (walk.n_slots > MAX_SLOTS) return fail(nullptr, ELX_E_UNSUPPORTED, "tree: needs more than 32 live state slots");
 
-  std::vector<double> lambda((size_t)C * K), A((size_t)C * K * K), B((size_t)C * K * K);
-  for (int c = 0; c < C; ++c)
+  // Eigen path (reversible components) or, when any component has no symmetric eigensystem (asymmetric
+  // exchangeabilities, a zero stationary frequency) or ELX_FLAG_PADE is set, the general Pade path on
+  // Q = setDiagonal(E diag pi) (RateMatrix.hs:87-103).
+  std::vector<double> lambda((size_t)C * K), A((size_t)C * K * K), B((size_t)C * K * K), Qh;
+  bool use_pade = opts && (opts->flags & ELX_FLAG_PADE);
+  for (int c = 0; c < C && !use_pade; ++c)
     if (!eigen_reversible(K, model->pi + (size_t)c * K, model->exch + (size_t)c * K * K, &lambda[(size_t)c * K],
                           &A[(size_t)c * K * K], &B[(size_t)c * K * K], msg))
-      return fail(nullptr, ELX_E_UNSUPPORTED, msg);
+      use_pade = true;
+  if (use_pade) {
+    if (K > 32) return fail(nullptr, ELX_E_UNSUPPORTED, "model: the Pade path supports at most 32 states (" + msg + ")");
+    Qh.assign((size_t)C * K * K, 0.0);
+    for (int c = 0; c < C; ++c)
+      for (int i = 0; i < K; ++i) {
+        double rs = 0;
+        for (int j = 0; j < K; ++j) {
+          if (j == i) continue;
+          double v = model->exch[((size_t)c * K + i) * K + j] * model->pi[(size_t)c * K + j];
+          if (!std::isfinite(v)) return fail(nullptr, ELX_E_INVALID, "model: exchangeabilities must be finite");
+          Qh[((size_t)c * K + i) * K + j] = v;
+          rs += std::fabs(v);
+        }
+        Qh[((size_t)c * K + i) * K + i] = -rs;
+      }
+  }
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -501,6 +643,7 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   h->A = alias_bits(K); h->KP = 1 << h->A; h->device = dev; h->n_slots = walk.n_slots;
   h->rounds = (opts && opts->philox_rounds == 7) ? 7 : 10;
   h->flags = opts ? opts->flags : 0;
+  h->use_pade = use_pade ? 1 : 0;
   if (opts && opts->philox_rounds != 0 && opts->philox_rounds != 7 && opts->philox_rounds != 10) {
     delete h;
     return fail(nullptr, ELX_E_INVALID, "opts: philox_rounds must be 0, 7 or 10");
@@ -518,6 +661,10 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   CT(dalloc(&h->d_lambda, (size_t)C * K));
   CT(dalloc(&h->d_A, (size_t)C * K * K));
   CT(dalloc(&h->d_B, (size_t)C * K * K));
+  if (use_pade) {
+    CT(dalloc(&h->d_Q, (size_t)C * K * K));
+    CT(cudaMemcpy(h->d_Q, Qh.data(), sizeof(double) * Qh.size(), cudaMemcpyHostToDevice));
+  }
   CT(dalloc(&h->d_P, rows * K));
   CT(dalloc(&h->d_cum, rows * K));
   CT(dalloc(&h->d_e16, rows * h->KP));
@@ -568,7 +715,7 @@ void elx_destroy(elx_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   fast_tables_free(h);
-  cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
+  cudaFree(h->d_Q); cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
   cudaFree(h->d_e16); cudaFree(h->d_qlo); cudaFree(h->d_cumw); cudaFree(h->d_cumpi); cudaFree(h->d_walk);
   cudaFree(h->d_error_flag); cudaFree(h->d_scratch); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
   cudaFree(h->d_lut);

@@ -11,7 +11,8 @@
 struct elx_handle {
   int N = 0, K = 0, C = 0, T = 0, is_mixture = 0, A = 0, KP = 0, device = 0, n_slots = 0, rounds = 10, flags = 0;
   cudaStream_t stream = nullptr;
-  double *d_brlen = nullptr, *d_lambda = nullptr, *d_A = nullptr, *d_B = nullptr;
+  double *d_brlen = nullptr, *d_lambda = nullptr, *d_A = nullptr, *d_B = nullptr, *d_Q = nullptr;
+  int use_pade = 0;
   double *d_P = nullptr, *d_cum = nullptr, *d_cumw = nullptr, *d_cumpi = nullptr;
   uint16_t *d_e16 = nullptr;
   uint32_t *d_qlo = nullptr;

@@ -33,7 +33,7 @@ class Simulator:
     alias tables and the compiled tree walk."""
 
     def __init__(self, weights, ds, es, tree, is_mixture: bool = True, device: int = -1, philox_rounds: int = 0,
-                 force_generic: bool = False):
+                 force_generic: bool = False, pade: bool = False):
         ds = np.ascontiguousarray(ds, dtype=np.float64)
         es = np.ascontiguousarray(es, dtype=np.float64)
         if ds.ndim == 1:
@@ -54,7 +54,7 @@ class Simulator:
                         ds.ctypes.data_as(C.POINTER(C.c_double)), es.ctypes.data_as(C.POINTER(C.c_double)))
         t = L.elx_tree(len(parent), parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
                        leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
-        o = L.elx_opts(device, philox_rounds, L.ELX_FLAG_FORCE_GENERIC if force_generic else 0, 0)
+        o = L.elx_opts(device, philox_rounds, (L.ELX_FLAG_FORCE_GENERIC if force_generic else 0) | (L.ELX_FLAG_PADE if pade else 0), 0)
         h = C.c_void_p()
         self._h = None
         L.check(L.lib().elx_create(C.byref(m), C.byref(t), C.byref(o), C.byref(h)))

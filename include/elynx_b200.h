@@ -46,7 +46,7 @@ typedef enum {
   ELX_OK = 0,
   ELX_E_INVALID = -1,     /* bad argument (what the reference rejects with `error`) */
   ELX_E_CUDA = -2,        /* CUDA runtime failure / no device */
-  ELX_E_UNSUPPORTED = -3, /* e.g. non-reversible model (needs symmetric exch and pi > 0) */
+  ELX_E_UNSUPPORTED = -3, /* e.g. a tree needing more than 32 live state slots, a non-reversible model with K > 32 */
   ELX_E_NOMEM = -4,
   ELX_E_BAD_WEIGHTS = -5  /* mwc-random "categorical: bad weights!" */
 } elx_status;
@@ -79,6 +79,8 @@ typedef struct {
 } elx_opts;
 
 #define ELX_FLAG_FORCE_GENERIC 1 /* always use the generic global-table kernel (cross-check of the tiled one) */
+#define ELX_FLAG_PADE 2          /* build P(t) by the scaled Pade-7 + squaring kernel (hmatrix `expm`'s algorithm) instead of
+                                    the eigen form; taken automatically for non-reversible components */
 
 int elx_version(void);
 const char *elx_last_error(const elx_handle *h);

@@ -69,9 +69,9 @@ def test_validation_matches_reference_errors():
     expect_error("permutation", lambda: eb.Simulator(None, d, e, BadLeaf, is_mixture=False))
     expect_error("Number of weights", lambda: eb.Simulator(np.ones(3), np.stack([d, d]), np.stack([e, e]), T3))  # MixtureModel.hs:86
     expect_error("bad weights", lambda: eb.Simulator(np.zeros(2), np.stack([d, d]), np.stack([e, e]), T3))
-    asym = e.copy()
-    asym[0, 1] = 2.0
-    expect_error("symmetric", lambda: eb.Simulator(None, d, asym, T3, is_mixture=False))
+    big = np.ones((40, 40)) - np.eye(40)
+    big[0, 1] = 2.0  # non-reversible models take the Pade path, which stops at 32 states
+    expect_error("at most 32 states", lambda: eb.Simulator(None, np.full(40, 1 / 40), big, T3, is_mixture=False))
 
 
 def test_no_cpu_fallback_without_a_device():

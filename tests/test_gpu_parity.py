@@ -417,3 +417,53 @@ def test_fasta_straight_to_pinned_file_image(tmp_path):
         one = str(tmp_path / "one.fasta")
         simulate_fasta_to_file(sim, 9, s, names, om.ALPHABET_CHARS[model[4]], one)
         assert open(one, "rb").read() == ref
+
+
+# ---------------------------------------------------------------------------------------------
+# general (Pade) K1 path: non-reversible models and zero stationary frequencies
+# ---------------------------------------------------------------------------------------------
+def test_pade_path_matches_hmatrix_expm_closely():
+    """ELX_FLAG_PADE runs hmatrix expm's own algorithm on the device: agreement with the restatement ~1e-14."""
+    model = model_case("lg_g4")
+    tree = om.parse_newick("((a:1e-6,b:1e-4):1e-2,(c:0.1,d:1.0):5.0,e:20.0,f:0.0);")
+    ref = om.prob_tables(model[2], model[3], tree.brlen)
+    with make_sim(model, tree, pade=True) as sim:
+        p = sim.ptables()
+        cum = sim.ptables(cumulative=True)
+    assert np.max(np.abs(p - ref) / np.maximum(ref, 1e-300)) < 1e-12  # element-wise, also on the 1e-6 branch
+    assert np.max(np.abs(p - ref)) < 5e-15
+    assert np.array_equal(cum, np.cumsum(p, axis=-1))
+
+
+@pytest.mark.parametrize("kind", ["asymmetric", "zero_pi", "zero_pi_protein"])
+def test_non_reversible_models(kind):
+    rng = np.random.default_rng(3)
+    if kind == "asymmetric":
+        ds = np.array([[0.1, 0.2, 0.3, 0.4]])
+        es = rng.uniform(0.2, 2.0, size=(1, 4, 4))
+        es[0][np.arange(4), np.arange(4)] = 0
+    elif kind == "zero_pi":
+        ds = np.array([[0.5, 0.5, 0.0, 0.0]])
+        es = (np.ones((4, 4)) - np.eye(4))[None]
+    else:
+        pi = om.lg_stat_dist().copy()
+        pi[[3, 7]] = 0.0
+        ds = (pi / pi.sum())[None]
+        es = om.lg_exch()[None]
+    tree = tree_from_file("UltraMetric.tree")
+    ref = om.prob_tables(ds, es, tree.brlen)
+    sim = eb.Simulator(None, ds, es, tree, is_mixture=False)
+    with sim:
+        p = sim.ptables()
+        assert np.max(np.abs(p - ref)) < 1e-13
+        u = uniforms(rng, tree.n_nodes + 1, 3000)
+        leaves, _, internal = sim.simulate_injected(u, keep_internal=True)
+        _, l0, i0 = osim.simulate_injected(False, tree.parent, tree.leaf_row, np.ones(1), ds, p, u, keep_internal=True)
+        assert np.array_equal(leaves, l0) and np.array_equal(internal, i0)
+        e16, qlo = sim.alias_tables()
+        fr = sim.simulate(4, 3000)[0]
+        l1, _, _ = spec.freerun(False, tree.parent, tree.leaf_row, np.ones(1), ds, e16, qlo, 4, 0, 3000)
+        assert np.array_equal(fr, l1)
+        if kind != "asymmetric":
+            dead = np.nonzero(ds[0] == 0)[0]
+            assert not np.isin(fr, dead).any()  # states with zero frequency are never entered
