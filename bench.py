@@ -255,6 +255,8 @@ def run_product(args):
     e2e = None
     if not args.no_e2e:
         e2e_sites = min(sites, args.e2e_sites)
+        if world > 1:  # keep the pinned host buffers of all ranks of the box together under ~24 GB
+            e2e_sites = max(16, min(e2e_sites, int(24e9 / (T * world)) // 16 * 16))
         host = torch.empty((T, e2e_sites), dtype=torch.uint8, pin_memory=True)
         hnp = host.numpy()
         import ctypes as C
