@@ -467,3 +467,23 @@ def test_non_reversible_models(kind):
         if kind != "asymmetric":
             dead = np.nonzero(ds[0] == 0)[0]
             assert not np.isin(fr, dead).any()  # states with zero frequency are never entered
+
+
+@pytest.mark.parametrize("name,tree_file", [("hky_g4", "Newick.tree"), ("lg_g4", "UltraMetric.tree"), ("c60", "UltraMetric.tree")])
+def test_philox7_option_matches_spec(name, tree_file):
+    """philox_rounds = 7 (the minimum Crush-resistant round count; +15 % throughput) is a library option; both the generic
+    and the tiled kernels must follow the same spec with 7 rounds."""
+    model = model_case(name)
+    is_mix, ws, ds, es, _ = model
+    tree = tree_from_file(tree_file)
+    s = 6000
+    outs = []
+    for fg in (True, False):
+        with make_sim(model, tree, force_generic=fg, philox_rounds=7) as sim:
+            e16, qlo = sim.alias_tables()
+            leaves, comps, _ = sim.simulate(21, s, site0=32, want_comps=True)
+            outs.append(leaves)
+    l0, c0, _ = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, 21, 32, s, rounds=7)
+    assert np.array_equal(outs[0], l0) and np.array_equal(outs[1], l0) and np.array_equal(comps, c0)
+    l10, _, _ = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, 21, 32, s, rounds=10)
+    assert not np.array_equal(l10, l0)
