@@ -10,7 +10,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -648,10 +647,6 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
     delete h;
     return fail(nullptr, ELX_E_INVALID, "opts: philox_rounds must be 0, 7 or 10");
   }
-  h->walk_host = walk.recs;
-  h->leaf_row_host.assign(tree->leaf_row, tree->leaf_row + N);
-  h->parent_host.assign(tree->parent, tree->parent + N);
-  h->brlen_host.assign(tree->brlen, tree->brlen + N);
   auto bail = [&](int code, const std::string &m) { std::string mm = m; elx_destroy(h); return fail(nullptr, code, mm); };
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return bail(ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
   CT(cudaSetDevice(dev));
@@ -717,7 +712,7 @@ void elx_destroy(elx_handle *h) {
   fast_tables_free(h);
   cudaFree(h->d_Q); cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
   cudaFree(h->d_e16); cudaFree(h->d_qlo); cudaFree(h->d_cumw); cudaFree(h->d_cumpi); cudaFree(h->d_walk);
-  cudaFree(h->d_error_flag); cudaFree(h->d_scratch); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
+  cudaFree(h->d_error_flag); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
   cudaFree(h->d_lut);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

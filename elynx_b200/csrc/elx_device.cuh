@@ -33,10 +33,6 @@ __host__ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
   return c;
 }
 
-__host__ __device__ __forceinline__ uint4 philox_rounds(uint4 c, uint2 k, int rounds) {
-  return rounds == 7 ? philox4x32<7>(c, k) : philox4x32<10>(c, k);
-}
-
 // 53-bit uniform in (0,1] from two Philox words (used for the component and root-state draws).
 __host__ __device__ __forceinline__ double u53_positive(uint32_t lo, uint32_t hi) {
   uint64_t w = ((uint64_t)hi << 32) | lo;

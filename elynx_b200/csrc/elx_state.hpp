@@ -18,7 +18,6 @@ struct elx_handle {
   uint32_t *d_qlo = nullptr;
   elx::WalkRec *d_walk = nullptr;
   int *d_error_flag = nullptr;
-  uint8_t *d_scratch = nullptr;
   // FASTA frame (names, offsets, alphabet LUT)
   uint8_t *d_names = nullptr, *d_lut = nullptr;
   int64_t *d_name_off = nullptr, *d_seq_off = nullptr;
@@ -26,9 +25,6 @@ struct elx_handle {
   std::string fasta_names_key;
   // tiled ("fast") kernel tables, owned by elx_fast.cu
   void *fast = nullptr;
-  std::vector<elx::WalkRec> walk_host;
-  std::vector<int32_t> leaf_row_host, parent_host;
-  std::vector<double> brlen_host;
   int64_t launches = 0;
   std::string last_error;
 };
