@@ -18,6 +18,7 @@ ELX_E_NOMEM = -4
 ELX_E_BAD_WEIGHTS = -5
 ELX_FLAG_FORCE_GENERIC = 1
 ELX_FLAG_PADE = 2
+ELX_FLAG_SINGLE_DRAWS = 4
 
 
 class ElxError(RuntimeError):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "elx_create": (C.c_int, [C.POINTER(elx_model), C.POINTER(elx_tree), C.POINTER(elx_opts), C.POINTER(_VP)]),
     "elx_destroy": (None, [_VP]),
     "elx_tree_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
+    "elx_tree_pair_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
     "elx_n_leaves": (_I32, [_VP]),
     "elx_n_nodes": (_I32, [_VP]),
     "elx_n_states": (_I32, [_VP]),
@@ -62,6 +64,8 @@ SIGNATURES = {
     "elx_ptables_set": (C.c_int, [_VP, _VP]),
     "elx_alias_columns": (_I32, [_VP]),
     "elx_alias_get": (C.c_int, [_VP, _VP, _VP]),
+    "elx_pair_groups": (_I32, [_VP]),
+    "elx_pair_get": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "elx_simulate": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_synchronize": (C.c_int, [_VP]),

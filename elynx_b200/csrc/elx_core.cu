@@ -261,6 +261,11 @@ __global__ void k1_alias(int64_t rows, int K, int A, const double *__restrict__ 
   }
 }
 
+void launch_k1_alias(elx_handle *h, int64_t rows, int K, int A, const double *P, uint16_t *e16, uint32_t *qlo) {
+  k1_alias<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(rows, K, A, P, e16, qlo);
+  h->launches++;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2 (injected-uniforms mode): one thread per site, reference semantics bit for bit.
 // categorical: cv = row-cumulative table; p = cv[K-1] * u (one rounded fp64 multiply); first i with cv[i] >= p.
@@ -517,6 +522,8 @@ static int build_tables_from_p(elx_handle *h, bool have_p) {
   CUDA_TRY(h, cudaGetLastError());
   int rc = fast_tables_build(h);
   if (rc) return rc;
+  rc = pair_tables_build(h);
+  if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -686,6 +693,12 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   CT(cudaMemcpy(h->d_cumpi, cumpi.data(), sizeof(double) * cumpi.size(), cudaMemcpyHostToDevice));
   CT(cudaMemcpy(h->d_walk, walk.recs.data(), sizeof(WalkRec) * N, cudaMemcpyHostToDevice));
 #undef CT
+  // Pair mode: with K <= 4 the free-running kernels draw the children of a node two at a time (elx_pair.cu).
+  if (K <= 4 && !(h->flags & ELX_FLAG_SINGLE_DRAWS)) {
+    std::string pmsg;
+    int prc = pair_create(h, tree->parent, tree->leaf_row, pmsg);
+    if (prc) { std::string m = pmsg.empty() ? h->last_error : pmsg; elx_destroy(h); return fail(nullptr, prc, m); }
+  }
   int rc = build_tables_from_p(h, false);
   if (rc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, rc, m); }
   *out = h;
@@ -705,11 +718,31 @@ int elx_tree_walk_info(const elx_tree *tree, int32_t *n_leaves, int32_t *n_slots
   return 0;
 }
 
+int elx_tree_pair_walk_info(const elx_tree *tree, int32_t *n_groups, int32_t *n_slots, int32_t *recs) {
+  if (!tree || tree->n_nodes < 1 || !tree->parent || !tree->leaf_row) return fail(nullptr, ELX_E_INVALID, "tree: empty or NULL arrays");
+  WalkProgram walk;
+  int T = 0;
+  std::string msg;
+  if (!compile_walk(tree->n_nodes, tree->parent, tree->leaf_row, walk, T, msg)) return fail(nullptr, ELX_E_INVALID, msg);
+  PairProgram pp;
+  compile_pair_walk(tree->n_nodes, tree->parent, tree->leaf_row, pp);
+  if (n_groups) *n_groups = (int32_t)pp.recs.size();
+  if (n_slots) *n_slots = pp.n_slots;
+  if (recs)
+    for (size_t g = 0; g < pp.recs.size(); ++g) {
+      const PairRec &r = pp.recs[g];
+      int32_t *o = recs + 7 * g;
+      o[0] = r.nodeA; o[1] = r.nodeB; o[2] = r.src; o[3] = r.dstA; o[4] = r.dstB; o[5] = r.leafA; o[6] = r.leafB;
+    }
+  return 0;
+}
+
 void elx_destroy(elx_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   fast_tables_free(h);
+  pair_free(h);
   cudaFree(h->d_Q); cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
   cudaFree(h->d_e16); cudaFree(h->d_qlo); cudaFree(h->d_cumw); cudaFree(h->d_cumpi); cudaFree(h->d_walk);
   cudaFree(h->d_error_flag); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
@@ -753,6 +786,14 @@ int elx_alias_get(elx_handle *h, uint16_t *e16, uint32_t *qlo) {
   return 0;
 }
 
+int32_t elx_pair_groups(const elx_handle *h) { return h ? pair_groups(h) : 0; }
+
+int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16, uint32_t *pqlo) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "elx_pair_get: null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return pair_get(h, node_a, node_b, pe16, pqlo);
+}
+
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves, int64_t leaves_pitch,
                         int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch) {
   int rc = check_sim_args(h, site0, nsites, d_leaves, leaves_pitch, d_internal, internal_pitch);
@@ -762,6 +803,12 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   SimArgs a = base_args(h);
   a.leaves = d_leaves; a.leaves_pitch = leaves_pitch; a.comps = d_comps; a.internal = d_internal;
   a.internal_pitch = internal_pitch; a.site0 = site0; a.nsites = nsites; a.seed = seed;
+  if (h->pair) {
+    int used = 0;
+    rc = pair_simulate(h, a, &used);
+    if (rc) return rc;
+    if (used) return 0;
+  }
   if (!(h->flags & ELX_FLAG_FORCE_GENERIC)) {
     int used = 0;
     rc = fast_simulate(h, a, &used);

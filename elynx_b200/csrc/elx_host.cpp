@@ -96,6 +96,81 @@ bool compile_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, W
   return true;
 }
 
+void compile_pair_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, PairProgram &out) {
+  const int N = n_nodes;
+  std::vector<std::vector<int>> kids(N);
+  for (int n = 1; n < N; ++n) kids[parent[n]].push_back(n);
+  std::vector<int64_t> size(N, 1);
+  for (int n = N - 1; n >= 1; --n) size[parent[n]] += size[n];
+  for (int n = 0; n < N; ++n)
+    std::stable_sort(kids[n].begin(), kids[n].end(), [&](int a, int b) { return size[a] < size[b]; });
+
+  out.recs.clear();
+  out.recs.reserve((size_t)N / 2 + 2);
+  std::vector<int> free_slots;
+  int high = 0;
+  auto alloc = [&]() {
+    if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
+    return high++;
+  };
+  // the groups of v: consecutive pairs of its size-sorted children; with an odd count the lightest child stands alone,
+  // so that the heaviest child is always in the last group
+  auto n_groups = [&](int v) { return (int)(kids[v].size() + 1) / 2; };
+  auto group = [&](int v, int gi, int &x, int &y) {
+    const std::vector<int> &k = kids[v];
+    const int odd = (int)k.size() & 1;
+    if (odd && gi == 0) { x = k[0]; y = -1; return; }
+    const int i = 2 * gi - odd;
+    x = k[i]; y = k[i + 1];
+  };
+  auto emit = [&](int A, int B, int src, int free_after_read) {
+    PairRec r;
+    r.nodeA = A; r.nodeB = B; r.src = (int16_t)src;
+    if (free_after_read >= 0) free_slots.push_back(free_after_read);  // the kernel reads src before it writes dstA/dstB
+    r.dstA = (int8_t)((!kids[A].empty() && n_groups(A) > 1) ? alloc() : -1);
+    r.dstB = (int8_t)((B >= 0 && !kids[B].empty()) ? alloc() : -1);
+    r.leafA = kids[A].empty() ? leaf_row[A] : -1;
+    r.leafB = (B >= 0 && kids[B].empty()) ? leaf_row[B] : -1;
+    out.recs.push_back(r);
+    return r;
+  };
+  struct Frame { int v, src_in, vs, gi, stage, A, B, dstA, dstB; };
+  std::vector<Frame> st;
+  {
+    PairRec r = emit(0, -1, -1, -1);
+    if (!kids[0].empty()) st.push_back(Frame{0, -1, r.dstA, 0, 0, 0, 0, 0, 0});
+  }
+  while (!st.empty()) {
+    Frame &f = st.back();
+    if (f.stage == 0) {
+      if (f.gi == n_groups(f.v)) { st.pop_back(); continue; }
+      int x, y;
+      group(f.v, f.gi, x, y);
+      int A = x, B = y;
+      if (y >= 0 && kids[x].empty() && !kids[y].empty()) { A = y; B = x; }  // the internal member continues in registers
+      const bool last = f.gi + 1 == n_groups(f.v);
+      const int src = f.gi == 0 ? f.src_in : f.vs;
+      PairRec r = emit(A, B, src, last ? f.vs : -1);
+      f.A = A; f.B = B; f.dstA = r.dstA; f.dstB = r.dstB;
+      f.stage = 1;
+    } else if (f.stage == 1) {
+      f.stage = 2;
+      if (!kids[f.A].empty()) {
+        Frame c{f.A, -1, f.dstA, 0, 0, 0, 0, 0, 0};
+        st.push_back(c);  // invalidates f
+      }
+    } else {
+      f.stage = 0;
+      f.gi++;
+      if (f.B >= 0 && !kids[f.B].empty()) {
+        Frame c{f.B, f.dstB, f.dstB, 0, 0, 0, 0, 0, 0};
+        st.push_back(c);
+      }
+    }
+  }
+  out.n_slots = high;
+}
+
 bool eigen_reversible(int K, const double *pi, const double *exch, double *lambda, double *A, double *B,
                       std::string &msg) {
   std::vector<double> S((size_t)K * K), V((size_t)K * K, 0.0), sq(K);

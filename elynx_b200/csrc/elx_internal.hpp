@@ -27,6 +27,27 @@ struct WalkProgram {
 bool compile_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, WalkProgram &out, int &n_leaves,
                   std::string &msg);
 
+// One step of the PAIR walk (models with K <= 4 states): the children of a node are drawn in groups of two from ONE joint
+// alias row indexed by the parent's state (16 outcomes = state A | state B << 2), which halves the draws per cell.
+// Member A is the one whose states stay in registers for the next record (an internal node; the lighter one when both
+// are internal), member B is pushed to a slot (internal) or written to its leaf row.  nodeB = -1: a group of one (the
+// root, the odd child of a multifurcation, the child of a unary node).
+struct PairRec {
+  int32_t nodeA, nodeB;
+  int16_t src;         // slot holding the parent's states; -1: registers (the previous record's member A, or the root states)
+  int8_t dstA, dstB;   // slot receiving A's / B's states, -1: none (A: only nodes with several groups need one)
+  int32_t leafA, leafB;  // output rows, -1 for internal nodes (and for an absent B)
+};
+
+struct PairProgram {
+  std::vector<PairRec> recs;
+  int n_slots = 0;
+};
+
+// Groups the children of every node (lightest first, the heaviest child in the last group) and orders the records so that
+// a record whose parent is the previous record's member A follows it directly.  Expects arrays compile_walk accepted.
+void compile_pair_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, PairProgram &out);
+
 // Symmetric eigen-decomposition (cyclic Jacobi) of S = D^{1/2} Q D^{-1/2}, Q = setDiagonal(E diag(pi)).
 // Produces lambda[K], A = D^{-1/2} V and B = V^T D^{1/2} so that exp(Qt) = I + A diag(expm1(lambda t)) B.
 bool eigen_reversible(int K, const double *pi, const double *exch, double *lambda, double *A, double *B,

@@ -25,11 +25,22 @@ struct elx_handle {
   std::string fasta_names_key;
   // tiled ("fast") kernel tables, owned by elx_fast.cu
   void *fast = nullptr;
+  // pair mode (K <= 4): joint two-children draws, owned by elx_pair.cu
+  void *pair = nullptr;
   int64_t launches = 0;
   std::string last_error;
 };
 
 namespace elx {
+
+// Device form of a PairRec (16 bytes, streamed through shared memory next to the group's alias rows).
+struct PairRecDev {
+  int32_t nodeA;
+  int16_t src;
+  int8_t dstA, dstB;
+  int32_t leafA, leafB;
+};
+static_assert(sizeof(PairRecDev) == 16, "PairRecDev must stay 16 bytes");
 
 struct SimArgs {
   int N, K, C, is_mixture, n_slots, A, rounds;
@@ -39,6 +50,12 @@ struct SimArgs {
   const double *cumpi;  // [C][K]
   const uint16_t *e16;  // [N][C][K][KP]
   const uint32_t *qlo;  // [N][C][K][KP]
+  // pair mode: G records in walk order, joint alias rows [G][C][K][16]
+  int G;
+  const PairRecDev *pairs;
+  const int32_t *pair_nodeB;
+  const uint16_t *pe16;
+  const uint32_t *pqlo;
   uint8_t *leaves;      // [T][leaves_pitch]
   int64_t leaves_pitch;
   int32_t *comps;       // [nsites] or null
@@ -57,5 +74,16 @@ int fail(elx_handle *h, int code, const std::string &msg);
 int fast_tables_build(elx_handle *h);
 void fast_tables_free(elx_handle *h);
 int fast_simulate(elx_handle *h, const SimArgs &a, int *used);
+
+// elx_pair.cu: pair mode (models with K <= 4 unless ELX_FLAG_SINGLE_DRAWS): the children of a node are drawn two at a time
+int pair_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row, std::string &msg);  // walk + buffers
+int pair_tables_build(elx_handle *h);                                                             // joint alias rows from d_P
+void pair_free(elx_handle *h);
+int pair_groups(const elx_handle *h);
+int pair_get(elx_handle *h, int32_t *nodeA, int32_t *nodeB, uint16_t *pe16, uint32_t *pqlo);
+int pair_simulate(elx_handle *h, SimArgs &a, int *used);
+
+// elx_core.cu
+void launch_k1_alias(elx_handle *h, int64_t rows, int K, int A, const double *P, uint16_t *e16, uint32_t *qlo);
 
 }  // namespace elx

@@ -33,7 +33,7 @@ class Simulator:
     alias tables and the compiled tree walk."""
 
     def __init__(self, weights, ds, es, tree, is_mixture: bool = True, device: int = -1, philox_rounds: int = 0,
-                 force_generic: bool = False, pade: bool = False):
+                 force_generic: bool = False, pade: bool = False, single_draws: bool = False):
         ds = np.ascontiguousarray(ds, dtype=np.float64)
         es = np.ascontiguousarray(es, dtype=np.float64)
         if ds.ndim == 1:
@@ -54,7 +54,8 @@ class Simulator:
                         ds.ctypes.data_as(C.POINTER(C.c_double)), es.ctypes.data_as(C.POINTER(C.c_double)))
         t = L.elx_tree(len(parent), parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
                        leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
-        o = L.elx_opts(device, philox_rounds, (L.ELX_FLAG_FORCE_GENERIC if force_generic else 0) | (L.ELX_FLAG_PADE if pade else 0), 0)
+        o = L.elx_opts(device, philox_rounds, (L.ELX_FLAG_FORCE_GENERIC if force_generic else 0) | (L.ELX_FLAG_PADE if pade else 0) |
+                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0), 0)
         h = C.c_void_p()
         self._h = None
         L.check(L.lib().elx_create(C.byref(m), C.byref(t), C.byref(o), C.byref(h)))
@@ -63,6 +64,7 @@ class Simulator:
         self.n_nodes = int(L.lib().elx_n_nodes(h))
         self.n_leaves = int(L.lib().elx_n_leaves(h))
         self.alias_columns = int(L.lib().elx_alias_columns(h))
+        self.pair_groups = int(L.lib().elx_pair_groups(h))  # > 0: K <= 4, sibling pairs are drawn jointly (elx_pair.cu)
 
     # -- lifetime --------------------------------------------------------------------------
     def close(self):
@@ -114,6 +116,19 @@ class Simulator:
         qlo = np.empty(shape, dtype=np.uint32)
         L.check(L.lib().elx_alias_get(self._h, _ptr(e16), _ptr(qlo)), self._h)
         return e16, qlo
+
+    def pair_tables(self):
+        """(node_a[G], node_b[G], pe16[G][C][K][16], pqlo[G][C][K][16]) of the pair-mode records, or None."""
+        g = self.pair_groups
+        if g == 0:
+            return None
+        node_a = np.empty(g, dtype=np.int32)
+        node_b = np.empty(g, dtype=np.int32)
+        shape = (g, self.n_components, self.n_states, 16)
+        pe16 = np.empty(shape, dtype=np.uint16)
+        pqlo = np.empty(shape, dtype=np.uint32)
+        L.check(L.lib().elx_pair_get(self._h, _ptr(node_a), _ptr(node_b), _ptr(pe16), _ptr(pqlo)), self._h)
+        return node_a, node_b, pe16, pqlo
 
     # -- simulation ----------------------------------------------------------------------------
     def simulate(self, seed: int, nsites: int, site0: int = 0, want_comps: bool = False, keep_internal: bool = False):

@@ -79,6 +79,8 @@ typedef struct {
 } elx_opts;
 
 #define ELX_FLAG_FORCE_GENERIC 1 /* always use the generic global-table kernel (cross-check of the tiled one) */
+#define ELX_FLAG_SINGLE_DRAWS 4  /* models with K <= 4: draw node by node (one alias row per node) instead of the default joint
+                                    draw of sibling pairs; a different (equally exact) free-running stream */
 #define ELX_FLAG_PADE 2          /* build P(t) by the scaled Pade-7 + squaring kernel (hmatrix `expm`'s algorithm) instead of
                                     the eigen form; taken automatically for non-reversible components */
 
@@ -96,6 +98,11 @@ void elx_destroy(elx_handle *h);
  * and of live state slots the walk needs (<= floor(log2 N) + 1 for any tree).  walk_nodes (optional, [N]) receives the
  * visiting order as preorder node indices. */
 int elx_tree_walk_info(const elx_tree *tree, int32_t *n_leaves, int32_t *n_slots, int32_t *walk_nodes);
+
+/* Host-only: the pair walk (see elx_pair_groups below) of a tree: number of records, live state slots, and the records
+ * themselves, 7 int32 each: node_a, node_b (-1: group of one), src slot (-1: registers), dst slot of a / of b (-1: none),
+ * leaf row of a / of b (-1: internal).  recs (optional) must hold 7 * n_nodes values (there are at most n_nodes records). */
+int elx_tree_pair_walk_info(const elx_tree *tree, int32_t *n_groups, int32_t *n_slots, int32_t *recs);
 
 int32_t elx_n_leaves(const elx_handle *h);
 int32_t elx_n_nodes(const elx_handle *h);
@@ -115,6 +122,14 @@ int elx_ptables_set(elx_handle *h, const double *p);
  * KP = elx_alias_columns(h).  See DESIGN.md "free-running draw". */
 int32_t elx_alias_columns(const elx_handle *h);
 int elx_alias_get(elx_handle *h, uint16_t *e16, uint32_t *qlo);
+
+/* Pair mode (models with at most 4 states, unless ELX_FLAG_SINGLE_DRAWS): siblings are independent given their parent, so
+ * the free-running kernels draw the children of a node two at a time from the joint row P_A[i][sa] * P_B[i][sb]
+ * (16 outcomes, o = sa | sb << 2) -- one draw per alignment cell instead of two.  elx_pair_groups: number of records G
+ * (0 = the handle draws node by node).  elx_pair_get: the records in walk order (node_a[G], node_b[G], -1 = a group of
+ * one) and their alias rows pe16 / pqlo [G][C][K][16] ([threshold high bits : 12][alias : 4] / 32 low threshold bits). */
+int32_t elx_pair_groups(const elx_handle *h);
+int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16, uint32_t *pqlo);
 
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
  * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed); the result is a

@@ -14,6 +14,12 @@
  *                         j = x16 & (KP-1); r = x16 >> A; e = e16[n][c][parent][j]
  *                         r < e>>A -> j ;  r > e>>A -> alias = e & (KP-1) ;
  *                         tie -> y = philox(s lo, s hi, n, 1).x0 ;  y < qlo[n][c][parent][j] ? j : alias
+ *
+ * Pair mode (models with K <= 4; elynx_b200/csrc/elx_pair.cu): the children of a node are drawn two at a time from the
+ * joint row of record g = (nodeA, nodeB | parent), 16 outcomes o = state(nodeA) | state(nodeB) << 2:
+ *   x16 as above with n = nodeA;  j = x16 & 15; r = x16 >> 4; e = pe16[g][c][parent state][j]
+ *   r < e>>4 -> o = j ;  r > e>>4 -> o = e & 15 ;  tie -> philox(s lo, s hi, nodeA, 1).x0 < pqlo[g][c][parent state][j] ? j : e & 15
+ * Records come in walk order (a record's parent is drawn by an earlier record; node_b = -1 for a group of one).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -88,5 +94,62 @@ int spec_freerun(int N, int K, int C, int is_mixture, int A, int rounds, const i
     }
   }
   free(st);
+  return 0;
+}
+
+int spec_freerun_pair(int N, int K, int C, int is_mixture, int rounds, const int32_t *parent, const int32_t *leaf_row,
+                      const double *cumw, const double *cumpi, int G, const int32_t *node_a, const int32_t *node_b,
+                      const uint16_t *pe16, const uint32_t *pqlo, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves,
+                      int64_t leaves_pitch, int32_t *comps, uint8_t *internal, int64_t internal_pitch) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint8_t *st = (uint8_t *)malloc((size_t)N);
+  uint8_t *done = (uint8_t *)malloc((size_t)N);
+  for (int64_t col = 0; col < nsites; ++col) {
+    uint64_t s = (uint64_t)(site0 + col);
+    int c = 0;
+    if (is_mixture) {
+      uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 2};
+      philox(rounds, x, k0, k1);
+      uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+      c = cat_cum(cumw, C, (double)((w >> 11) + 1) * 0x1p-53);
+      if (c < 0) { free(st); free(done); return -(N + 1); }
+    }
+    if (comps) comps[col] = c;
+    uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 3};
+    philox(rounds, x, k0, k1);
+    uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+    int root = cat_cum(cumpi + (int64_t)c * K, K, (double)((w >> 11) + 1) * 0x1p-53);
+    if (root < 0) { free(st); free(done); return -(N + 2); }
+    for (int n = 0; n < N; ++n) done[n] = 0;
+    for (int g = 0; g < G; ++g) {
+      const int nA = node_a[g], nB = node_b[g];
+      if (nA < 0 || nA >= N || nB >= N || done[nA] || (nB >= 0 && (done[nB] || parent[nB] != parent[nA]))) { free(st); free(done); return -1; }
+      if (parent[nA] >= 0 && !done[parent[nA]]) { free(st); free(done); return -2; }  /* not in walk order */
+      int par = parent[nA] < 0 ? root : st[parent[nA]];
+      uint64_t gg = s >> 3;
+      uint32_t y[4] = {(uint32_t)gg, (uint32_t)(gg >> 32), (uint32_t)nA, 0};
+      philox(rounds, y, k0, k1);
+      int f = (int)(s & 7);
+      uint32_t x16 = (y[f >> 1] >> ((f & 1) * 16)) & 0xffffu;
+      uint32_t j = x16 & 15u, r = x16 >> 4;
+      int64_t idx = ((((int64_t)g * C + c) * K) + par) * 16 + j;
+      uint32_t e = pe16[idx], qh = e >> 4, al = e & 15u, o;
+      if (r < qh) o = j;
+      else if (r > qh) o = al;
+      else {
+        uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)nA, 1};
+        philox(rounds, z, k0, k1);
+        o = z[0] < pqlo[idx] ? j : al;
+      }
+      st[nA] = (uint8_t)(o & 3u); done[nA] = 1;
+      if (nB >= 0) { st[nB] = (uint8_t)(o >> 2); done[nB] = 1; }
+    }
+    for (int n = 0; n < N; ++n) {
+      if (!done[n]) { free(st); free(done); return -3; }
+      if (leaf_row[n] >= 0) leaves[(int64_t)leaf_row[n] * leaves_pitch + col] = st[n];
+      if (internal) internal[(int64_t)n * internal_pitch + col] = st[n];
+    }
+  }
+  free(st); free(done);
   return 0;
 }

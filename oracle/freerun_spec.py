@@ -26,6 +26,7 @@ def lib():
             build()
         _lib = C.CDLL(_SO)
         _lib.spec_freerun.restype = C.c_int
+        _lib.spec_freerun_pair.restype = C.c_int
     return _lib
 
 
@@ -42,6 +43,34 @@ def alias_bits(k):
     while (1 << a) < k:
         a += 1
     return max(a, 2)
+
+
+def freerun_pair(is_mixture, parent, leaf_row, ws, ds, pair, seed, site0, nsites, rounds=10, keep_internal=False):
+    """Pair mode (K <= 4): pair = (node_a[G], node_b[G], pe16[G][C][K][16], pqlo[G][C][K][16]) in walk order."""
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+    node_a = np.ascontiguousarray(pair[0], dtype=np.int32)
+    node_b = np.ascontiguousarray(pair[1], dtype=np.int32)
+    pe16 = np.ascontiguousarray(pair[2], dtype=np.uint16)
+    pqlo = np.ascontiguousarray(pair[3], dtype=np.uint32)
+    g, c, k, cols = pe16.shape
+    assert cols == 16 and pqlo.shape == pe16.shape and node_a.shape == (g,) and node_b.shape == (g,)
+    n = len(parent)
+    cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
+    cumpi = np.ascontiguousarray(np.cumsum(np.asarray(ds, dtype=np.float64).reshape(c, k), axis=1))
+    t = int((leaf_row >= 0).sum())
+    leaves = np.zeros((t, max(nsites, 1)), dtype=np.uint8)
+    comps = np.zeros(max(nsites, 1), dtype=np.int32)
+    internal = np.zeros((n, max(nsites, 1)), dtype=np.uint8) if keep_internal else None
+    vp = C.c_void_p
+    rc = lib().spec_freerun_pair(n, k, c, int(bool(is_mixture)), rounds, vp(parent.ctypes.data), vp(leaf_row.ctypes.data),
+                                 vp(cumw.ctypes.data), vp(cumpi.ctypes.data), g, vp(node_a.ctypes.data), vp(node_b.ctypes.data),
+                                 vp(pe16.ctypes.data), vp(pqlo.ctypes.data), C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0),
+                                 C.c_int64(nsites), vp(leaves.ctypes.data), C.c_int64(max(nsites, 1)), vp(comps.ctypes.data),
+                                 vp(internal.ctypes.data) if keep_internal else None, C.c_int64(max(nsites, 1)))
+    if rc:
+        raise RuntimeError("spec_freerun_pair rc=%d" % rc)
+    return leaves[:, :nsites], comps[:nsites], (internal[:, :nsites] if keep_internal else None)
 
 
 def freerun(is_mixture, parent, leaf_row, ws, ds, e16, qlo, seed, site0, nsites, rounds=10, keep_internal=False):

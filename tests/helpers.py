@@ -63,3 +63,57 @@ def uniforms(rng, rows, s):
     """doubles in (0,1] like uniformDoublePositive01M: w64/2^64 + 2^-65"""
     w = rng.integers(0, 2 ** 64, size=(rows, s), dtype=np.uint64)
     return w.astype(np.float64) / 18446744073709551616.0 + 2.0 ** -65
+
+
+def spec_freerun(sim, model, tree, seed, site0, s, **kw):
+    """The executable spec of the product's free-running draw for this handle, run on the handle's own tables:
+    pair mode (K <= 4: sibling pairs drawn jointly) or node by node."""
+    import oracle.freerun_spec as spec
+
+    is_mix, ws, ds = model[0], model[1], model[2]
+    pair = sim.pair_tables()
+    if pair is not None:
+        return spec.freerun_pair(is_mix, tree.parent, tree.leaf_row, ws, ds, pair, seed, site0, s, **kw)
+    e16, qlo = sim.alias_tables()
+    return spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, seed, site0, s, **kw)
+
+
+def alias_masses(e, qlo, a):
+    """Integer outcome masses (sum 2^48 per row) encoded by alias rows e = [q_hi : 16-a][alias : a], qlo."""
+    kp = 1 << a
+    cap = 1 << (48 - a)
+    e = e.astype(np.int64)
+    al = e & (kp - 1)
+    q = ((e >> a) << 32) | qlo.astype(np.int64)
+    q = np.where(al == np.arange(kp), cap, q)  # alias == self means "always accept"
+    mass = np.zeros(e.shape, dtype=np.int64)
+    for j in range(kp):
+        mass[..., j] += q[..., j]
+        np.put_along_axis(mass, al[..., j:j + 1], np.take_along_axis(mass, al[..., j:j + 1], -1) + (cap - q[..., j:j + 1]), -1)
+    return mass
+
+
+def check_pair_tables(p, pair, parent):
+    """Every non-root node is in exactly one record, members of a record are siblings, records are in walk order, and
+    the joint rows carry integer masses (sum 2^48) equal to P_A[i][sa] * P_B[i][sb] (normalised) within 2^-44."""
+    node_a, node_b, pe16, pqlo = pair
+    n, c, k, _ = p.shape
+    seen = np.zeros(n, dtype=bool)
+    for g, (a, b) in enumerate(zip(node_a, node_b)):
+        assert 0 <= a < n and not seen[a] and (parent[a] < 0 or seen[parent[a]])
+        seen[a] = True
+        if b >= 0:
+            assert not seen[b] and parent[b] == parent[a]
+            seen[b] = True
+    assert seen.all()
+    assert node_a[0] == 0 and node_b[0] == -1
+    mass = alias_masses(pe16, pqlo, 4)
+    assert np.all(mass.sum(-1) == 1 << 48)
+    pn = p / p.sum(-1, keepdims=True)
+    pa = pn[node_a]  # [G][C][K][K]
+    pb = np.where((node_b >= 0)[:, None, None, None], pn[np.maximum(node_b, 0)], (np.arange(k) == 0).astype(float))
+    joint = np.zeros(pe16.shape)
+    for sa in range(k):
+        for sb in range(k):
+            joint[..., sa | (sb << 2)] = pa[..., sa] * pb[..., sb]
+    assert np.max(np.abs(mass / float(1 << 48) - joint)) < 2.0 ** -44

@@ -135,3 +135,91 @@ def test_walk_program_slot_bound():
         pos[order] = np.arange(n)
         assert all(pos[parent[i]] < pos[i] for i in range(1, n))
         assert ns <= int(math.floor(math.log2(n))) + 1 if n > 1 else ns == 1, (n, ns)
+
+
+def test_pair_walk_program():
+    """Pair walk (K <= 4 models): every node in exactly one record, members are siblings, a record's parent is drawn
+    earlier, src = -1 only right after the record that drew the parent as member A, slots are written before they are
+    read and never clobbered while live, and the live-slot count stays logarithmic for binary trees."""
+    import ctypes as C
+    import math
+
+    from elynx_b200 import model as pm
+
+    rng = np.random.default_rng(5)
+    cases = []
+    for n, seed in ((1000, 1), (10000, 3), (3, 0), (2, 0), (257, 9)):
+        t = pm.birth_death_tree(n, 1.0, 0.5, seed=seed)
+        cases.append((np.asarray(t.parent), np.asarray(t.leaf_row), True))
+    cases.append((np.array([-1]), np.array([0]), True))
+    # random multifurcating / unary trees in preorder
+    for _ in range(20):
+        parent, kids = [-1], {0: 0}
+        n = int(rng.integers(2, 200))
+        stack = [0]
+        while len(parent) < n:
+            p = stack[-1]
+            if rng.random() < 0.35 and len(stack) > 1:
+                stack.pop()
+                continue
+            parent.append(p)
+            kids[p] = kids.get(p, 0) + 1
+            stack.append(len(parent) - 1)
+        parent = np.array(parent)
+        is_leaf = np.ones(len(parent), dtype=bool)
+        is_leaf[parent[1:]] = False
+        leaf_row = np.where(is_leaf, np.cumsum(is_leaf) - 1, -1)
+        cases.append((parent, leaf_row, False))
+    for parent, leaf_row, binary in cases:
+        n = len(parent)
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+        brlen = np.zeros(n)
+        t = L.elx_tree(n, parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
+                       leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
+        ng, ns = C.c_int32(), C.c_int32()
+        recs = np.full((n, 7), -99, dtype=np.int32)
+        L.check(L.lib().elx_tree_pair_walk_info(C.byref(t), C.byref(ng), C.byref(ns), C.c_void_p(recs.ctypes.data)))
+        recs = recs[:ng.value]
+        nchild = np.bincount(parent[1:], minlength=n)
+        drawn = np.zeros(n, dtype=bool)
+        slot_owner = {}  # slot -> node whose states it holds
+        reads_left = {}  # node -> records that still have to read its slot
+        prev_a = None
+        for g, (a, b, src, dst_a, dst_b, leaf_a, leaf_b) in enumerate(recs.tolist()):
+            assert not drawn[a] and (b < 0 or (not drawn[b] and parent[b] == parent[a]))
+            par = parent[a]
+            if g == 0:
+                assert a == 0 and b == -1 and src == -1
+            elif src == -1:
+                assert par == prev_a, "registers hold the previous record's member A"
+            else:
+                assert slot_owner.get(src) == par, "slot must still hold the parent's states"
+            if par >= 0:
+                assert drawn[par]
+                reads_left[par] -= 1
+                if reads_left[par] == 0:
+                    for s_, o in list(slot_owner.items()):
+                        if o == par:
+                            del slot_owner[s_]
+            for node, dst, leaf in ((a, dst_a, leaf_a), (b, dst_b, leaf_b)):
+                if node < 0:
+                    assert dst == -1 and leaf == -1
+                    continue
+                drawn[node] = True
+                assert leaf == (leaf_row[node] if nchild[node] == 0 else -1)
+                groups = (nchild[node] + 1) // 2
+                reads_left[node] = groups
+                if dst >= 0:
+                    assert nchild[node] > 0 and dst not in slot_owner, "would clobber a live slot"
+                    slot_owner[dst] = node
+                    assert dst < ns.value
+            if nchild[a] > 0:
+                assert dst_a >= 0 or (nchild[a] + 1) // 2 == 1
+            if b >= 0 and nchild[b] > 0:
+                assert dst_b >= 0
+            prev_a = a if nchild[a] > 0 else None
+        assert drawn.all() and not slot_owner
+        if binary and n > 1:
+            assert ng.value == (n - 1) // 2 + 1
+            assert ns.value <= int(math.floor(math.log2(n))) + 1, (n, ns.value)

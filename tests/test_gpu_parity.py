@@ -7,7 +7,7 @@ import oracle.freerun_spec as spec
 import oracle.model as om
 import oracle.pruning as pruning
 import oracle.sim as osim
-from helpers import model_case, random_tree, tree_from_file, uniforms
+from helpers import alias_masses, check_pair_tables, model_case, random_tree, spec_freerun, tree_from_file, uniforms
 
 pytestmark = pytest.mark.gpu
 
@@ -143,19 +143,7 @@ def test_injected_bad_weights_is_an_error():
 # ---------------------------------------------------------------------------------------------
 def check_alias_tables(p, e16, qlo, k):
     """The alias tables encode integer masses m_i with sum 2^48 and m_i / 2^48 == p_i / sum(p) within 2^-45."""
-    a = spec.alias_bits(k)
-    kp = 1 << a
-    cap = 1 << (48 - a)
-    e = e16.astype(np.int64)
-    qh = e >> a
-    al = e & (kp - 1)
-    q = (qh << 32) | qlo.astype(np.int64)
-    self_col = al == np.arange(kp)
-    q = np.where(self_col, cap, q)  # alias == self means "always accept"
-    mass = np.zeros(p.shape[:-1] + (kp,), dtype=np.int64)
-    for j in range(kp):
-        mass[..., j] += q[..., j]
-        np.put_along_axis(mass, al[..., j:j + 1], np.take_along_axis(mass, al[..., j:j + 1], -1) + (cap - q[..., j:j + 1]), -1)
+    mass = alias_masses(e16, qlo, spec.alias_bits(k))
     assert np.all(mass.sum(-1) == 1 << 48)
     assert np.all(mass[..., k:] == 0)
     pn = p / p.sum(-1, keepdims=True)
@@ -166,19 +154,57 @@ def check_alias_tables(p, e16, qlo, k):
                                              ("lg_g4", "UltraMetric.tree", 3000), ("c10", "UltraMetric.tree", 2000),
                                              ("mixture_dna", "Newick.tree", 2000), ("c60", "UltraMetric.tree", 9000),
                                              ("c60", "Newick.tree", 1000)])
-@pytest.mark.parametrize("force_generic", [True, False])
-def test_freerun_matches_spec(name, tree_file, s, force_generic):
+@pytest.mark.parametrize("force_generic,single_draws", [(True, False), (False, False), (True, True), (False, True)])
+def test_freerun_matches_spec(name, tree_file, s, force_generic, single_draws):
+    """Every free-running kernel (generic / tiled; pair mode / node by node) against the executable spec, on the
+    device's own tables, which are themselves checked against the P rows in exact integer arithmetic."""
     model = model_case(name)
     is_mix, ws, ds, es, _ = model
+    k = ds.shape[1]
+    if single_draws and k > 4:
+        pytest.skip("single_draws only changes models with K <= 4")
     tree = tree_from_file(tree_file)
-    with make_sim(model, tree, force_generic=force_generic) as sim:
+    with make_sim(model, tree, force_generic=force_generic, single_draws=single_draws) as sim:
         e16, qlo = sim.alias_tables()
-        check_alias_tables(sim.ptables(), e16, qlo, ds.shape[1])
+        check_alias_tables(sim.ptables(), e16, qlo, k)
+        assert (sim.pair_groups > 0) == (k <= 4 and not single_draws)
+        if sim.pair_groups:
+            check_pair_tables(sim.ptables(), sim.pair_tables(), tree.parent)
         for seed, site0 in ((0, 0), (0xDEADBEEFCAFEF00D, 0), (7, 8 * 1000003), (7, 13)):
             leaves, comps, internal = sim.simulate(seed, s, site0=site0, want_comps=True, keep_internal=True)
-            l0, c0, i0 = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, seed, site0, s, keep_internal=True)
-            assert np.array_equal(leaves, l0), (seed, site0)
-            assert np.array_equal(comps, c0) and np.array_equal(internal, i0)
+            l0, c0, i0 = spec_freerun(sim, model, tree, seed, site0, s, keep_internal=True)
+            assert np.array_equal(internal, i0), (seed, site0)
+            assert np.array_equal(leaves, l0) and np.array_equal(comps, c0)
+            leaves2, comps2, _ = sim.simulate(seed, s, site0=site0, want_comps=True)  # the tiled kernels keep no internal states
+            assert np.array_equal(leaves2, l0) and np.array_equal(comps2, c0)
+
+
+@pytest.mark.parametrize("shape", ["multifurcating", "caterpillar", "unary", "single", "cherry"])
+def test_pair_walk_odd_trees(shape):
+    """Pair mode on trees that are not binary: groups of one, several groups per node, a node that is root and leaf."""
+    rng = np.random.default_rng(11)
+    model = model_case("hky_g4")
+    if shape == "multifurcating":
+        tree = random_tree(37, rng, multifurcate=True, zero_frac=0.2)
+    elif shape == "caterpillar":
+        s_ = "t0:0.1"
+        for i in range(1, 70):
+            s_ = "(%s,t%d:0.05):0.02" % (s_, i)
+        tree = om.parse_newick(s_ + ";")
+    elif shape == "unary":
+        tree = om.parse_newick("(((a:0.1):0.2,(b:0.3,c:0.1,d:0.2,e:0.4,f:0.01):0.1):0.3);")
+    elif shape == "single":
+        tree = om.parse_newick("a:0.3;")
+    else:
+        tree = om.parse_newick("(a:0.1,b:0.2):0.5;")
+    for fg in (True, False):
+        with make_sim(model, tree, force_generic=fg) as sim:
+            check_pair_tables(sim.ptables(), sim.pair_tables(), tree.parent)
+            for s, site0 in ((4099, 0), (1000, 77)):
+                leaves, comps, internal = sim.simulate(5, s, site0=site0, want_comps=True, keep_internal=True)
+                l0, c0, i0 = spec_freerun(sim, model, tree, 5, site0, s, keep_internal=True)
+                assert np.array_equal(internal, i0) and np.array_equal(leaves, l0) and np.array_equal(comps, c0)
+                assert np.array_equal(sim.simulate(5, s, site0=site0)[0], l0)
 
 
 def test_freerun_refinement_path_is_exercised():
@@ -187,12 +213,12 @@ def test_freerun_refinement_path_is_exercised():
     model = model_case("hky")
     is_mix, ws, ds, es, _ = model
     tree = om.parse_newick("(" + ",".join("t%d:0.013" % i for i in range(64)) + ");")
-    with make_sim(model, tree) as sim:
-        e16, qlo = sim.alias_tables()
-        s = 200000
-        leaves, _, _ = sim.simulate(3, s)
-        l0, _, _ = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, 3, 0, s)
-        assert np.array_equal(leaves, l0)
+    for single in (False, True):
+        with make_sim(model, tree, single_draws=single) as sim:
+            s = 200000
+            leaves, _, _ = sim.simulate(3, s)
+            l0, _, _ = spec_freerun(sim, model, tree, 3, 0, s)
+            assert np.array_equal(leaves, l0)
 
 
 def test_freerun_partition_invariance():
@@ -460,9 +486,8 @@ def test_non_reversible_models(kind):
         leaves, _, internal = sim.simulate_injected(u, keep_internal=True)
         _, l0, i0 = osim.simulate_injected(False, tree.parent, tree.leaf_row, np.ones(1), ds, p, u, keep_internal=True)
         assert np.array_equal(leaves, l0) and np.array_equal(internal, i0)
-        e16, qlo = sim.alias_tables()
         fr = sim.simulate(4, 3000)[0]
-        l1, _, _ = spec.freerun(False, tree.parent, tree.leaf_row, np.ones(1), ds, e16, qlo, 4, 0, 3000)
+        l1, _, _ = spec_freerun(sim, (False, np.ones(1), ds), tree, 4, 0, 3000)
         assert np.array_equal(fr, l1)
         if kind != "asymmetric":
             dead = np.nonzero(ds[0] == 0)[0]
@@ -480,10 +505,9 @@ def test_philox7_option_matches_spec(name, tree_file):
     outs = []
     for fg in (True, False):
         with make_sim(model, tree, force_generic=fg, philox_rounds=7) as sim:
-            e16, qlo = sim.alias_tables()
             leaves, comps, _ = sim.simulate(21, s, site0=32, want_comps=True)
             outs.append(leaves)
-    l0, c0, _ = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, 21, 32, s, rounds=7)
+            l0, c0, _ = spec_freerun(sim, model, tree, 21, 32, s, rounds=7)
+            l10, _, _ = spec_freerun(sim, model, tree, 21, 32, s, rounds=10)
     assert np.array_equal(outs[0], l0) and np.array_equal(outs[1], l0) and np.array_equal(comps, c0)
-    l10, _, _ = spec.freerun(is_mix, tree.parent, tree.leaf_row, ws, ds, e16, qlo, 21, 32, s, rounds=10)
     assert not np.array_equal(l10, l0)
