@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128, 4) k2_pair_tiled(PairArgs fa) {
         if (store_mode) store_leaf(a, leaf_base, leafA, col0, store_mode, make_uint4(by[0] & SM, by[1] & SM, by[2] & SM, by[3] & SM));
       } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) par[q] = (c2[q] & 0x00030003u) * 32u + cbase[q];
+        for (int q = 0; q < 8; ++q) par[q] = ((c2[q] << 5) & 0x00600060u) | cbase[q];
         if (dstA >= 0) sts_v4(slot_base + (uint32_t)dstA * slot_stride, make_uint4(by[0] & SM, by[1] & SM, by[2] & SM, by[3] & SM));
       }
       if (leafB >= 0) {

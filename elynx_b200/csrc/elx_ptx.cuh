@@ -56,17 +56,24 @@ __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, dou
   return -1;
 }
 
+// Byte stores of a partial 16-site group (first / last group of a site range, unaligned buffers).  Rolled on purpose:
+// unrolled, ptxas hoists the 16 64-bit column-bound predicates above the mode branch and every node pays for them.
+__device__ __forceinline__ void store_leaf_bytes(uint8_t *dstp, int64_t col0, int64_t nsites, uint4 o) {
+#pragma unroll 1
+  for (int i = 0; i < 16; ++i) {
+    const int64_t col = col0 + i;
+    const uint32_t wv = i < 8 ? (i < 4 ? o.x : o.y) : (i < 12 ? o.z : o.w);
+    if (col >= 0 && col < nsites) dstp[i] = (uint8_t)(wv >> ((i & 3) * 8));
+  }
+}
+
 __device__ __forceinline__ void store_leaf(const SimArgs &a, uint8_t *leaf_base, int leaf_row, int64_t col0, int store_mode,
                                            uint4 o) {
   uint8_t *dstp = leaf_base + (int64_t)leaf_row * a.leaves_pitch;
   if (store_mode == 1) {
     stg_cs_v4(dstp, o);  // 32 lanes x 16 B = 512 contiguous bytes of the [taxon][site] row, streaming (evict-first)
   } else {
-    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-    for (int i = 0; i < 16; ++i) {
-      int64_t col = col0 + i;
-      if (col >= 0 && col < a.nsites) dstp[i] = (uint8_t)(ow[i >> 2] >> ((i & 3) * 8));
-    }
+    store_leaf_bytes(dstp, col0, a.nsites, o);
   }
 }
 
