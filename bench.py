@@ -202,7 +202,7 @@ def run_product(args):
 
     sim = eb.Simulator(model.weights if model.is_mixture else None, model.pi, model.exch, tree, is_mixture=model.is_mixture,
                        device=local_rank, force_generic=args.force_generic, philox_rounds=args.philox_rounds,
-                       single_draws=args.single_draws)
+                       single_draws=args.single_draws, pair_draws=args.pair_draws)
     stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
     d_leaves = torch.empty((T, pitch), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
@@ -266,7 +266,7 @@ def run_product(args):
         def e2e_step():
             s2 = eb.Simulator(model.weights if model.is_mixture else None, model.pi, model.exch, tree, is_mixture=model.is_mixture,
                               device=local_rank, force_generic=args.force_generic, philox_rounds=args.philox_rounds,
-                              single_draws=args.single_draws)
+                              single_draws=args.single_draws, pair_draws=args.pair_draws)
             L.check(L.lib().elx_simulate(s2.handle, C.c_uint64(seed), site0, e2e_sites, C.c_void_p(hnp.ctypes.data), e2e_sites, None, None, 0),
                     s2.handle)
             n = s2.launch_count
@@ -306,7 +306,8 @@ def run_product(args):
                    "components": model.n_components, "parallelism": "site-range sharding x%d, no data-path collective" % world,
                    "l2": "output %d MB per step >> 126 MB L2, no flush needed" % (T * sites // 2 ** 20),
                    "kernel": "generic" if args.force_generic else "auto",
-                   "draws": "joint sibling pairs" if sim.pair_groups else "node by node", "philox_rounds": args.philox_rounds or 10},
+                   "draws": ("one draw per cap of <= 4 frontier nodes (inner nodes summed out), %d draws per site" % sim.quad_groups) if sim.quad_groups
+                   else ("joint sibling pairs" if sim.pair_groups else "node by node"), "philox_rounds": args.philox_rounds or 10},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": T * sites, "kernel_ms": kms,
                      "note": "1 byte per alignment cell (uint8 leaf state written once); CUDA events on the handle's stream; "
@@ -345,6 +346,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--single-draws", action="store_true", help="K <= 4 models: node-by-node draws instead of joint sibling pairs (A/B runs)")
+    ap.add_argument("--pair-draws", action="store_true", help="K <= 4 models: joint sibling pairs instead of quad mode (A/B runs)")
     ap.add_argument("--philox-rounds", type=int, default=0, choices=[0, 7, 10], help="0 = library default (10)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "product" and not args.sites:

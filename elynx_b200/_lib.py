@@ -19,6 +19,8 @@ ELX_E_BAD_WEIGHTS = -5
 ELX_FLAG_FORCE_GENERIC = 1
 ELX_FLAG_PADE = 2
 ELX_FLAG_SINGLE_DRAWS = 4
+ELX_FLAG_PAIR_DRAWS = 8
+ELX_QUAD_REC_INTS = 52
 
 
 class ElxError(RuntimeError):
@@ -66,6 +68,9 @@ SIGNATURES = {
     "elx_alias_get": (C.c_int, [_VP, _VP, _VP]),
     "elx_pair_groups": (_I32, [_VP]),
     "elx_pair_get": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "elx_quad_groups": (_I32, [_VP]),
+    "elx_quad_get": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "elx_tree_quad_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
     "elx_simulate": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_synchronize": (C.c_int, [_VP]),

@@ -524,6 +524,8 @@ static int build_tables_from_p(elx_handle *h, bool have_p) {
   if (rc) return rc;
   rc = pair_tables_build(h);
   if (rc) return rc;
+  rc = quad_tables_build(h);
+  if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -699,6 +701,11 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
     int prc = pair_create(h, tree->parent, tree->leaf_row, pmsg);
     if (prc) { std::string m = pmsg.empty() ? h->last_error : pmsg; elx_destroy(h); return fail(nullptr, prc, m); }
   }
+  // Quad mode on top of it (leaves-only calls): one draw per cap of up to 4 frontier nodes (elx_quad.cu).
+  if (K <= 4 && !(h->flags & (ELX_FLAG_SINGLE_DRAWS | ELX_FLAG_PAIR_DRAWS))) {
+    int qrc = quad_create(h, tree->parent, tree->leaf_row);
+    if (qrc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, qrc, m); }
+  }
   int rc = build_tables_from_p(h, false);
   if (rc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, rc, m); }
   *out = h;
@@ -737,12 +744,28 @@ int elx_tree_pair_walk_info(const elx_tree *tree, int32_t *n_groups, int32_t *n_
   return 0;
 }
 
+int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs) {
+  if (!tree || tree->n_nodes < 1 || !tree->parent || !tree->leaf_row) return fail(nullptr, ELX_E_INVALID, "tree: empty or NULL arrays");
+  WalkProgram walk;
+  int T = 0;
+  std::string msg;
+  if (!compile_walk(tree->n_nodes, tree->parent, tree->leaf_row, walk, T, msg)) return fail(nullptr, ELX_E_INVALID, msg);
+  QuadProgram qp;
+  compile_quad_walk(tree->n_nodes, tree->parent, tree->leaf_row, qp);
+  if (n_records) *n_records = (int32_t)qp.recs.size();
+  if (n_slots) *n_slots = qp.n_slots;
+  if (recs)
+    for (size_t g = 0; g < qp.recs.size(); ++g) quad_rec_to_ints(qp.recs[g], recs + g * ELX_QUAD_REC_INTS);
+  return 0;
+}
+
 void elx_destroy(elx_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   fast_tables_free(h);
   pair_free(h);
+  quad_free(h);
   cudaFree(h->d_Q); cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
   cudaFree(h->d_e16); cudaFree(h->d_qlo); cudaFree(h->d_cumw); cudaFree(h->d_cumpi); cudaFree(h->d_walk);
   cudaFree(h->d_error_flag); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
@@ -794,6 +817,14 @@ int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16
   return pair_get(h, node_a, node_b, pe16, pqlo);
 }
 
+int32_t elx_quad_groups(const elx_handle *h) { return h ? quad_groups(h) : 0; }
+
+int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "elx_quad_get: null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return quad_get(h, recs, qe32, qlo16);
+}
+
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves, int64_t leaves_pitch,
                         int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch) {
   int rc = check_sim_args(h, site0, nsites, d_leaves, leaves_pitch, d_internal, internal_pitch);
@@ -803,6 +834,12 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   SimArgs a = base_args(h);
   a.leaves = d_leaves; a.leaves_pitch = leaves_pitch; a.comps = d_comps; a.internal = d_internal;
   a.internal_pitch = internal_pitch; a.site0 = site0; a.nsites = nsites; a.seed = seed;
+  if (h->quad) {
+    int used = 0;
+    rc = quad_simulate(h, a, &used);
+    if (rc) return rc;
+    if (used) return 0;
+  }
   if (h->pair) {
     int used = 0;
     rc = pair_simulate(h, a, &used);

@@ -171,6 +171,151 @@ void compile_pair_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
   out.n_slots = high;
 }
 
+void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, QuadProgram &out) {
+  const int N = n_nodes;
+  constexpr int W = 4, INF = 1 << 29;
+  std::vector<std::vector<int>> kids(N);
+  for (int n = 1; n < N; ++n) kids[parent[n]].push_back(n);
+  std::vector<int64_t> size(N, 1);
+  for (int n = N - 1; n >= 1; --n) size[parent[n]] += size[n];
+  for (int n = 0; n < N; ++n)
+    std::stable_sort(kids[n].begin(), kids[n].end(), [&](int a, int b) { return size[a] < size[b]; });
+
+  // ---- tree DP.  "Open cap" = the cap that contains the branch above v.  cost[v][w]: fewest draws inside v's subtree
+  // when the open cap has w frontier nodes at or below v; nn[v][w]: how many nodes of the open cap lie at or below v.
+  // w == 1 is either "v is a frontier node" (closed: v's own caps are counted) or, for a unary v, "v is summed out".
+  struct Choice {
+    std::vector<int8_t> kw[W + 1];       // v summed out: frontier share of every kid (kids[] order)
+    std::vector<int8_t> ckw;             // v closed: share and cap number of every kid (caps = runs of kids)
+    std::vector<int32_t> cgrp;
+    bool closed1 = true;                 // the w == 1 entry is the closed one
+  };
+  std::vector<Choice> ch(N);
+  std::vector<int> cost((size_t)N * (W + 1), INF), nn((size_t)N * (W + 1), 0);
+  auto C_ = [&](int v, int w) -> int & { return cost[(size_t)v * (W + 1) + w]; };
+  auto N_ = [&](int v, int w) -> int & { return nn[(size_t)v * (W + 1) + w]; };
+  struct Part { int cost = INF, nodes = 0; std::vector<int8_t> kw; std::vector<int32_t> grp; };
+  for (int v = N - 1; v >= 0; --v) {
+    const std::vector<int> &k = kids[v];
+    if (k.empty()) { C_(v, 1) = 0; N_(v, 1) = 1; continue; }
+    // v summed out: all kids share the open cap
+    if ((int)k.size() <= W) {
+      Part comb[W + 1];
+      comb[0].cost = 0;
+      for (size_t i = 0; i < k.size(); ++i) {
+        Part nx[W + 1];
+        for (int w0 = 0; w0 <= W; ++w0) {
+          if (comb[w0].cost >= INF) continue;
+          for (int w = 1; w0 + w <= W; ++w) {
+            if (C_(k[i], w) >= INF) continue;
+            const int val = comb[w0].cost + C_(k[i], w);
+            Part &t = nx[w0 + w];
+            if (val < t.cost) { t.cost = val; t.nodes = comb[w0].nodes + N_(k[i], w); t.kw = comb[w0].kw; t.kw.push_back((int8_t)w); }
+          }
+        }
+        for (int w = 0; w <= W; ++w) comb[w] = nx[w];
+      }
+      for (int w = 1; w <= W; ++w)
+        if (comb[w].cost < INF && comb[w].nodes + 1 <= QUAD_MAX_CAP) {
+          C_(v, w) = comb[w].cost; N_(v, w) = comb[w].nodes + 1; ch[v].kw[w] = comb[w].kw;
+        }
+    }
+    // v closed: its kids are packed, in order, into caps of at most W frontier nodes (state = frontier size of the cap being filled)
+    Part dp[W + 1];
+    dp[0].cost = 0;
+    for (size_t i = 0; i < k.size(); ++i) {
+      Part nx[W + 1];
+      for (int s0 = 0; s0 <= W; ++s0) {
+        if (dp[s0].cost >= INF) continue;
+        for (int w = 1; w <= W; ++w) {
+          if (C_(k[i], w) >= INF) continue;
+          const int grp0 = dp[s0].grp.empty() ? -1 : dp[s0].grp.back();
+          if (s0 > 0 && s0 + w <= W && dp[s0].nodes + N_(k[i], w) <= QUAD_MAX_CAP) {  // joins the cap being filled
+            const int val = dp[s0].cost + C_(k[i], w);
+            Part &t = nx[s0 + w];
+            if (val < t.cost) {
+              t = dp[s0]; t.cost = val; t.nodes += N_(k[i], w); t.kw.push_back((int8_t)w); t.grp.push_back(grp0);
+            }
+          }
+          const int val = dp[s0].cost + C_(k[i], w) + 1;  // starts a new cap
+          Part &t = nx[w];
+          if (val < t.cost) {
+            t = dp[s0]; t.cost = val; t.nodes = N_(k[i], w); t.kw.push_back((int8_t)w); t.grp.push_back(grp0 + 1);
+          }
+        }
+      }
+      for (int s = 0; s <= W; ++s) dp[s] = nx[s];
+    }
+    int best = 1;
+    for (int s = 1; s <= W; ++s) if (dp[s].cost < dp[best].cost) best = s;
+    ch[v].ckw = dp[best].kw; ch[v].cgrp = dp[best].grp;
+    if (dp[best].cost < C_(v, 1)) { C_(v, 1) = dp[best].cost; N_(v, 1) = 1; ch[v].closed1 = true; } else ch[v].closed1 = false;
+  }
+
+  // ---- records, depth first (light caps and light frontier nodes first), slots
+  out.recs.clear();
+  std::vector<int> free_slots;
+  int high = 0;
+  auto alloc = [&]() {
+    if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
+    return high++;
+  };
+  struct Frame { int v, slot, gi, n_groups; std::vector<std::pair<int, int>> pending; size_t pi; };
+  std::vector<Frame> st;
+  auto n_groups = [&](int v) { return ch[v].cgrp.empty() ? 0 : (int)ch[v].cgrp.back() + 1; };
+  st.push_back(Frame{0, alloc(), 0, n_groups(0), {}, 0});
+  struct Visit { int x, w, par; };
+  std::vector<Visit> vs;
+  while (!st.empty()) {
+    Frame &f = st.back();
+    if (f.pi < f.pending.size()) {
+      const std::pair<int, int> nb = f.pending[f.pi++];
+      st.push_back(Frame{nb.first, nb.second, 0, n_groups(nb.first), {}, 0});  // invalidates f
+      continue;
+    }
+    if (f.gi == f.n_groups) { st.pop_back(); continue; }
+    QuadRec r;
+    r.root = f.v; r.src = (int16_t)f.slot; r.n_cap = 0;
+    for (int q = 0; q < 4; ++q) { r.out[q] = -1; r.dst[q] = -1; r.leaf[q] = -1; }
+    int nf = 0;
+    vs.clear();
+    const std::vector<int> &k = kids[f.v];
+    for (size_t i = k.size(); i-- > 0;)
+      if (ch[f.v].cgrp[i] == f.gi) vs.push_back(Visit{k[i], ch[f.v].ckw[i], -1});
+    std::vector<int> boundary;
+    while (!vs.empty()) {
+      const Visit t = vs.back();
+      vs.pop_back();
+      QuadCapNode &cn = r.cap[r.n_cap];
+      cn.node = t.x; cn.par = (int8_t)t.par; cn.fr = -1;
+      const int local = r.n_cap++;
+      const bool is_leaf = kids[t.x].empty();
+      if (is_leaf || (t.w == 1 && ch[t.x].closed1)) {
+        cn.fr = (int8_t)nf;
+        r.out[nf] = t.x;
+        r.leaf[nf] = is_leaf ? leaf_row[t.x] : -1;
+        if (!is_leaf) boundary.push_back(nf);
+        ++nf;
+      } else {
+        const std::vector<int> &kk = kids[t.x];
+        for (size_t i = kk.size(); i-- > 0;) vs.push_back(Visit{kk[i], ch[t.x].kw[t.w][i], local});
+      }
+    }
+    f.gi++;
+    if (f.gi == f.n_groups) free_slots.push_back(f.slot);  // the record reads src before it writes dst
+    std::stable_sort(boundary.begin(), boundary.end(), [&](int a, int b) { return size[r.out[a]] < size[r.out[b]]; });
+    f.pending.clear();
+    f.pi = 0;
+    for (int q : boundary) {
+      const int s = alloc();
+      r.dst[q] = (int8_t)s;
+      f.pending.push_back(std::make_pair(r.out[q], s));
+    }
+    out.recs.push_back(r);
+  }
+  out.n_slots = high;
+}
+
 bool eigen_reversible(int K, const double *pi, const double *exch, double *lambda, double *A, double *B,
                       std::string &msg) {
   std::vector<double> S((size_t)K * K), V((size_t)K * K, 0.0), sq(K);

@@ -48,6 +48,38 @@ struct PairProgram {
 // a record whose parent is the previous record's member A follows it directly.  Expects arrays compile_walk accepted.
 void compile_pair_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, PairProgram &out);
 
+// One step of the QUAD walk (models with K <= 4 states).  The tree is cut into "caps": connected pieces hanging below a
+// node r whose state is known (the root, or a frontier node of an earlier cap), with at most 4 FRONTIER nodes (tree
+// leaves, or internal nodes whose state is kept in a slot and that root further caps); every other node of the cap is
+// MARGINALISED -- its state is summed out of the joint distribution of the frontier given r and never drawn.  One
+// record = one cap = ONE draw from a 256-outcome alias row (o = sum_k state(out[k]) << 2k).  Only the leaves'
+// joint distribution matters to simulateAndFlatten (MarkovProcessAlongTree.hs:71-98), and it is unchanged.
+constexpr int QUAD_MAX_CAP = 12;  // nodes of a cap without its root (binary trees need at most 7)
+struct QuadCapNode {
+  int32_t node;   // preorder index (selects the P(t) table of the branch above it)
+  int8_t par;     // index of its parent in cap[], -1: the cap's root r
+  int8_t fr;      // frontier position 0..3, -1: marginalised
+};
+struct QuadRec {
+  int32_t root;       // r
+  int32_t out[4];     // frontier nodes, -1: absent; out[0] keys the record's Philox counters
+  int16_t src;        // slot holding r's states
+  int8_t dst[4];      // slot receiving out[k]'s states (internal frontier nodes), -1: none
+  int32_t leaf[4];    // output row of out[k], -1: internal / absent
+  int32_t n_cap;
+  QuadCapNode cap[QUAD_MAX_CAP];  // in preorder of the cap (parents first)
+};
+
+struct QuadProgram {
+  std::vector<QuadRec> recs;
+  int n_slots = 0;
+};
+
+// Cuts the tree into the minimum number of caps (tree DP over the open cap's frontier size), orders the records depth
+// first with the heaviest frontier node last and assigns slots (slot 0 = the root states; a record reads src before it
+// writes dst, so a slot freed by a node's last cap is reused at once).  Expects arrays compile_walk accepted.
+void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, QuadProgram &out);
+
 // Symmetric eigen-decomposition (cyclic Jacobi) of S = D^{1/2} Q D^{-1/2}, Q = setDiagonal(E diag(pi)).
 // Produces lambda[K], A = D^{-1/2} V and B = V^T D^{1/2} so that exp(Qt) = I + A diag(expm1(lambda t)) B.
 bool eigen_reversible(int K, const double *pi, const double *exch, double *lambda, double *A, double *B,

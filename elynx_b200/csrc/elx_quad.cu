@@ -1,0 +1,595 @@
+// Quad mode of the free-running simulation (K2) for models with at most 4 states (DNA) on sm_100a.
+//
+// The reference draws one state per (site, node) from the row of the parent's state (`jump`, Simulate/MarkovProcess.hs:48-49,
+// walk MarkovProcessAlongTree.hs:88-98) and simulateAndFlatten keeps the leaves only (:71-83).  The joint distribution of
+// the leaves is all that matters, so internal nodes whose state nobody needs can be SUMMED OUT instead of drawn: the
+// host cuts the tree into "caps" (elx_internal.hpp, compile_quad_walk) -- pieces below a node r of known state with at
+// most 4 frontier nodes (leaves, or internal nodes kept in a slot because further caps hang below them) -- and every cap
+// is ONE draw from the 256-outcome joint row  P(frontier states | state of r)  (Felsenstein-style sums over the cap's
+// inner nodes, k1_quad_joint).  A random binary tree with T leaves needs about 0.36 T such draws, i.e. 2.8 alignment
+// cells per draw instead of 1 (pair mode) or 0.5 (node by node), and every per-draw cost of the hot loop shrinks alike.
+//
+// Draw specification (oracle/freerun_spec.c spec_freerun_quad executes it on the CPU; kernels must agree bit for bit):
+//   record g = (out[0..3] | r), site s, component c, state i of r:
+//     x32 = word (s & 3) of philox(s>>2 lo, s>>2 hi, out[0], TAG_NODE);  x32 = [t : 24][j : 8]
+//     e = qe32[g][c][i][j] = [q_hi : 24][alias : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
+//     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 16) < qlo16[g][c][i][j] ? j : alias
+//     state(out[k]) = (o >> 2k) & 3
+// The joint rows carry integer masses round(p / sum * 2^48) (Vose pairing in exact integer arithmetic, column capacity 2^40).
+//
+// Kernels: k1_quad_joint, k1_alias_quad (tables), k2_quad_generic (tables through L1/L2; the cross-check),
+// k2_quad_tiled (the hot kernel: one record + its 4 KB x C joint rows per stage, streamed through shared memory by a
+// producer warp with TMA bulk copies; 16 sites per thread; full/empty mbarriers, no CTA barrier in the loop).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/elynx_b200.h"
+#include "elx_device.cuh"
+#include "elx_ptx.cuh"
+#include "elx_state.hpp"
+
+namespace elx {
+
+constexpr int QUAD_MAX_SLOTS = 24;
+constexpr int QUAD_MAX_NSTAGE = 8;
+constexpr int QUAD_COLS = 256;
+
+// Device form of a record (32 bytes, streamed through shared memory in front of the record's joint rows).
+struct QuadRecDev {
+  uint32_t node0;
+  int8_t src, dst[4], nfr, pad[2];
+  int32_t pad2;
+  int32_t leaf[4];  // second 16-byte half
+};
+static_assert(sizeof(QuadRecDev) == 32, "QuadRecDev must stay 32 bytes");
+
+struct QuadCapDev {
+  int32_t n;
+  int32_t node[QUAD_MAX_CAP];
+  int8_t par[QUAD_MAX_CAP], fr[QUAD_MAX_CAP];
+  int32_t pad;
+};
+
+struct QuadTables {
+  QuadProgram prog;
+  int G = 0;
+  QuadRecDev *d_recs = nullptr;
+  QuadCapDev *d_caps = nullptr;
+  double *d_joint = nullptr;    // [G][C][4][256]
+  uint32_t *d_qe32 = nullptr;   // [G][C][4][256]
+  uint16_t *d_qlo16 = nullptr;  // [G][C][4][256]
+  uint8_t *d_ftab = nullptr;    // [G] x (32 B record + tb bytes of rows)
+  int tiled = 0, threads = 0, nstage = 0, tb = 0, stage_bytes = 0;
+  size_t smem = 0;
+};
+
+struct QuadArgs {
+  SimArgs s;
+  int G;
+  const QuadRecDev *recs;
+  const uint32_t *qe32;
+  const uint16_t *qlo16;
+  const uint8_t *ftab;
+  int tb, stage_bytes, nstage;
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1 (quad rows): joint[g][c][i][o] = P(frontier states = o | state of the cap's root = i), the cap's inner nodes summed
+// out by one pruning pass (children before parents).  One thread per (g, c, i, o); rows i >= K stay zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void k1_quad_joint(int G, int C, int K, const QuadCapDev *__restrict__ caps, const double *__restrict__ P,
+                              double *__restrict__ joint) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)G * C * 4 * QUAD_COLS) return;
+  const int o = (int)(idx & 255), i = (int)((idx >> 8) & 3), c = (int)((idx >> 10) % C), g = (int)((idx >> 10) / C);
+  if (i >= K) { joint[idx] = 0.0; return; }
+  const QuadCapDev cap = caps[g];
+  double L[QUAD_MAX_CAP][4];
+  int used = 0;
+  for (int n = 0; n < cap.n; ++n) {
+    const int fr = cap.fr[n];
+    if (fr >= 0) used |= 3 << (2 * fr);
+    for (int s = 0; s < 4; ++s) L[n][s] = fr < 0 ? 1.0 : (((o >> (2 * fr)) & 3) == s ? 1.0 : 0.0);
+  }
+  if (o & ~used) { joint[idx] = 0.0; return; }  // absent frontier positions are fixed at state 0
+  double top = 1.0;
+  for (int n = cap.n - 1; n >= 0; --n) {
+    const double *pn = P + ((int64_t)cap.node[n] * C + c) * K * K;
+    const int p = cap.par[n];
+    if (p >= 0) {
+      for (int s = 0; s < K; ++s) {
+        double msg = 0.0;
+        for (int t = 0; t < K; ++t) {
+          double v = pn[s * K + t];
+          if (!(v > 0.0)) v = 0.0;
+          msg = __dadd_rn(msg, __dmul_rn(v, L[n][t]));
+        }
+        L[p][s] = __dmul_rn(L[p][s], msg);
+      }
+    } else {
+      double msg = 0.0;
+      for (int t = 0; t < K; ++t) {
+        double v = pn[i * K + t];
+        if (!(v > 0.0)) v = 0.0;
+        msg = __dadd_rn(msg, __dmul_rn(v, L[n][t]));
+      }
+      top = __dmul_rn(top, msg);
+    }
+  }
+  joint[idx] = top;
+}
+
+// Alias rows of 256 columns: integer masses m_o = round(p_o / sum * 2^48) (residual to the largest), Vose pairing, column
+// capacity 2^40; entry = [threshold bits 39..16 : 24][alias : 8], qlo16 = threshold bits 15..0.  One thread per row.
+__global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, uint32_t *__restrict__ e32, uint16_t *__restrict__ qlo16) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  constexpr int KP = QUAD_COLS;
+  constexpr int64_t CAP = (int64_t)1 << 40;
+  int64_t m[KP], q[KP];
+  int16_t alias[KP], small[KP], large[KP];
+  const double *p = joint + r * KP;
+  double sum = 0.0;
+  for (int j = 0; j < KP; ++j) sum += p[j] > 0.0 ? p[j] : 0.0;
+  int64_t tot = 0;
+  int big = 0;
+  for (int j = 0; j < KP; ++j) {
+    const double v = p[j] > 0.0 ? p[j] : 0.0;
+    m[j] = sum > 0.0 ? (int64_t)llrint(v / sum * 0x1p48) : (j == 0 ? ((int64_t)1 << 48) : 0);
+    tot += m[j];
+    if (m[j] > m[big]) big = j;
+  }
+  m[big] += ((int64_t)1 << 48) - tot;
+  int ns = 0, nl = 0;
+  for (int j = KP - 1; j >= 0; --j) {
+    alias[j] = (int16_t)j;
+    q[j] = CAP;
+    if (m[j] < CAP) small[ns++] = (int16_t)j; else large[nl++] = (int16_t)j;
+  }
+  while (ns > 0 && nl > 0) {
+    const int s = small[--ns], l = large[--nl];
+    q[s] = m[s];
+    alias[s] = (int16_t)l;
+    m[l] -= CAP - m[s];
+    if (m[l] < CAP) small[ns++] = (int16_t)l; else large[nl++] = (int16_t)l;
+  }
+  for (int j = 0; j < KP; ++j) {
+    int64_t qq = q[j];
+    int al = alias[j];
+    if (qq >= CAP) { qq = CAP - 1; al = j; }  // a full column: always accept (alias = self)
+    e32[r * KP + j] = (uint32_t)(((qq >> 16) << 8) | (int64_t)al);
+    qlo16[r * KP + j] = (uint16_t)(qq & 0xffff);
+  }
+}
+
+// stage image of record g: [QuadRecDev][C x 4 x 256 entries]
+__global__ void k_build_quad_ftab(int G, int stage_bytes, const QuadRecDev *__restrict__ recs, const uint32_t *__restrict__ qe32,
+                                  uint8_t *__restrict__ ftab) {
+  const int chunks = stage_bytes / 16;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)G * chunks) return;
+  const int g = (int)(i / chunks), ch = (int)(i % chunks);
+  uint4 v;
+  if (ch < 2) v = reinterpret_cast<const uint4 *>(recs + g)[ch];
+  else v = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(qe32) + (size_t)g * (stage_bytes - 32))[ch - 2];
+  reinterpret_cast<uint4 *>(ftab + (size_t)g * stage_bytes)[ch] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 quad mode, generic: any C, tables through L1/L2, one thread per 4 consecutive sites (one Philox call per record).
+// ---------------------------------------------------------------------------------------------
+template <int ROUNDS>
+__global__ void k2_quad_generic(QuadArgs fa) {
+  const SimArgs &a = fa.s;
+  const int64_t g4 = (a.site0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t sbase = g4 << 2;
+  if (sbase >= a.site0 + a.nsites) return;
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  uint32_t slot[QUAD_MAX_SLOTS];
+  uint32_t CB = 0, R0 = 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag, (uint64_t)sbase + d, key.x, key.y);
+    const uint32_t c = cr & 0xffffu, root = cr >> 16;
+    CB |= (c * 4u) << (8 * d);
+    R0 |= (c * 4u + root) << (8 * d);
+    const int64_t col = sbase + d - a.site0;
+    if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = (int32_t)c;
+  }
+  slot[0] = R0;
+  constexpr uint32_t SM = 0x03030303u;
+  for (int g = 0; g < fa.G; ++g) {
+    const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(fa.recs + g));
+    const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(fa.recs + g) + 1);
+    const int src = (int)(int8_t)(h0.y & 0xffu);
+    const int dst[4] = {(int)(int8_t)((h0.y >> 8) & 0xffu), (int)(int8_t)((h0.y >> 16) & 0xffu), (int)(int8_t)(h0.y >> 24),
+                        (int)(int8_t)(h0.z & 0xffu)};
+    const int leaf[4] = {(int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+    const uint32_t Rv = slot[src];
+    const uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)g4, (uint32_t)((uint64_t)g4 >> 32), h0.x, TAG_NODE), key);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    uint32_t W = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const uint32_t rowid = (Rv >> (8 * d)) & 0xffu, j = w[d] & 0xffu;
+      const int64_t idx = (((int64_t)g * a.C * 4 + rowid) << 8) | j;
+      const uint32_t e = __ldg(fa.qe32 + idx), t = w[d] >> 8, qh = e >> 8;
+      uint32_t o;
+      if (t < qh) o = j;
+      else if (t > qh) o = e & 0xffu;
+      else {
+        const uint64_t s = (uint64_t)sbase + d;
+        const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), h0.x, TAG_REFINE), key);
+        o = (z.x >> 16) < (uint32_t)__ldg(fa.qlo16 + idx) ? j : (e & 0xffu);
+      }
+      W |= o << (8 * d);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t v = (W >> (2 * k)) & SM;
+      if (leaf[k] >= 0) {
+        uint8_t *dstp = a.leaves + (int64_t)leaf[k] * a.leaves_pitch + (sbase - a.site0);
+        for (int d = 0; d < 4; ++d) {
+          const int64_t col = sbase + d - a.site0;
+          if (col >= 0 && col < a.nsites) dstp[d] = (uint8_t)(v >> (8 * d));
+        }
+      } else if (dst[k] >= 0) {
+        slot[dst[k]] = v | CB;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 quad mode, tiled (the hot kernel).  THREADS consumer threads x 16 consecutive sites each (four Philox calls per
+// record) + one producer warp.  A slot holds one byte per site: comp * 4 + state = the row of the record's table, so the
+// entry index of a draw is  row << 8 | j  -- one PRMT to move the row byte, one LOP3 to merge j, one IMAD for the address.
+// The outcome byte (4 x 2-bit states) falls out of a 32-bit min of draw and entry; a leaf row is (W >> 2k) & 0x03030303
+// of the packed outcome bytes, written as 512 contiguous bytes per warp with one 128-bit streaming store per lane.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int ROUNDS, int THREADS>
+__global__ void __launch_bounds__(THREADS + 32, (THREADS <= 256 ? 2 : 1)) k2_quad_tiled(QuadArgs fa) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const SimArgs &a = fa.s;
+  const int tid = threadIdx.x;
+  const int nstage = fa.nstage;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty_bar = full_bar + QUAD_MAX_NSTAGE;
+  const uint32_t stage_smem = smem_u32(smem + 128);
+  const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
+  constexpr uint32_t slot_stride = THREADS * 16u;
+
+  if (tid == 0) {
+    for (int i = 0; i < nstage; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  __syncthreads();
+
+  if (tid >= THREADS) {
+    // producer warp: one lane keeps the ring full
+    if (tid == THREADS) {
+      int buf = 0;
+      uint32_t phase = 1;  // the first pass over the ring finds every buffer free
+      for (int g = 0; g < fa.G; ++g) {
+        if (g >= nstage) mbar_wait(smem_u32(&empty_bar[buf]), phase);
+        mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
+        tma_bulk_g2s(stage_smem + (uint32_t)(buf * fa.stage_bytes), fa.ftab + (size_t)g * fa.stage_bytes, (uint32_t)fa.stage_bytes,
+                     smem_u32(&full_bar[buf]));
+        if (++buf == nstage) { buf = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  // 16 sites per thread, aligned on global site index multiples of 16; the lanes of a warp own consecutive groups
+  const int64_t g16 = (a.site0 >> 4) + (int64_t)blockIdx.x * THREADS + tid;
+  const int64_t sbase = g16 << 4;
+  const int64_t col0 = sbase - a.site0;
+  const bool any = sbase < a.site0 + a.nsites;
+  const bool full = (col0 >= 0) && (col0 + 16 <= a.nsites);
+  uint32_t CB[4] = {0, 0, 0, 0}, R[4] = {0, 0, 0, 0};  // per site one byte: comp * 4 and comp * 4 + state
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag, (uint64_t)sbase + i,
+                                               key.x, key.y);
+    const uint32_t c = cr & 0xffffu, root = cr >> 16;
+    CB[i >> 2] |= (c * 4u) << (8 * (i & 3));
+    R[i >> 2] |= (c * 4u + root) << (8 * (i & 3));
+    const int64_t col = col0 + i;
+    if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = (int32_t)c;
+  }
+  const uint32_t slot_base = slots_smem + (uint32_t)tid * 16u;
+  sts_v4(slot_base, make_uint4(R[0], R[1], R[2], R[3]));  // slot 0 = the root states
+  int store_mode = !any ? 0
+                        : (full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
+                           ((col0 & 15) == 0)) ? 1 : 2;
+  asm volatile("" : "+r"(store_mode));
+  uint8_t *leaf_base = a.leaves + col0;
+  asm volatile("" : "+l"(leaf_base));
+  const uint64_t G0 = (uint64_t)sbase >> 2;  // a multiple of 4: the four counters of a record differ in the low 2 bits
+  const uint32_t G0lo = (uint32_t)G0, Ghi = (uint32_t)(G0 >> 32);
+  constexpr uint32_t SM = 0x03030303u;
+
+  int buf = 0;
+  uint32_t phase = 0;
+  for (int g = 0; g < fa.G; ++g) {
+    mbar_wait(smem_u32(&full_bar[buf]), phase);
+    const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
+    const uint4 h0 = lds_v4(sbuf);
+    const uint4 h1 = lds_v4(sbuf + 16u);
+    const uint32_t node0 = h0.x;
+    const int src = (int)(int8_t)(h0.y & 0xffu);
+    const uint32_t tbl = sbuf + 32u;
+#ifdef ELX_DEBUG_BOUNDS
+    if (src < 0 || src >= a.n_slots || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
+#endif
+    const uint4 rv = lds_v4(slot_base + (uint32_t)src * slot_stride);
+    const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
+    uint32_t W[4];
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
+      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+      uint32_t c[4], t[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t rb = __byte_perm(Rq[q], 0u, 0x4404u | ((uint32_t)i << 4));  // row byte of site 4q+i -> bits 8..15
+        const uint32_t idx = (w[i] & 0xffu) | rb;
+#ifdef ELX_DEBUG_BOUNDS
+        if (idx * 4u + 4u > (uint32_t)fa.tb) atomicExch(a.error_flag, -7);
+#endif
+        const uint32_t e = lds_u32(tbl + idx * 4u);
+        c[i] = min(w[i], e);
+        t[i] = w[i] ^ e;
+      }
+      m = min(min(m, t[0]), min(t[1], min(t[2], t[3])));
+      W[q] = __byte_perm(__byte_perm(c[0], c[1], 0x0040u), __byte_perm(c[2], c[3], 0x0040u), 0x5410u);
+    }
+    if (m < 256u) {
+      // exact path (2^-24 per draw): some draw hit its threshold's high 24 bits; redo this thread's 16 draws one by one
+      // and settle the tied ones with 16 more random bits.  Rolled, call-free and array-free on purpose (elx_fast.cu).
+#pragma unroll 1
+      for (int s = 0; s < 16; ++s) {
+        const int q = s >> 2, i = s & 3;
+        const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
+        const uint32_t w = i == 0 ? x.x : (i == 1 ? x.y : (i == 2 ? x.z : x.w));
+        const uint32_t row = lds_u8(slot_base + (uint32_t)src * slot_stride + (uint32_t)s);
+        const uint32_t j = w & 0xffu, idx = (row << 8) | j;
+        const uint32_t e = lds_u32(tbl + idx * 4u);
+        if ((w ^ e) < 256u) {
+          const uint64_t sg = (uint64_t)sbase + (uint64_t)s;
+          const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), key);
+          const uint32_t ql = (uint32_t)__ldg(fa.qlo16 + ((((int64_t)g * a.C * 4 + row) << 8) | j));
+          const uint32_t o = (z.x >> 16) < ql ? j : (e & 0xffu);
+          const uint32_t sh = 8u * (uint32_t)i, keep = ~(0xffu << sh);
+          if (q == 0) W[0] = (W[0] & keep) | (o << sh);
+          if (q == 1) W[1] = (W[1] & keep) | (o << sh);
+          if (q == 2) W[2] = (W[2] & keep) | (o << sh);
+          if (q == 3) W[3] = (W[3] & keep) | (o << sh);
+        }
+      }
+    }
+    // this warp is done with the stage buffer (header fields are in registers)
+    const int dst0 = (int)(int8_t)((h0.y >> 8) & 0xffu), dst1 = (int)(int8_t)((h0.y >> 16) & 0xffu), dst2 = (int)(int8_t)(h0.y >> 24),
+              dst3 = (int)(int8_t)(h0.z & 0xffu);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[buf]));
+    if (++buf == nstage) { buf = 0; phase ^= 1u; }
+
+#define ELX_QUAD_OUT(k, leafk, dstk)                                                                                          \
+  if ((leafk) >= 0) {                                                                                                         \
+    if (store_mode)                                                                                                           \
+      store_leaf(a, leaf_base, (leafk), col0, store_mode,                                                                     \
+                 make_uint4((W[0] >> (2 * k)) & SM, (W[1] >> (2 * k)) & SM, (W[2] >> (2 * k)) & SM, (W[3] >> (2 * k)) & SM)); \
+  } else if ((dstk) >= 0) {                                                                                                   \
+    sts_v4(slot_base + (uint32_t)(dstk) * slot_stride,                                                                        \
+           make_uint4(((W[0] >> (2 * k)) & SM) | CB[0], ((W[1] >> (2 * k)) & SM) | CB[1], ((W[2] >> (2 * k)) & SM) | CB[2],   \
+                      ((W[3] >> (2 * k)) & SM) | CB[3]));                                                                     \
+  }
+    ELX_QUAD_OUT(0, (int)h1.x, dst0)
+    ELX_QUAD_OUT(1, (int)h1.y, dst1)
+    ELX_QUAD_OUT(2, (int)h1.z, dst2)
+    ELX_QUAD_OUT(3, (int)h1.w, dst3)
+#undef ELX_QUAD_OUT
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define QUAD_CUDA(h, expr)                                                                                      \
+  do {                                                                                                          \
+    cudaError_t _e = (expr);                                                                                    \
+    if (_e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+int quad_groups(const elx_handle *h) {
+  const QuadTables *qt = static_cast<const QuadTables *>(h->quad);
+  return qt ? qt->G : 0;
+}
+
+void quad_rec_to_ints(const QuadRec &r, int32_t *o) {
+  o[0] = r.root;
+  for (int k = 0; k < 4; ++k) { o[1 + k] = r.out[k]; o[5 + k] = r.leaf[k]; o[9 + k] = r.dst[k]; }
+  o[13] = r.src; o[14] = r.n_cap; o[15] = 0;
+  for (int i = 0; i < QUAD_MAX_CAP; ++i) {
+    const bool in = i < r.n_cap;
+    o[16 + 3 * i] = in ? r.cap[i].node : -1;
+    o[17 + 3 * i] = in ? r.cap[i].par : -1;
+    o[18 + 3 * i] = in ? r.cap[i].fr : -1;
+  }
+}
+
+// Geometry of the tiled kernel: the biggest CTA whose slot stack leaves room for a ring of at least two stages.
+static bool quad_geometry(int C, int n_slots, QuadTables *qt) {
+  const int tb = C * 4 * QUAD_COLS * 4;
+  const size_t stage = 32 + (size_t)tb;
+  int want_threads = 0, want_stages = 0;
+  if (const char *e = getenv("ELX_QUAD_THREADS")) want_threads = atoi(e);  // tuning knobs
+  if (const char *e = getenv("ELX_QUAD_NSTAGE")) want_stages = atoi(e);
+  const int cand[4] = {512, 384, 256, 256};
+  for (int ci = 0; ci < 4; ++ci) {
+    const int th = cand[ci];
+    if (want_threads && th != want_threads) continue;
+    const size_t per_cta = ci == 2 ? 113 * 1024 : 226 * 1024;  // 256 threads: two CTAs per SM when they fit
+    const size_t slots = (size_t)(n_slots > 0 ? n_slots : 1) * th * 16;
+    if (128 + 2 * stage + slots > per_cta) continue;
+    int nstage = (int)((per_cta - 128 - slots) / stage);
+    const int cap = want_stages ? want_stages : 4;
+    if (nstage > cap) nstage = cap;
+    if (nstage > QUAD_MAX_NSTAGE) nstage = QUAD_MAX_NSTAGE;
+    if (nstage < 2) continue;
+    qt->tiled = 1; qt->threads = th; qt->nstage = nstage; qt->tb = tb; qt->stage_bytes = (int)stage;
+    qt->smem = 128 + (size_t)nstage * stage + slots;
+    return true;
+  }
+  return false;
+}
+
+int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
+  QuadTables *qt = new QuadTables();
+  compile_quad_walk(h->N, parent, leaf_row, qt->prog);
+  const int G = qt->G = (int)qt->prog.recs.size();
+  // quad mode needs the tiled geometry (or at least the generic kernel's slot array); otherwise the handle stays in pair mode
+  if (G == 0 || qt->prog.n_slots > QUAD_MAX_SLOTS || (int64_t)h->C * 4 > 255) { delete qt; return 0; }
+  quad_geometry(h->C, qt->prog.n_slots, qt);
+  h->quad = qt;
+  std::vector<QuadRecDev> dev((size_t)G);
+  std::vector<QuadCapDev> caps((size_t)G);
+  for (int g = 0; g < G; ++g) {
+    const QuadRec &r = qt->prog.recs[g];
+    QuadRecDev &d = dev[g];
+    memset(&d, 0, sizeof d);
+    d.node0 = (uint32_t)r.out[0];
+    d.src = (int8_t)r.src;
+    d.nfr = 0;
+    for (int k = 0; k < 4; ++k) { d.dst[k] = r.dst[k]; d.leaf[k] = r.leaf[k]; if (r.out[k] >= 0) d.nfr++; }
+    QuadCapDev &c = caps[g];
+    memset(&c, 0, sizeof c);
+    c.n = r.n_cap;
+    for (int i = 0; i < r.n_cap; ++i) { c.node[i] = r.cap[i].node; c.par[i] = r.cap[i].par; c.fr[i] = r.cap[i].fr; }
+  }
+  const size_t ents = (size_t)G * h->C * 4 * QUAD_COLS;
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_recs, sizeof(QuadRecDev) * (size_t)G));
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_caps, sizeof(QuadCapDev) * (size_t)G));
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_joint, sizeof(double) * ents));
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qe32, sizeof(uint32_t) * ents));
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qlo16, sizeof(uint16_t) * ents));
+  QUAD_CUDA(h, cudaMemcpy(qt->d_recs, dev.data(), sizeof(QuadRecDev) * (size_t)G, cudaMemcpyHostToDevice));
+  QUAD_CUDA(h, cudaMemcpy(qt->d_caps, caps.data(), sizeof(QuadCapDev) * (size_t)G, cudaMemcpyHostToDevice));
+  if (qt->tiled) QUAD_CUDA(h, cudaMalloc((void **)&qt->d_ftab, (size_t)G * qt->stage_bytes));
+  return 0;
+}
+
+int quad_tables_build(elx_handle *h) {
+  QuadTables *qt = static_cast<QuadTables *>(h->quad);
+  if (!qt) return 0;
+  const int64_t ents = (int64_t)qt->G * h->C * 4 * QUAD_COLS;
+  k1_quad_joint<<<(unsigned)((ents + 255) / 256), 256, 0, h->stream>>>(qt->G, h->C, h->K, qt->d_caps, h->d_P, qt->d_joint);
+  h->launches++;
+  QUAD_CUDA(h, cudaGetLastError());
+  const int64_t rows = ents / QUAD_COLS;
+  k1_alias_quad<<<(unsigned)((rows + 63) / 64), 64, 0, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qlo16);
+  h->launches++;
+  QUAD_CUDA(h, cudaGetLastError());
+  if (qt->tiled) {
+    const int64_t n = (int64_t)qt->G * (qt->stage_bytes / 16);
+    k_build_quad_ftab<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(qt->G, qt->stage_bytes, qt->d_recs, qt->d_qe32, qt->d_ftab);
+    h->launches++;
+    QUAD_CUDA(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+void quad_free(elx_handle *h) {
+  QuadTables *qt = static_cast<QuadTables *>(h->quad);
+  if (!qt) return;
+  cudaFree(qt->d_recs); cudaFree(qt->d_caps); cudaFree(qt->d_joint); cudaFree(qt->d_qe32); cudaFree(qt->d_qlo16); cudaFree(qt->d_ftab);
+  delete qt;
+  h->quad = nullptr;
+}
+
+int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16) {
+  QuadTables *qt = static_cast<QuadTables *>(h->quad);
+  if (!qt) return fail(h, ELX_E_INVALID, "elx_quad_get: this handle has no quad tables");
+  if (recs)
+    for (int g = 0; g < qt->G; ++g) quad_rec_to_ints(qt->prog.recs[g], recs + (size_t)g * ELX_QUAD_REC_INTS);
+  const size_t n = (size_t)qt->G * h->C * 4 * QUAD_COLS;
+  if (qe32) QUAD_CUDA(h, cudaMemcpyAsync(qe32, qt->d_qe32, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (qlo16) QUAD_CUDA(h, cudaMemcpyAsync(qlo16, qt->d_qlo16, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+  QUAD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+template <int ROUNDS, int THREADS>
+static cudaError_t launch_quad_tiled(const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(k2_quad_tiled<ROUNDS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const unsigned blocks = (unsigned)((groups + THREADS - 1) / THREADS);
+  k2_quad_tiled<ROUNDS, THREADS><<<blocks, THREADS + 32, smem, stream>>>(fa);
+  return cudaGetLastError();
+}
+
+template <int ROUNDS>
+static cudaError_t launch_quad_tiled_t(int threads, const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
+  switch (threads) {
+    case 512: return launch_quad_tiled<ROUNDS, 512>(fa, groups, smem, stream);
+    case 384: return launch_quad_tiled<ROUNDS, 384>(fa, groups, smem, stream);
+    default: return launch_quad_tiled<ROUNDS, 256>(fa, groups, smem, stream);
+  }
+}
+
+int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
+  *used = 0;
+  QuadTables *qt = static_cast<QuadTables *>(h->quad);
+  if (!qt || a.internal) return 0;  // summed-out nodes have no states: `simulate` (keep internal states) draws pairs
+  QuadArgs fa;
+  fa.s = a;
+  fa.s.n_slots = qt->prog.n_slots;
+  fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qlo16 = qt->d_qlo16; fa.ftab = qt->d_ftab;
+  fa.tb = qt->tb; fa.stage_bytes = qt->stage_bytes; fa.nstage = qt->nstage;
+  cudaError_t e;
+  if (qt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC)) {
+    const int64_t g0 = a.site0 >> 4, g1 = (a.site0 + a.nsites + 15) >> 4;
+    e = h->rounds == 7 ? launch_quad_tiled_t<7>(qt->threads, fa, g1 - g0, qt->smem, h->stream)
+                       : launch_quad_tiled_t<10>(qt->threads, fa, g1 - g0, qt->smem, h->stream);
+  } else {
+    const int64_t g0 = a.site0 >> 2, g1 = (a.site0 + a.nsites + 3) >> 2;
+    const unsigned blocks = (unsigned)((g1 - g0 + 127) / 128);
+    if (h->rounds == 7) k2_quad_generic<7><<<blocks, 128, 0, h->stream>>>(fa);
+    else k2_quad_generic<10><<<blocks, 128, 0, h->stream>>>(fa);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("quad kernel launch: ") + cudaGetErrorString(e));
+  h->launches++;
+  *used = 1;
+  return 0;
+}
+
+}  // namespace elx

@@ -27,6 +27,8 @@ struct elx_handle {
   void *fast = nullptr;
   // pair mode (K <= 4): joint two-children draws, owned by elx_pair.cu
   void *pair = nullptr;
+  // quad mode (K <= 4): one draw per cap of up to 4 frontier nodes, inner nodes summed out; owned by elx_quad.cu
+  void *quad = nullptr;
   int64_t launches = 0;
   std::string last_error;
 };
@@ -82,6 +84,16 @@ void pair_free(elx_handle *h);
 int pair_groups(const elx_handle *h);
 int pair_get(elx_handle *h, int32_t *nodeA, int32_t *nodeB, uint16_t *pe16, uint32_t *pqlo);
 int pair_simulate(elx_handle *h, SimArgs &a, int *used);
+
+// elx_quad.cu: quad mode (models with K <= 4 unless ELX_FLAG_SINGLE_DRAWS / ELX_FLAG_PAIR_DRAWS); leaves h->quad null when
+// the tree or model does not fit (the handle then stays in pair mode)
+int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row);
+int quad_tables_build(elx_handle *h);
+void quad_free(elx_handle *h);
+int quad_groups(const elx_handle *h);
+void quad_rec_to_ints(const QuadRec &r, int32_t *o);  // ELX_QUAD_REC_INTS values, the layout include/elynx_b200.h documents
+int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16);
+int quad_simulate(elx_handle *h, SimArgs &a, int *used);
 
 // elx_core.cu
 void launch_k1_alias(elx_handle *h, int64_t rows, int K, int A, const double *P, uint16_t *e16, uint32_t *qlo);

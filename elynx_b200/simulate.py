@@ -33,7 +33,7 @@ class Simulator:
     alias tables and the compiled tree walk."""
 
     def __init__(self, weights, ds, es, tree, is_mixture: bool = True, device: int = -1, philox_rounds: int = 0,
-                 force_generic: bool = False, pade: bool = False, single_draws: bool = False):
+                 force_generic: bool = False, pade: bool = False, single_draws: bool = False, pair_draws: bool = False):
         ds = np.ascontiguousarray(ds, dtype=np.float64)
         es = np.ascontiguousarray(es, dtype=np.float64)
         if ds.ndim == 1:
@@ -55,7 +55,7 @@ class Simulator:
         t = L.elx_tree(len(parent), parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
                        leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
         o = L.elx_opts(device, philox_rounds, (L.ELX_FLAG_FORCE_GENERIC if force_generic else 0) | (L.ELX_FLAG_PADE if pade else 0) |
-                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0), 0)
+                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0) | (L.ELX_FLAG_PAIR_DRAWS if pair_draws else 0), 0)
         h = C.c_void_p()
         self._h = None
         L.check(L.lib().elx_create(C.byref(m), C.byref(t), C.byref(o), C.byref(h)))
@@ -65,6 +65,8 @@ class Simulator:
         self.n_leaves = int(L.lib().elx_n_leaves(h))
         self.alias_columns = int(L.lib().elx_alias_columns(h))
         self.pair_groups = int(L.lib().elx_pair_groups(h))  # > 0: K <= 4, sibling pairs are drawn jointly (elx_pair.cu)
+        # > 0: K <= 4, leaves-only calls draw one cap of <= 4 frontier nodes at a time, inner nodes summed out (elx_quad.cu)
+        self.quad_groups = int(L.lib().elx_quad_groups(h))
 
     # -- lifetime --------------------------------------------------------------------------
     def close(self):
@@ -129,6 +131,18 @@ class Simulator:
         pqlo = np.empty(shape, dtype=np.uint32)
         L.check(L.lib().elx_pair_get(self._h, _ptr(node_a), _ptr(node_b), _ptr(pe16), _ptr(pqlo)), self._h)
         return node_a, node_b, pe16, pqlo
+
+    def quad_tables(self):
+        """(recs[G][ELX_QUAD_REC_INTS], qe32[G][C][4][256], qlo16[G][C][4][256]) of the quad-mode records, or None."""
+        g = self.quad_groups
+        if g == 0:
+            return None
+        recs = np.empty((g, L.ELX_QUAD_REC_INTS), dtype=np.int32)
+        shape = (g, self.n_components, 4, 256)
+        qe32 = np.empty(shape, dtype=np.uint32)
+        qlo16 = np.empty(shape, dtype=np.uint16)
+        L.check(L.lib().elx_quad_get(self._h, _ptr(recs), _ptr(qe32), _ptr(qlo16)), self._h)
+        return recs, qe32, qlo16
 
     # -- simulation ----------------------------------------------------------------------------
     def simulate(self, seed: int, nsites: int, site0: int = 0, want_comps: bool = False, keep_internal: bool = False):

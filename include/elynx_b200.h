@@ -81,6 +81,8 @@ typedef struct {
 #define ELX_FLAG_FORCE_GENERIC 1 /* always use the generic global-table kernel (cross-check of the tiled one) */
 #define ELX_FLAG_SINGLE_DRAWS 4  /* models with K <= 4: draw node by node (one alias row per node) instead of the default joint
                                     draw of sibling pairs; a different (equally exact) free-running stream */
+#define ELX_FLAG_PAIR_DRAWS 8    /* models with K <= 4: draw sibling pairs (pair mode) instead of the default quad mode (one draw per cap
+                                    of up to 4 frontier nodes, inner nodes summed out); a different, equally exact stream */
 #define ELX_FLAG_PADE 2          /* build P(t) by the scaled Pade-7 + squaring kernel (hmatrix `expm`'s algorithm) instead of
                                     the eigen form; taken automatically for non-reversible components */
 
@@ -130,6 +132,23 @@ int elx_alias_get(elx_handle *h, uint16_t *e16, uint32_t *qlo);
  * one) and their alias rows pe16 / pqlo [G][C][K][16] ([threshold high bits : 12][alias : 4] / 32 low threshold bits). */
 int32_t elx_pair_groups(const elx_handle *h);
 int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16, uint32_t *pqlo);
+
+/* Quad mode (the default for models with at most 4 states when only the leaves are requested; ELX_FLAG_PAIR_DRAWS /
+ * ELX_FLAG_SINGLE_DRAWS turn it off): simulateAndFlatten (:71-98) keeps the leaves only, so internal nodes whose state
+ * nobody needs are summed out instead of drawn.  The tree is cut into "caps" -- pieces below a node r of known state with at
+ * most 4 frontier nodes (leaves, or internal nodes kept because further caps hang below them) -- and every cap is ONE draw
+ * from the 256-outcome joint row P(frontier states | state of r), o = sum_k state(out[k]) << 2k.  The joint distribution of
+ * the leaves is exactly the reference's.  Calls that keep internal states (`internal` != NULL) draw pairs instead.
+ * A record is ELX_QUAD_REC_INTS int32: [0] r, [1..4] out[k] (-1: absent), [5..8] leaf row of out[k] (-1: internal),
+ * [9..12] slot receiving out[k] (-1: none), [13] slot holding r, [14] number of cap nodes n, [15] 0, then n triples
+ * [16+3i..] = (node, index of its parent in this list or -1 for r, frontier position or -1 for a summed-out node), parents
+ * first.  elx_quad_groups: number of records (0: no quad tables); elx_quad_get: the records in walk order and their alias
+ * rows qe32 / qlo16 [G][C][4][256] ([threshold bits 39..16 : 24][alias : 8] / threshold bits 15..0).
+ * elx_tree_quad_walk_info: host-only, the records of a tree (recs may be NULL; it must hold ELX_QUAD_REC_INTS * n_nodes). */
+#define ELX_QUAD_REC_INTS 52
+int32_t elx_quad_groups(const elx_handle *h);
+int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16);
+int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
 
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
  * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed); the result is a

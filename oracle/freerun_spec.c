@@ -20,6 +20,13 @@
  *   x16 as above with n = nodeA;  j = x16 & 15; r = x16 >> 4; e = pe16[g][c][parent state][j]
  *   r < e>>4 -> o = j ;  r > e>>4 -> o = e & 15 ;  tie -> philox(s lo, s hi, nodeA, 1).x0 < pqlo[g][c][parent state][j] ? j : e & 15
  * Records come in walk order (a record's parent is drawn by an earlier record; node_b = -1 for a group of one).
+ *
+ * Quad mode (models with K <= 4, leaves only; elynx_b200/csrc/elx_quad.cu): record g = (out[0..3] | r) draws the states of up to
+ * four frontier nodes below r at once from a 256-outcome joint row (inner nodes summed out), o = sum_k state(out[k]) << 2k:
+ *   x32 = word (s & 3) of philox(s>>2 lo, s>>2 hi, out[0], 0);  j = x32 & 255; t = x32 >> 8; e = qe32[g][c][state of r][j]
+ *   t < e>>8 -> o = j ;  t > e>>8 -> o = e & 255 ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 16) < qlo16[g][c][state of r][j] ? j : e & 255
+ * Records come in walk order (r is the root or a frontier node of an earlier record); recs = 52 int32 per record in the
+ * layout include/elynx_b200.h documents.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -152,4 +159,70 @@ int spec_freerun_pair(int N, int K, int C, int is_mixture, int rounds, const int
   }
   free(st); free(done);
   return 0;
+}
+
+#define QUAD_REC_INTS 52
+static int64_t quad_ties = 0;
+int64_t spec_quad_ties(void) { return quad_ties; } /* ties seen by the last spec_freerun_quad call */
+int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int32_t *leaf_row, const double *cumw,
+                      const double *cumpi, int G, const int32_t *recs, const uint32_t *qe32, const uint16_t *qlo16, uint64_t seed,
+                      int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch, int32_t *comps) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint8_t *st = (uint8_t *)malloc((size_t)N);
+  uint8_t *done = (uint8_t *)malloc((size_t)N);
+  int rc = 0;
+  quad_ties = 0;
+  for (int64_t col = 0; col < nsites && !rc; ++col) {
+    uint64_t s = (uint64_t)(site0 + col);
+    int c = 0;
+    if (is_mixture) {
+      uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 2};
+      philox(rounds, x, k0, k1);
+      uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+      c = cat_cum(cumw, C, (double)((w >> 11) + 1) * 0x1p-53);
+      if (c < 0) { rc = -(N + 1); break; }
+    }
+    if (comps) comps[col] = c;
+    uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 3};
+    philox(rounds, x, k0, k1);
+    uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+    int root = cat_cum(cumpi + (int64_t)c * K, K, (double)((w >> 11) + 1) * 0x1p-53);
+    if (root < 0) { rc = -(N + 2); break; }
+    for (int n = 0; n < N; ++n) done[n] = 0;
+    st[0] = (uint8_t)root; done[0] = 1;
+    for (int g = 0; g < G; ++g) {
+      const int32_t *r = recs + (size_t)g * QUAD_REC_INTS;
+      const int rt = r[0], n0 = r[1];
+      if (rt < 0 || rt >= N || !done[rt] || n0 < 0 || n0 >= N) { rc = -2; break; }  /* not in walk order */
+      uint64_t gg = s >> 2;
+      uint32_t y[4] = {(uint32_t)gg, (uint32_t)(gg >> 32), (uint32_t)n0, 0};
+      philox(rounds, y, k0, k1);
+      uint32_t x32 = y[s & 3], j = x32 & 255u, t = x32 >> 8;
+      int64_t idx = (((int64_t)g * C + c) * 4 + st[rt]) * 256 + j;
+      uint32_t e = qe32[idx], qh = e >> 8, al = e & 255u, o;
+      if (t < qh) o = j;
+      else if (t > qh) o = al;
+      else {
+        uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)n0, 1};
+        philox(rounds, z, k0, k1);
+        o = (z[0] >> 16) < qlo16[idx] ? j : al;
+        ++quad_ties;
+      }
+      for (int k = 0; k < 4; ++k) {
+        const int n = r[1 + k];
+        if (n < 0) continue;
+        if (n >= N || done[n]) { rc = -1; break; }
+        st[n] = (uint8_t)((o >> (2 * k)) & 3u); done[n] = 1;
+      }
+      if (rc) break;
+    }
+    if (rc) break;
+    for (int n = 0; n < N; ++n)
+      if (leaf_row[n] >= 0) {
+        if (!done[n]) { rc = -3; break; }
+        leaves[(int64_t)leaf_row[n] * leaves_pitch + col] = st[n];
+      }
+  }
+  free(st); free(done);
+  return rc;
 }

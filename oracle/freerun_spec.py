@@ -27,6 +27,8 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.spec_freerun.restype = C.c_int
         _lib.spec_freerun_pair.restype = C.c_int
+        _lib.spec_freerun_quad.restype = C.c_int
+        _lib.spec_quad_ties.restype = C.c_int64
     return _lib
 
 
@@ -94,3 +96,36 @@ def freerun(is_mixture, parent, leaf_row, ws, ds, e16, qlo, seed, site0, nsites,
     if rc:
         raise RuntimeError("spec_freerun rc=%d" % rc)
     return leaves[:, :nsites], comps[:nsites], (internal[:, :nsites] if keep_internal else None)
+
+
+QUAD_REC_INTS = 52
+
+
+def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites, rounds=10):
+    """Quad mode (K <= 4, leaves only): quad = (recs[G][52], qe32[G][C][4][256], qlo16[G][C][4][256]) in walk order."""
+    leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+    recs = np.ascontiguousarray(quad[0], dtype=np.int32)
+    qe32 = np.ascontiguousarray(quad[1], dtype=np.uint32)
+    qlo16 = np.ascontiguousarray(quad[2], dtype=np.uint16)
+    g, c, four, cols = qe32.shape
+    assert four == 4 and cols == 256 and qlo16.shape == qe32.shape and recs.shape == (g, QUAD_REC_INTS)
+    n = len(leaf_row)
+    k = np.asarray(ds).reshape(c, -1).shape[1]
+    cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
+    cumpi = np.ascontiguousarray(np.cumsum(np.asarray(ds, dtype=np.float64).reshape(c, k), axis=1))
+    t = int((leaf_row >= 0).sum())
+    leaves = np.zeros((t, max(nsites, 1)), dtype=np.uint8)
+    comps = np.zeros(max(nsites, 1), dtype=np.int32)
+    vp = C.c_void_p
+    rc = lib().spec_freerun_quad(n, k, c, int(bool(is_mixture)), rounds, vp(leaf_row.ctypes.data), vp(cumw.ctypes.data),
+                                 vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(qe32.ctypes.data), vp(qlo16.ctypes.data),
+                                 C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0), C.c_int64(nsites), vp(leaves.ctypes.data),
+                                 C.c_int64(max(nsites, 1)), vp(comps.ctypes.data))
+    if rc:
+        raise RuntimeError("spec_freerun_quad rc=%d" % rc)
+    return leaves[:, :nsites], comps[:nsites], None
+
+
+def quad_ties():
+    """Number of tied draws the last freerun_quad call had to refine."""
+    return int(lib().spec_quad_ties())

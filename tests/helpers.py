@@ -67,10 +67,14 @@ def uniforms(rng, rows, s):
 
 def spec_freerun(sim, model, tree, seed, site0, s, **kw):
     """The executable spec of the product's free-running draw for this handle, run on the handle's own tables:
-    pair mode (K <= 4: sibling pairs drawn jointly) or node by node."""
+    quad mode (K <= 4, leaves only: one draw per cap), pair mode (K <= 4: sibling pairs drawn jointly) or node by node."""
     import oracle.freerun_spec as spec
 
     is_mix, ws, ds = model[0], model[1], model[2]
+    quad = sim.quad_tables()
+    if quad is not None and not kw.get("keep_internal"):
+        kw.pop("keep_internal", None)
+        return spec.freerun_quad(is_mix, tree.parent, tree.leaf_row, ws, ds, quad, seed, site0, s, **kw)
     pair = sim.pair_tables()
     if pair is not None:
         return spec.freerun_pair(is_mix, tree.parent, tree.leaf_row, ws, ds, pair, seed, site0, s, **kw)
@@ -117,3 +121,118 @@ def check_pair_tables(p, pair, parent):
         for sb in range(k):
             joint[..., sa | (sb << 2)] = pa[..., sa] * pb[..., sb]
     assert np.max(np.abs(mass / float(1 << 48) - joint)) < 2.0 ** -44
+
+
+def quad_masses(qe32, qlo16):
+    """Integer outcome masses (sum 2^48 per row) encoded by quad alias rows qe32 = [q bits 39..16 : 24][alias : 8], qlo16."""
+    cap = 1 << 40
+    e = qe32.astype(np.int64)
+    al = e & 255
+    q = ((e >> 8) << 16) | qlo16.astype(np.int64)
+    q = np.where(al == np.arange(256), cap, q)
+    flat_q = q.reshape(-1, 256)
+    flat_al = al.reshape(-1, 256)
+    mass = flat_q.copy()
+    rows = np.arange(flat_q.shape[0])
+    for j in range(256):
+        np.add.at(mass, (rows, flat_al[:, j]), cap - flat_q[:, j])
+    return mass.reshape(q.shape)
+
+
+def check_quad_walk(recs, parent, leaf_row, n_slots=None):
+    """Structural validity of a quad walk: every leaf is a frontier node of exactly one record, every record hangs below a
+    node whose state is known (the root or an earlier frontier node), cap nodes form a connected piece below it with
+    parents listed first, inner nodes have ALL their children inside the cap, and slots are never read stale."""
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    for v in range(1, n):
+        kids[parent[v]].append(v)
+    known = {0: 0}      # node -> slot holding its state
+    live = {0: 0}       # slot -> node
+    drawn = set()
+    covered = set()     # nodes that appear in some cap (frontier or summed out)
+    for r in recs:
+        root, out, leaf, dst, src, ncap = int(r[0]), r[1:5], r[5:9], r[9:13], int(r[13]), int(r[14])
+        assert root in known and known[root] == src and live.get(src) == root, "record reads a slot that does not hold its root"
+        cap = [(int(r[16 + 3 * i]), int(r[17 + 3 * i]), int(r[18 + 3 * i])) for i in range(ncap)]
+        nodes = [c[0] for c in cap]
+        assert len(set(nodes)) == ncap
+        fr_seen = {}
+        for i, (node, par, fr) in enumerate(cap):
+            assert par < i
+            assert parent[node] == (root if par < 0 else cap[par][0])
+            assert node not in covered
+            covered.add(node)
+            if fr >= 0:
+                assert out[fr] == node and fr not in fr_seen
+                fr_seen[fr] = node
+                assert leaf[fr] == leaf_row[node]
+                assert (dst[fr] >= 0) == bool(kids[node])
+            else:
+                assert kids[node], "a leaf cannot be summed out"
+                in_cap = [c[0] for c in cap if c[1] == i]
+                assert sorted(in_cap) == sorted(kids[node]), "a summed-out node must have all its children in the cap"
+        assert sorted(fr_seen) == list(range(len(fr_seen))) and all(out[k] == -1 for k in range(len(fr_seen), 4))
+        # slots: src is read first, then the frontier slots are written; a slot may only be overwritten once every cap
+        # below the node it holds has been emitted (this record included)
+        for k, node in fr_seen.items():
+            drawn.add(node)
+            if dst[k] >= 0:
+                old = live.get(int(dst[k]))
+                if old is not None:
+                    assert all(c in covered for c in kids[old]), "slot overwritten while its node still has caps to draw"
+                    del known[old]
+                live[int(dst[k])] = node
+                known[node] = int(dst[k])
+    assert covered == set(range(1, n)), "every non-root node is in exactly one cap"
+    assert all(v in drawn for v in range(n) if leaf_row[v] >= 0 and v != 0)
+    for v in range(n):
+        if kids[v] and (v == 0 or v in drawn):
+            assert all(c in covered for c in kids[v])
+    if n_slots is not None:
+        assert max([0] + [int(x) for r in recs for x in list(r[9:13]) + [r[13]]]) < max(n_slots, 1)
+
+
+def quad_joint_reference(p, rec, k):
+    """P(frontier states | root state) [C][K][256] of one quad record by brute-force summation over the inner nodes."""
+    c = p.shape[1]
+    ncap = int(rec[14])
+    cap = [(int(rec[16 + 3 * i]), int(rec[17 + 3 * i]), int(rec[18 + 3 * i])) for i in range(ncap)]
+    inner = [i for i, x in enumerate(cap) if x[2] < 0]
+    out = np.zeros((c, k, 256))
+    nfr = sum(1 for x in cap if x[2] >= 0)
+    import itertools
+    for o in range(4 ** nfr):
+        fs = [(o >> (2 * f)) & 3 for f in range(nfr)]
+        if any(s >= k for s in fs):
+            continue
+        for assign in itertools.product(range(k), repeat=len(inner)):
+            st = {}
+            for i, a in zip(inner, assign):
+                st[i] = a
+            for i, x in enumerate(cap):
+                if x[2] >= 0:
+                    st[i] = fs[x[2]]
+            for root_state in range(k):
+                pr = np.ones(c)
+                for i, (node, par, fr) in enumerate(cap):
+                    ps = root_state if par < 0 else st[par]
+                    pr = pr * p[node, :, ps, st[i]]
+                out[:, root_state, o] += pr
+    return out
+
+
+def check_quad_tables(p, quad, parent, leaf_row, max_records=40):
+    """The walk is valid and the alias rows carry integer masses (sum 2^48) equal to the caps' joint probabilities."""
+    recs, qe32, qlo16 = quad
+    check_quad_walk(recs, parent, leaf_row)
+    k = p.shape[2]
+    mass = quad_masses(qe32, qlo16)
+    assert np.all(mass[:, :, :k].sum(-1) == 1 << 48)
+    pn = p / p.sum(-1, keepdims=True)
+    step = max(1, len(recs) // max_records)
+    for g in range(0, len(recs), step):
+        ref = quad_joint_reference(pn, recs[g], k)
+        ref = ref / ref.sum(-1, keepdims=True)
+        got = mass[g, :, :k] / float(1 << 48)
+        assert np.max(np.abs(got - ref)) < 2.0 ** -40, (g, np.max(np.abs(got - ref)))

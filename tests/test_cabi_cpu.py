@@ -223,3 +223,63 @@ def test_pair_walk_program():
         if binary and n > 1:
             assert ng.value == (n - 1) // 2 + 1
             assert ns.value <= int(math.floor(math.log2(n))) + 1, (n, ns.value)
+
+
+def test_quad_walk_program():
+    """Quad walk (K <= 4 models, leaves only): the tree is cut into caps of at most 4 frontier nodes; helpers.check_quad_walk
+    verifies the structure (every non-root node in exactly one cap, summed-out nodes keep all their children in the cap,
+    roots are known when read, slots never clobbered while live).  Binary trees need between T/4 and T/2 records."""
+    import ctypes as C
+
+    from helpers import check_quad_walk
+    from elynx_b200 import model as pm
+
+    rng = np.random.default_rng(6)
+    cases = []
+    for n, seed in ((1000, 1), (10000, 3), (3, 0), (2, 0), (257, 9)):
+        t = pm.birth_death_tree(n, 1.0, 0.5, seed=seed)
+        cases.append((np.asarray(t.parent), np.asarray(t.leaf_row), True))
+    cases.append((np.array([-1]), np.array([0]), True))
+    # ladder (caterpillar) with 3000 leaves, a star with 1000 leaves and a unary chain of 40 nodes above a cherry
+    parent, leaf_row, cur = [-1], [-1], 0
+    for i in range(2999):
+        parent += [cur, cur]
+        leaf_row += [i, -1 if i < 2998 else 2999]
+        cur = len(parent) - 1
+    cases.append((np.array(parent), np.array(leaf_row), True))
+    cases.append((np.array([-1] + [0] * 1000), np.array([-1] + list(range(1000))), False))
+    cases.append((np.array([-1] + list(range(40)) + [40, 40]), np.array([-1] * 41 + [0, 1]), False))
+    for _ in range(30):
+        parent = [-1]
+        n = int(rng.integers(2, 300))
+        stack = [0]
+        while len(parent) < n:
+            p = stack[-1]
+            if rng.random() < 0.35 and len(stack) > 1:
+                stack.pop()
+                continue
+            parent.append(p)
+            stack.append(len(parent) - 1)
+        parent = np.array(parent)
+        is_leaf = np.ones(len(parent), dtype=bool)
+        is_leaf[parent[1:]] = False
+        cases.append((parent, np.where(is_leaf, np.cumsum(is_leaf) - 1, -1), False))
+    for parent, leaf_row, binary in cases:
+        n = len(parent)
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+        brlen = np.zeros(n)
+        t = L.elx_tree(n, parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
+                       leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
+        ng, ns = C.c_int32(), C.c_int32()
+        L.check(L.lib().elx_tree_quad_walk_info(C.byref(t), C.byref(ng), C.byref(ns), None))
+        recs = np.full((max(ng.value, 1), L.ELX_QUAD_REC_INTS), -99, dtype=np.int32)
+        L.check(L.lib().elx_tree_quad_walk_info(C.byref(t), C.byref(ng), C.byref(ns), C.c_void_p(recs.ctypes.data)))
+        recs = recs[:ng.value]
+        check_quad_walk(recs, parent, leaf_row, ns.value)
+        nleaves = int((leaf_row >= 0).sum())
+        if n > 1:
+            assert (nleaves + 3) // 4 <= ng.value
+            assert ns.value <= 24
+        if binary and n > 3:
+            assert ng.value <= (nleaves + 1) // 2, (nleaves, ng.value)

@@ -7,7 +7,7 @@ import oracle.freerun_spec as spec
 import oracle.model as om
 import oracle.pruning as pruning
 import oracle.sim as osim
-from helpers import alias_masses, check_pair_tables, model_case, random_tree, spec_freerun, tree_from_file, uniforms
+from helpers import alias_masses, check_pair_tables, check_quad_tables, model_case, random_tree, spec_freerun, tree_from_file, uniforms
 
 pytestmark = pytest.mark.gpu
 
@@ -154,29 +154,38 @@ def check_alias_tables(p, e16, qlo, k):
                                              ("lg_g4", "UltraMetric.tree", 3000), ("c10", "UltraMetric.tree", 2000),
                                              ("mixture_dna", "Newick.tree", 2000), ("c60", "UltraMetric.tree", 9000),
                                              ("c60", "Newick.tree", 1000)])
-@pytest.mark.parametrize("force_generic,single_draws", [(True, False), (False, False), (True, True), (False, True)])
-def test_freerun_matches_spec(name, tree_file, s, force_generic, single_draws):
-    """Every free-running kernel (generic / tiled; pair mode / node by node) against the executable spec, on the
-    device's own tables, which are themselves checked against the P rows in exact integer arithmetic."""
+@pytest.mark.parametrize("force_generic", [True, False])
+@pytest.mark.parametrize("draws", ["default", "pair", "single"])
+def test_freerun_matches_spec(name, tree_file, s, force_generic, draws):
+    """Every free-running kernel (generic / tiled; quad mode / pair mode / node by node) against the executable spec, on
+    the device's own tables, which are themselves checked against the P rows in exact integer arithmetic."""
     model = model_case(name)
     is_mix, ws, ds, es, _ = model
     k = ds.shape[1]
-    if single_draws and k > 4:
-        pytest.skip("single_draws only changes models with K <= 4")
+    if draws != "default" and k > 4:
+        pytest.skip("pair_draws / single_draws only change models with K <= 4")
     tree = tree_from_file(tree_file)
-    with make_sim(model, tree, force_generic=force_generic, single_draws=single_draws) as sim:
+    with make_sim(model, tree, force_generic=force_generic, single_draws=draws == "single", pair_draws=draws == "pair") as sim:
         e16, qlo = sim.alias_tables()
         check_alias_tables(sim.ptables(), e16, qlo, k)
-        assert (sim.pair_groups > 0) == (k <= 4 and not single_draws)
+        assert (sim.pair_groups > 0) == (k <= 4 and draws != "single")
+        assert (sim.quad_groups > 0) == (k <= 4 and draws == "default")
         if sim.pair_groups:
             check_pair_tables(sim.ptables(), sim.pair_tables(), tree.parent)
+        if sim.quad_groups:
+            check_quad_tables(sim.ptables(), sim.quad_tables(), tree.parent, tree.leaf_row)
         for seed, site0 in ((0, 0), (0xDEADBEEFCAFEF00D, 0), (7, 8 * 1000003), (7, 13)):
+            # calls that keep the internal states never sum nodes out: pair mode / node by node
             leaves, comps, internal = sim.simulate(seed, s, site0=site0, want_comps=True, keep_internal=True)
             l0, c0, i0 = spec_freerun(sim, model, tree, seed, site0, s, keep_internal=True)
             assert np.array_equal(internal, i0), (seed, site0)
             assert np.array_equal(leaves, l0) and np.array_equal(comps, c0)
-            leaves2, comps2, _ = sim.simulate(seed, s, site0=site0, want_comps=True)  # the tiled kernels keep no internal states
-            assert np.array_equal(leaves2, l0) and np.array_equal(comps2, c0)
+            # leaves only: quad mode when the handle has it (a different stream), else the same stream as above
+            leaves2, comps2, _ = sim.simulate(seed, s, site0=site0, want_comps=True)
+            l1, c1, _ = spec_freerun(sim, model, tree, seed, site0, s)
+            assert np.array_equal(leaves2, l1) and np.array_equal(comps2, c1)
+            if not sim.quad_groups:
+                assert np.array_equal(l1, l0)
 
 
 @pytest.mark.parametrize("shape", ["multifurcating", "caterpillar", "unary", "single", "cherry"])
@@ -198,13 +207,19 @@ def test_pair_walk_odd_trees(shape):
     else:
         tree = om.parse_newick("(a:0.1,b:0.2):0.5;")
     for fg in (True, False):
-        with make_sim(model, tree, force_generic=fg) as sim:
-            check_pair_tables(sim.ptables(), sim.pair_tables(), tree.parent)
-            for s, site0 in ((4099, 0), (1000, 77)):
-                leaves, comps, internal = sim.simulate(5, s, site0=site0, want_comps=True, keep_internal=True)
-                l0, c0, i0 = spec_freerun(sim, model, tree, 5, site0, s, keep_internal=True)
-                assert np.array_equal(internal, i0) and np.array_equal(leaves, l0) and np.array_equal(comps, c0)
-                assert np.array_equal(sim.simulate(5, s, site0=site0)[0], l0)
+        for pair_draws in (True, False):
+            with make_sim(model, tree, force_generic=fg, pair_draws=pair_draws) as sim:
+                check_pair_tables(sim.ptables(), sim.pair_tables(), tree.parent)
+                assert (sim.quad_groups > 0) == (not pair_draws and tree.n_nodes > 1)
+                if sim.quad_groups:
+                    check_quad_tables(sim.ptables(), sim.quad_tables(), tree.parent, tree.leaf_row)
+                for s, site0 in ((4099, 0), (1000, 77)):
+                    leaves, comps, internal = sim.simulate(5, s, site0=site0, want_comps=True, keep_internal=True)
+                    l0, c0, i0 = spec_freerun(sim, model, tree, 5, site0, s, keep_internal=True)
+                    assert np.array_equal(internal, i0) and np.array_equal(leaves, l0) and np.array_equal(comps, c0)
+                    l1, c1, _ = spec_freerun(sim, model, tree, 5, site0, s)
+                    leaves2, comps2, _ = sim.simulate(5, s, site0=site0, want_comps=True)
+                    assert np.array_equal(leaves2, l1) and np.array_equal(comps2, c1)
 
 
 def test_freerun_refinement_path_is_exercised():
@@ -213,12 +228,27 @@ def test_freerun_refinement_path_is_exercised():
     model = model_case("hky")
     is_mix, ws, ds, es, _ = model
     tree = om.parse_newick("(" + ",".join("t%d:0.013" % i for i in range(64)) + ");")
-    for single in (False, True):
-        with make_sim(model, tree, single_draws=single) as sim:
+    for kw in ({"pair_draws": True}, {"single_draws": True}):
+        with make_sim(model, tree, **kw) as sim:
             s = 200000
             leaves, _, _ = sim.simulate(3, s)
             l0, _, _ = spec_freerun(sim, model, tree, 3, 0, s)
             assert np.array_equal(leaves, l0)
+
+
+def test_quad_refinement_path_is_exercised():
+    """Quad mode ties (draw == threshold in the high 24 bits) come at 2^-24 per draw: run enough draws that the spec sees
+    several, on both quad kernels."""
+    model = model_case("hky_g4")
+    tree = om.parse_newick("(" + ",".join("t%d:0.013" % i for i in range(64)) + ");")
+    s = 6_000_000  # 16 records x 6e6 sites = 9.6e7 draws: 5.7 ties expected
+    with make_sim(model, tree) as sim:
+        assert sim.quad_groups == 16
+        l0, _, _ = spec_freerun(sim, model, tree, 3, 0, s)
+        assert spec.quad_ties() > 0
+        assert np.array_equal(sim.simulate(3, s)[0], l0)
+    with make_sim(model, tree, force_generic=True) as sim:
+        assert np.array_equal(sim.simulate(3, s)[0], l0)
 
 
 def test_freerun_partition_invariance():
