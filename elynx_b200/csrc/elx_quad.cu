@@ -65,7 +65,7 @@ struct QuadTables {
   uint32_t *d_qe32 = nullptr;   // [G][C][4][256]
   uint16_t *d_qlo16 = nullptr;  // [G][C][4][256]
   uint8_t *d_ftab = nullptr;    // [G] x (32 B record + tb bytes of rows)
-  int tiled = 0, threads = 0, nstage = 0, tb = 0, stage_bytes = 0;
+  int tiled = 0, threads = 0, minb = 1, nstage = 0, tb = 0, stage_bytes = 0;
   size_t smem = 0;
 };
 
@@ -168,19 +168,6 @@ __global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, ui
   }
 }
 
-// stage image of record g: [QuadRecDev][C x 4 x 256 entries]
-__global__ void k_build_quad_ftab(int G, int stage_bytes, const QuadRecDev *__restrict__ recs, const uint32_t *__restrict__ qe32,
-                                  uint8_t *__restrict__ ftab) {
-  const int chunks = stage_bytes / 16;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)G * chunks) return;
-  const int g = (int)(i / chunks), ch = (int)(i % chunks);
-  uint4 v;
-  if (ch < 2) v = reinterpret_cast<const uint4 *>(recs + g)[ch];
-  else v = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(qe32) + (size_t)g * (stage_bytes - 32))[ch - 2];
-  reinterpret_cast<uint4 *>(ftab + (size_t)g * stage_bytes)[ch] = v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // K2 quad mode, generic: any C, tables through L1/L2, one thread per 4 consecutive sites (one Philox call per record).
 // ---------------------------------------------------------------------------------------------
@@ -263,12 +250,130 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// prmt.b32 in its default mode: selector nibble n picks byte (n & 7) of {a, b}; bit 3 of the nibble replicates that byte's
+// sign bit over the whole byte instead (__byte_perm masks the selector with 0x7777 and loses this)
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+  return d;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int ROUNDS, int THREADS>
-__global__ void __launch_bounds__(THREADS + 32, (THREADS <= 256 ? 2 : 1)) k2_quad_tiled(QuadArgs fa) {
+// Stage header of the tiled kernel (32 bytes in front of the record's rows), decoded on the host so that the loop
+// spends no instruction on it: out[k] >= 0: leaf row; out[k] = 0x80000000 | byte offset of the slot: internal frontier
+// node; out[k] = 0xffffffff: absent.
+struct QuadStageHdr {
+  uint32_t node0;
+  uint32_t src_off;  // byte offset of the slot holding the root's states (slot * THREADS * 16)
+  uint32_t pad[2];
+  uint32_t out[4];
+};
+static_assert(sizeof(QuadStageHdr) == 32, "QuadStageHdr must stay 32 bytes");
+
+// The record loop of one thread.  FAST: every 16-site group of this thread is stored with one aligned 128-bit store
+// (whole groups inside the site range, 16-byte aligned rows) -- the loop is compiled twice so that the common case
+// carries no store-mode tests.
+template <int ROUNDS, int THREADS, bool FAST>
+__device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t full_bar0, const uint32_t empty_bar0,
+                                             const uint32_t stage_smem, const uint32_t slot_base, const uint32_t CB0,
+                                             const uint32_t CB1, const uint32_t CB2, const uint32_t CB3, const int64_t sbase,
+                                             const int64_t col0, uint8_t *leaf_base, const int store_mode, const int lane) {
+  const SimArgs &a = fa.s;
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const uint64_t G0 = (uint64_t)sbase >> 2;  // a multiple of 4: the four counters of a record differ in the low 2 bits
+  const uint32_t G0lo = (uint32_t)G0, Ghi = (uint32_t)(G0 >> 32);
+  constexpr uint32_t SM = 0x03030303u;
+  const uint32_t slot_base_m = slot_base - 0x80000000u;  // + (0x80000000 | offset) = slot_base + offset
+  const int nstage = fa.nstage;
+  int buf = 0;
+  uint32_t phase = 0;
+  for (int g = 0; g < fa.G; ++g) {
+    mbar_wait(full_bar0 + 8u * (uint32_t)buf, phase);
+    const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
+    const uint4 h0 = lds_v4(sbuf);
+    const uint4 h1 = lds_v4(sbuf + 16u);
+    const uint32_t node0 = h0.x;
+    const uint32_t tbl = sbuf + 32u;
+#ifdef ELX_DEBUG_BOUNDS
+    if (h0.y >= (uint32_t)a.n_slots * THREADS * 16u || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
+#endif
+    const uint4 rv = lds_v4(slot_base + h0.y);
+    const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
+    uint32_t W[4];
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
+      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+      uint32_t c[4], t[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // entry index = row << 8 | j in ONE byte permute: byte 0 = j (low byte of the draw), byte 1 = row byte of site
+        // 4q+i, bytes 2,3 = that byte's sign replicated = 0 (rows are < 128)
+        const uint32_t idx = i == 0 ? prmt<0xcc40u>(w[i], Rq[q]) : i == 1 ? prmt<0xdd50u>(w[i], Rq[q])
+                           : i == 2 ? prmt<0xee60u>(w[i], Rq[q]) : prmt<0xff70u>(w[i], Rq[q]);
+#ifdef ELX_DEBUG_BOUNDS
+        if (idx * 4u + 4u > (uint32_t)fa.tb) atomicExch(a.error_flag, -7);
+#endif
+        const uint32_t e = lds_u32(tbl + idx * 4u);
+        c[i] = min(w[i], e);
+        t[i] = w[i] ^ e;
+      }
+      m = min(min(m, t[0]), min(t[1], min(t[2], t[3])));
+      W[q] = __byte_perm(__byte_perm(c[0], c[1], 0x0040u), __byte_perm(c[2], c[3], 0x0040u), 0x5410u);
+    }
+    if (m < 256u) {
+      // exact path (2^-24 per draw): some draw hit its threshold's high 24 bits; redo this thread's 16 draws one by one
+      // and settle the tied ones with 16 more random bits.  Rolled, call-free and array-free on purpose (elx_fast.cu).
+#pragma unroll 1
+      for (int s = 0; s < 16; ++s) {
+        const int q = s >> 2, i = s & 3;
+        const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
+        const uint32_t w = i == 0 ? x.x : (i == 1 ? x.y : (i == 2 ? x.z : x.w));
+        const uint32_t row = lds_u8(slot_base + h0.y + (uint32_t)s);
+        const uint32_t j = w & 0xffu, idx = (row << 8) | j;
+        const uint32_t e = lds_u32(tbl + idx * 4u);
+        if ((w ^ e) < 256u) {
+          const uint64_t sg = (uint64_t)sbase + (uint64_t)s;
+          const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), key);
+          const uint32_t ql = (uint32_t)__ldg(fa.qlo16 + ((((int64_t)g * a.C * 4 + row) << 8) | j));
+          const uint32_t o = (z.x >> 16) < ql ? j : (e & 0xffu);
+          const uint32_t sh = 8u * (uint32_t)i, keep = ~(0xffu << sh);
+          if (q == 0) W[0] = (W[0] & keep) | (o << sh);
+          if (q == 1) W[1] = (W[1] & keep) | (o << sh);
+          if (q == 2) W[2] = (W[2] & keep) | (o << sh);
+          if (q == 3) W[3] = (W[3] & keep) | (o << sh);
+        }
+      }
+    }
+    // this warp is done with the stage buffer (the header is in registers)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar0 + 8u * (uint32_t)buf);
+    if (++buf == nstage) { buf = 0; phase ^= 1u; }
+
+#define ELX_QUAD_OUT(k, code)                                                                                                  \
+  if ((int32_t)(code) >= 0) {                                                                                                  \
+    const uint4 v = make_uint4((W[0] >> (2 * k)) & SM, (W[1] >> (2 * k)) & SM, (W[2] >> (2 * k)) & SM, (W[3] >> (2 * k)) & SM); \
+    if (FAST) stg_cs_v4(leaf_base + (int64_t)(code) * a.leaves_pitch, v);                                                      \
+    else if (store_mode) store_leaf(a, leaf_base, (int)(code), col0, store_mode, v);                                           \
+  } else if ((code) != 0xffffffffu) {                                                                                          \
+    sts_v4(slot_base_m + (code),                                                                                               \
+           make_uint4(((W[0] >> (2 * k)) & SM) | CB0, ((W[1] >> (2 * k)) & SM) | CB1, ((W[2] >> (2 * k)) & SM) | CB2,          \
+                      ((W[3] >> (2 * k)) & SM) | CB3));                                                                        \
+  }
+    ELX_QUAD_OUT(0, h1.x)
+    ELX_QUAD_OUT(1, h1.y)
+    ELX_QUAD_OUT(2, h1.z)
+    ELX_QUAD_OUT(3, h1.w)
+#undef ELX_QUAD_OUT
+  }
+}
+
+template <int ROUNDS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS + 32, MINB) k2_quad_tiled(QuadArgs fa) {
   extern __shared__ __align__(128) uint8_t smem[];
   const SimArgs &a = fa.s;
   const int tid = threadIdx.x;
@@ -277,7 +382,6 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS <= 256 ? 2 : 1)) k2_qua
   uint64_t *empty_bar = full_bar + QUAD_MAX_NSTAGE;
   const uint32_t stage_smem = smem_u32(smem + 128);
   const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
-  constexpr uint32_t slot_stride = THREADS * 16u;
 
   if (tid == 0) {
     for (int i = 0; i < nstage; ++i) {
@@ -325,99 +429,44 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS <= 256 ? 2 : 1)) k2_qua
   }
   const uint32_t slot_base = slots_smem + (uint32_t)tid * 16u;
   sts_v4(slot_base, make_uint4(R[0], R[1], R[2], R[3]));  // slot 0 = the root states
-  int store_mode = !any ? 0
-                        : (full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
-                           ((col0 & 15) == 0)) ? 1 : 2;
-  asm volatile("" : "+r"(store_mode));
+  const int store_mode = !any ? 0
+                              : (full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
+                                 ((col0 & 15) == 0)) ? 1 : 2;
   uint8_t *leaf_base = a.leaves + col0;
-  asm volatile("" : "+l"(leaf_base));
-  const uint64_t G0 = (uint64_t)sbase >> 2;  // a multiple of 4: the four counters of a record differ in the low 2 bits
-  const uint32_t G0lo = (uint32_t)G0, Ghi = (uint32_t)(G0 >> 32);
-  constexpr uint32_t SM = 0x03030303u;
+  asm volatile("" : "+l"(leaf_base));  // keep the sum in registers: recomputed per store it costs two ALU adds
+  // the fast loop needs the whole WARP in store mode 1 (the loops synchronise per warp)
+  const bool fast = __all_sync(0xffffffffu, store_mode == 1);
+  if (fast)
+    quad_records<ROUNDS, THREADS, true>(fa, smem_u32(full_bar), smem_u32(empty_bar), stage_smem, slot_base, CB[0], CB[1], CB[2], CB[3],
+                                        sbase, col0, leaf_base, 1, tid & 31);
+  else
+    quad_records<ROUNDS, THREADS, false>(fa, smem_u32(full_bar), smem_u32(empty_bar), stage_smem, slot_base, CB[0], CB[1], CB[2], CB[3],
+                                         sbase, col0, leaf_base, store_mode, tid & 31);
+}
 
-  int buf = 0;
-  uint32_t phase = 0;
-  for (int g = 0; g < fa.G; ++g) {
-    mbar_wait(smem_u32(&full_bar[buf]), phase);
-    const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
-    const uint4 h0 = lds_v4(sbuf);
-    const uint4 h1 = lds_v4(sbuf + 16u);
-    const uint32_t node0 = h0.x;
-    const int src = (int)(int8_t)(h0.y & 0xffu);
-    const uint32_t tbl = sbuf + 32u;
-#ifdef ELX_DEBUG_BOUNDS
-    if (src < 0 || src >= a.n_slots || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
-#endif
-    const uint4 rv = lds_v4(slot_base + (uint32_t)src * slot_stride);
-    const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
-    uint32_t W[4];
-    uint32_t m = 0xffffffffu;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
-      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-      uint32_t c[4], t[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t rb = __byte_perm(Rq[q], 0u, 0x4404u | ((uint32_t)i << 4));  // row byte of site 4q+i -> bits 8..15
-        const uint32_t idx = (w[i] & 0xffu) | rb;
-#ifdef ELX_DEBUG_BOUNDS
-        if (idx * 4u + 4u > (uint32_t)fa.tb) atomicExch(a.error_flag, -7);
-#endif
-        const uint32_t e = lds_u32(tbl + idx * 4u);
-        c[i] = min(w[i], e);
-        t[i] = w[i] ^ e;
-      }
-      m = min(min(m, t[0]), min(t[1], min(t[2], t[3])));
-      W[q] = __byte_perm(__byte_perm(c[0], c[1], 0x0040u), __byte_perm(c[2], c[3], 0x0040u), 0x5410u);
+// stage image of record g: [QuadStageHdr][C x 4 x 256 entries]
+__global__ void k_build_quad_ftab(int G, int stage_bytes, int threads, const QuadRecDev *__restrict__ recs, const uint32_t *__restrict__ qe32,
+                                  uint8_t *__restrict__ ftab) {
+  const int chunks = stage_bytes / 16;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)G * chunks) return;
+  const int g = (int)(i / chunks), ch = (int)(i % chunks);
+  uint4 v;
+  if (ch < 2) {
+    const QuadRecDev r = recs[g];
+    const uint32_t stride = (uint32_t)threads * 16u;
+    if (ch == 0) {
+      v = make_uint4(r.node0, (uint32_t)r.src * stride, 0u, 0u);
+    } else {
+      uint32_t o[4];
+      for (int k = 0; k < 4; ++k)
+        o[k] = r.leaf[k] >= 0 ? (uint32_t)r.leaf[k] : (r.dst[k] >= 0 ? (0x80000000u | ((uint32_t)r.dst[k] * stride)) : 0xffffffffu);
+      v = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    if (m < 256u) {
-      // exact path (2^-24 per draw): some draw hit its threshold's high 24 bits; redo this thread's 16 draws one by one
-      // and settle the tied ones with 16 more random bits.  Rolled, call-free and array-free on purpose (elx_fast.cu).
-#pragma unroll 1
-      for (int s = 0; s < 16; ++s) {
-        const int q = s >> 2, i = s & 3;
-        const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
-        const uint32_t w = i == 0 ? x.x : (i == 1 ? x.y : (i == 2 ? x.z : x.w));
-        const uint32_t row = lds_u8(slot_base + (uint32_t)src * slot_stride + (uint32_t)s);
-        const uint32_t j = w & 0xffu, idx = (row << 8) | j;
-        const uint32_t e = lds_u32(tbl + idx * 4u);
-        if ((w ^ e) < 256u) {
-          const uint64_t sg = (uint64_t)sbase + (uint64_t)s;
-          const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), key);
-          const uint32_t ql = (uint32_t)__ldg(fa.qlo16 + ((((int64_t)g * a.C * 4 + row) << 8) | j));
-          const uint32_t o = (z.x >> 16) < ql ? j : (e & 0xffu);
-          const uint32_t sh = 8u * (uint32_t)i, keep = ~(0xffu << sh);
-          if (q == 0) W[0] = (W[0] & keep) | (o << sh);
-          if (q == 1) W[1] = (W[1] & keep) | (o << sh);
-          if (q == 2) W[2] = (W[2] & keep) | (o << sh);
-          if (q == 3) W[3] = (W[3] & keep) | (o << sh);
-        }
-      }
-    }
-    // this warp is done with the stage buffer (header fields are in registers)
-    const int dst0 = (int)(int8_t)((h0.y >> 8) & 0xffu), dst1 = (int)(int8_t)((h0.y >> 16) & 0xffu), dst2 = (int)(int8_t)(h0.y >> 24),
-              dst3 = (int)(int8_t)(h0.z & 0xffu);
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[buf]));
-    if (++buf == nstage) { buf = 0; phase ^= 1u; }
-
-#define ELX_QUAD_OUT(k, leafk, dstk)                                                                                          \
-  if ((leafk) >= 0) {                                                                                                         \
-    if (store_mode)                                                                                                           \
-      store_leaf(a, leaf_base, (leafk), col0, store_mode,                                                                     \
-                 make_uint4((W[0] >> (2 * k)) & SM, (W[1] >> (2 * k)) & SM, (W[2] >> (2 * k)) & SM, (W[3] >> (2 * k)) & SM)); \
-  } else if ((dstk) >= 0) {                                                                                                   \
-    sts_v4(slot_base + (uint32_t)(dstk) * slot_stride,                                                                        \
-           make_uint4(((W[0] >> (2 * k)) & SM) | CB[0], ((W[1] >> (2 * k)) & SM) | CB[1], ((W[2] >> (2 * k)) & SM) | CB[2],   \
-                      ((W[3] >> (2 * k)) & SM) | CB[3]));                                                                     \
+  } else {
+    v = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(qe32) + (size_t)g * (stage_bytes - 32))[ch - 2];
   }
-    ELX_QUAD_OUT(0, (int)h1.x, dst0)
-    ELX_QUAD_OUT(1, (int)h1.y, dst1)
-    ELX_QUAD_OUT(2, (int)h1.z, dst2)
-    ELX_QUAD_OUT(3, (int)h1.w, dst3)
-#undef ELX_QUAD_OUT
-  }
+  reinterpret_cast<uint4 *>(ftab + (size_t)g * stage_bytes)[ch] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,18 +495,21 @@ void quad_rec_to_ints(const QuadRec &r, int32_t *o) {
   }
 }
 
-// Geometry of the tiled kernel: the biggest CTA whose slot stack leaves room for a ring of at least two stages.
+// Geometry of the tiled kernel: CTA size x CTAs per SM, preferred order first (measured on cfg2: 2 x 256 threads beats
+// 1 x 512 by 5 %); the slot stack must leave room for a ring of at least two stages.
 static bool quad_geometry(int C, int n_slots, QuadTables *qt) {
   const int tb = C * 4 * QUAD_COLS * 4;
   const size_t stage = 32 + (size_t)tb;
-  int want_threads = 0, want_stages = 0;
+  int want_threads = 0, want_stages = 0, want_minb = 0;
   if (const char *e = getenv("ELX_QUAD_THREADS")) want_threads = atoi(e);  // tuning knobs
   if (const char *e = getenv("ELX_QUAD_NSTAGE")) want_stages = atoi(e);
-  const int cand[4] = {512, 384, 256, 256};
-  for (int ci = 0; ci < 4; ++ci) {
-    const int th = cand[ci];
+  if (const char *e = getenv("ELX_QUAD_MINB")) want_minb = atoi(e);
+  const int cand[5][2] = {{256, 2}, {512, 1}, {384, 1}, {256, 1}, {256, 3}};
+  for (int ci = 0; ci < 5; ++ci) {
+    const int th = cand[ci][0], minb = cand[ci][1];
     if (want_threads && th != want_threads) continue;
-    const size_t per_cta = ci == 2 ? 113 * 1024 : 226 * 1024;  // 256 threads: two CTAs per SM when they fit
+    if (want_minb ? minb != want_minb : minb == 3) continue;  // three CTAs per SM only on request
+    const size_t per_cta = (size_t)226 * 1024 / minb;
     const size_t slots = (size_t)(n_slots > 0 ? n_slots : 1) * th * 16;
     if (128 + 2 * stage + slots > per_cta) continue;
     int nstage = (int)((per_cta - 128 - slots) / stage);
@@ -465,7 +517,7 @@ static bool quad_geometry(int C, int n_slots, QuadTables *qt) {
     if (nstage > cap) nstage = cap;
     if (nstage > QUAD_MAX_NSTAGE) nstage = QUAD_MAX_NSTAGE;
     if (nstage < 2) continue;
-    qt->tiled = 1; qt->threads = th; qt->nstage = nstage; qt->tb = tb; qt->stage_bytes = (int)stage;
+    qt->tiled = 1; qt->threads = th; qt->minb = minb; qt->nstage = nstage; qt->tb = tb; qt->stage_bytes = (int)stage;
     qt->smem = 128 + (size_t)nstage * stage + slots;
     return true;
   }
@@ -477,7 +529,7 @@ int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
   compile_quad_walk(h->N, parent, leaf_row, qt->prog);
   const int G = qt->G = (int)qt->prog.recs.size();
   // quad mode needs the tiled geometry (or at least the generic kernel's slot array); otherwise the handle stays in pair mode
-  if (G == 0 || qt->prog.n_slots > QUAD_MAX_SLOTS || (int64_t)h->C * 4 > 255) { delete qt; return 0; }
+  if (G == 0 || qt->prog.n_slots > QUAD_MAX_SLOTS || (int64_t)h->C * 4 > 127) { delete qt; return 0; }
   quad_geometry(h->C, qt->prog.n_slots, qt);
   h->quad = qt;
   std::vector<QuadRecDev> dev((size_t)G);
@@ -520,7 +572,7 @@ int quad_tables_build(elx_handle *h) {
   QUAD_CUDA(h, cudaGetLastError());
   if (qt->tiled) {
     const int64_t n = (int64_t)qt->G * (qt->stage_bytes / 16);
-    k_build_quad_ftab<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(qt->G, qt->stage_bytes, qt->d_recs, qt->d_qe32, qt->d_ftab);
+    k_build_quad_ftab<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(qt->G, qt->stage_bytes, qt->threads, qt->d_recs, qt->d_qe32, qt->d_ftab);
     h->launches++;
     QUAD_CUDA(h, cudaGetLastError());
   }
@@ -547,21 +599,23 @@ int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16) {
   return 0;
 }
 
-template <int ROUNDS, int THREADS>
+template <int ROUNDS, int THREADS, int MINB>
 static cudaError_t launch_quad_tiled(const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(k2_quad_tiled<ROUNDS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k2_quad_tiled<ROUNDS, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((groups + THREADS - 1) / THREADS);
-  k2_quad_tiled<ROUNDS, THREADS><<<blocks, THREADS + 32, smem, stream>>>(fa);
+  k2_quad_tiled<ROUNDS, THREADS, MINB><<<blocks, THREADS + 32, smem, stream>>>(fa);
   return cudaGetLastError();
 }
 
 template <int ROUNDS>
-static cudaError_t launch_quad_tiled_t(int threads, const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
-  switch (threads) {
-    case 512: return launch_quad_tiled<ROUNDS, 512>(fa, groups, smem, stream);
-    case 384: return launch_quad_tiled<ROUNDS, 384>(fa, groups, smem, stream);
-    default: return launch_quad_tiled<ROUNDS, 256>(fa, groups, smem, stream);
+static cudaError_t launch_quad_tiled_t(int threads, int minb, const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
+  switch (threads * 10 + minb) {
+    case 5121: return launch_quad_tiled<ROUNDS, 512, 1>(fa, groups, smem, stream);
+    case 3841: return launch_quad_tiled<ROUNDS, 384, 1>(fa, groups, smem, stream);
+    case 2563: return launch_quad_tiled<ROUNDS, 256, 3>(fa, groups, smem, stream);
+    case 2562: return launch_quad_tiled<ROUNDS, 256, 2>(fa, groups, smem, stream);
+    default: return launch_quad_tiled<ROUNDS, 256, 1>(fa, groups, smem, stream);
   }
 }
 
@@ -577,8 +631,8 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
   cudaError_t e;
   if (qt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC)) {
     const int64_t g0 = a.site0 >> 4, g1 = (a.site0 + a.nsites + 15) >> 4;
-    e = h->rounds == 7 ? launch_quad_tiled_t<7>(qt->threads, fa, g1 - g0, qt->smem, h->stream)
-                       : launch_quad_tiled_t<10>(qt->threads, fa, g1 - g0, qt->smem, h->stream);
+    e = h->rounds == 7 ? launch_quad_tiled_t<7>(qt->threads, qt->minb, fa, g1 - g0, qt->smem, h->stream)
+                       : launch_quad_tiled_t<10>(qt->threads, qt->minb, fa, g1 - g0, qt->smem, h->stream);
   } else {
     const int64_t g0 = a.site0 >> 2, g1 = (a.site0 + a.nsites + 3) >> 2;
     const unsigned blocks = (unsigned)((g1 - g0 + 127) / 128);
