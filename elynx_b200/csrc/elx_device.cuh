@@ -33,6 +33,28 @@ __host__ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
   return c;
 }
 
+// The same function with the ten round keys (k + r * W) precomputed by the host: passed inside a kernel parameter block
+// they are constant-bank operands of the XORs instead of twenty live registers per thread.
+struct PhiloxRoundKeys {
+  uint32_t k[20];
+};
+inline PhiloxRoundKeys philox_round_keys(uint64_t seed) {
+  PhiloxRoundKeys rk;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+  return rk;
+}
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32_rk(uint4 c, const PhiloxRoundKeys &rk) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ rk.k[2 * r], lo1, hi0 ^ c.w ^ rk.k[2 * r + 1], lo0);
+  }
+  return c;
+}
+
 // 53-bit uniform in (0,1] from two Philox words (used for the component and root-state draws).
 __host__ __device__ __forceinline__ double u53_positive(uint32_t lo, uint32_t hi) {
   uint64_t w = ((uint64_t)hi << 32) | lo;

@@ -65,7 +65,7 @@ struct QuadTables {
   uint32_t *d_qe32 = nullptr;   // [G][C][4][256]
   uint16_t *d_qlo16 = nullptr;  // [G][C][4][256]
   uint8_t *d_ftab = nullptr;    // [G] x (32 B record + tb bytes of rows)
-  int tiled = 0, threads = 0, minb = 1, nstage = 0, tb = 0, stage_bytes = 0;
+  int tiled = 0, threads = 0, minb = 1, nstage = 0, tb = 0, stage_bytes = 0;  // threads: the CTA class (MAXT)
   size_t smem = 0;
 };
 
@@ -76,7 +76,8 @@ struct QuadArgs {
   const uint32_t *qe32;
   const uint16_t *qlo16;
   const uint8_t *ftab;
-  int tb, stage_bytes, nstage;
+  int tb, stage_bytes, nstage, slot_stride;
+  PhiloxRoundKeys rk;  // of the call's seed
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -267,7 +268,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // node; out[k] = 0xffffffff: absent.
 struct QuadStageHdr {
   uint32_t node0;
-  uint32_t src_off;  // byte offset of the slot holding the root's states (slot * THREADS * 16)
+  uint32_t src_off;  // byte offset of the slot holding the root's states (slot * slot stride)
   uint32_t pad[2];
   uint32_t out[4];
 };
@@ -276,7 +277,7 @@ static_assert(sizeof(QuadStageHdr) == 32, "QuadStageHdr must stay 32 bytes");
 // The record loop of one thread.  FAST: every 16-site group of this thread is stored with one aligned 128-bit store
 // (whole groups inside the site range, 16-byte aligned rows) -- the loop is compiled twice so that the common case
 // carries no store-mode tests.
-template <int ROUNDS, int THREADS, bool FAST>
+template <int ROUNDS, bool FAST>
 __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t full_bar0, const uint32_t empty_bar0,
                                              const uint32_t stage_smem, const uint32_t slot_base, const uint32_t CB0,
                                              const uint32_t CB1, const uint32_t CB2, const uint32_t CB3, const int64_t sbase,
@@ -298,7 +299,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
     const uint32_t node0 = h0.x;
     const uint32_t tbl = sbuf + 32u;
 #ifdef ELX_DEBUG_BOUNDS
-    if (h0.y >= (uint32_t)a.n_slots * THREADS * 16u || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
+    if (h0.y >= (uint32_t)a.n_slots * (uint32_t)fa.slot_stride || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
 #endif
     const uint4 rv = lds_v4(slot_base + h0.y);
     const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -306,7 +307,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
     uint32_t m = 0xffffffffu;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
+      const uint4 x = philox4x32_rk<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), fa.rk);
       const uint32_t w[4] = {x.x, x.y, x.z, x.w};
       uint32_t c[4], t[4];
 #pragma unroll
@@ -372,8 +373,12 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
   }
 }
 
-template <int ROUNDS, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS + 32, MINB) k2_quad_tiled(QuadArgs fa) {
+// MAXT: the largest CTA this instantiation is launched with (register budget); the actual number of consumer threads is
+// blockDim.x - 32, any multiple of 32 (the launch picks MAXT; smaller CTAs are a tuning knob).  Slots are MAXT * 16 bytes
+// apart whatever the CTA size, so that the stage headers (slot byte offsets) do not depend on it.
+template <int ROUNDS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT + 32, MINB) k2_quad_tiled(QuadArgs fa) {
+  const int THREADS = (int)blockDim.x - 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const SimArgs &a = fa.s;
   const int tid = threadIdx.x;
@@ -437,10 +442,10 @@ __global__ void __launch_bounds__(THREADS + 32, MINB) k2_quad_tiled(QuadArgs fa)
   // the fast loop needs the whole WARP in store mode 1 (the loops synchronise per warp)
   const bool fast = __all_sync(0xffffffffu, store_mode == 1);
   if (fast)
-    quad_records<ROUNDS, THREADS, true>(fa, smem_u32(full_bar), smem_u32(empty_bar), stage_smem, slot_base, CB[0], CB[1], CB[2], CB[3],
+    quad_records<ROUNDS, true>(fa, smem_u32(full_bar), smem_u32(empty_bar), stage_smem, slot_base, CB[0], CB[1], CB[2], CB[3],
                                         sbase, col0, leaf_base, 1, tid & 31);
   else
-    quad_records<ROUNDS, THREADS, false>(fa, smem_u32(full_bar), smem_u32(empty_bar), stage_smem, slot_base, CB[0], CB[1], CB[2], CB[3],
+    quad_records<ROUNDS, false>(fa, smem_u32(full_bar), smem_u32(empty_bar), stage_smem, slot_base, CB[0], CB[1], CB[2], CB[3],
                                          sbase, col0, leaf_base, store_mode, tid & 31);
 }
 
@@ -504,11 +509,11 @@ static bool quad_geometry(int C, int n_slots, QuadTables *qt) {
   if (const char *e = getenv("ELX_QUAD_THREADS")) want_threads = atoi(e);  // tuning knobs
   if (const char *e = getenv("ELX_QUAD_NSTAGE")) want_stages = atoi(e);
   if (const char *e = getenv("ELX_QUAD_MINB")) want_minb = atoi(e);
-  const int cand[5][2] = {{256, 2}, {512, 1}, {384, 1}, {256, 1}, {256, 3}};
-  for (int ci = 0; ci < 5; ++ci) {
+  const int cand[3][2] = {{256, 2}, {512, 1}, {256, 1}};
+  for (int ci = 0; ci < 3; ++ci) {
     const int th = cand[ci][0], minb = cand[ci][1];
     if (want_threads && th != want_threads) continue;
-    if (want_minb ? minb != want_minb : minb == 3) continue;  // three CTAs per SM only on request
+    if (want_minb && minb != want_minb) continue;
     const size_t per_cta = (size_t)226 * 1024 / minb;
     const size_t slots = (size_t)(n_slots > 0 ? n_slots : 1) * th * 16;
     if (128 + 2 * stage + slots > per_cta) continue;
@@ -544,8 +549,8 @@ int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
     for (int k = 0; k < 4; ++k) { d.dst[k] = r.dst[k]; d.leaf[k] = r.leaf[k]; if (r.out[k] >= 0) d.nfr++; }
     QuadCapDev &c = caps[g];
     memset(&c, 0, sizeof c);
-    c.n = r.n_cap;
-    for (int i = 0; i < r.n_cap; ++i) { c.node[i] = r.cap[i].node; c.par[i] = r.cap[i].par; c.fr[i] = r.cap[i].fr; }
+    c.n = r.n_cap < QUAD_MAX_CAP ? r.n_cap : QUAD_MAX_CAP;
+    for (int i = 0; i < c.n && i < QUAD_MAX_CAP; ++i) { c.node[i] = r.cap[i].node; c.par[i] = r.cap[i].par; c.fr[i] = r.cap[i].fr; }
   }
   const size_t ents = (size_t)G * h->C * 4 * QUAD_COLS;
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_recs, sizeof(QuadRecDev) * (size_t)G));
@@ -599,24 +604,21 @@ int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16) {
   return 0;
 }
 
-template <int ROUNDS, int THREADS, int MINB>
-static cudaError_t launch_quad_tiled(const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(k2_quad_tiled<ROUNDS, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int ROUNDS, int MAXT, int MINB>
+static cudaError_t launch_quad_tiled(int threads, const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(k2_quad_tiled<ROUNDS, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const unsigned blocks = (unsigned)((groups + THREADS - 1) / THREADS);
-  k2_quad_tiled<ROUNDS, THREADS, MINB><<<blocks, THREADS + 32, smem, stream>>>(fa);
+  const unsigned blocks = (unsigned)((groups + threads - 1) / threads);
+  k2_quad_tiled<ROUNDS, MAXT, MINB><<<blocks, threads + 32, smem, stream>>>(fa);
   return cudaGetLastError();
 }
 
 template <int ROUNDS>
-static cudaError_t launch_quad_tiled_t(int threads, int minb, const QuadArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
-  switch (threads * 10 + minb) {
-    case 5121: return launch_quad_tiled<ROUNDS, 512, 1>(fa, groups, smem, stream);
-    case 3841: return launch_quad_tiled<ROUNDS, 384, 1>(fa, groups, smem, stream);
-    case 2563: return launch_quad_tiled<ROUNDS, 256, 3>(fa, groups, smem, stream);
-    case 2562: return launch_quad_tiled<ROUNDS, 256, 2>(fa, groups, smem, stream);
-    default: return launch_quad_tiled<ROUNDS, 256, 1>(fa, groups, smem, stream);
-  }
+static cudaError_t launch_quad_tiled_t(int maxt, int minb, int threads, const QuadArgs &fa, int64_t groups, size_t smem,
+                                       cudaStream_t stream) {
+  if (maxt == 512) return launch_quad_tiled<ROUNDS, 512, 1>(threads, fa, groups, smem, stream);
+  if (minb == 2) return launch_quad_tiled<ROUNDS, 256, 2>(threads, fa, groups, smem, stream);
+  return launch_quad_tiled<ROUNDS, 256, 1>(threads, fa, groups, smem, stream);
 }
 
 int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
@@ -627,12 +629,20 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
   fa.s = a;
   fa.s.n_slots = qt->prog.n_slots;
   fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qlo16 = qt->d_qlo16; fa.ftab = qt->d_ftab;
-  fa.tb = qt->tb; fa.stage_bytes = qt->stage_bytes; fa.nstage = qt->nstage;
+  fa.tb = qt->tb; fa.stage_bytes = qt->stage_bytes; fa.nstage = qt->nstage; fa.slot_stride = qt->threads * 16;
+  fa.rk = philox_round_keys(a.seed);
   cudaError_t e;
   if (qt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC)) {
     const int64_t g0 = a.site0 >> 4, g1 = (a.site0 + a.nsites + 15) >> 4;
-    e = h->rounds == 7 ? launch_quad_tiled_t<7>(qt->threads, qt->minb, fa, g1 - g0, qt->smem, h->stream)
-                       : launch_quad_tiled_t<10>(qt->threads, qt->minb, fa, g1 - g0, qt->smem, h->stream);
+    // Measured on cfg2 (B200): SM throughput saturates at 16 consumer warps (2 x 256 or 1 x 512 threads) and drops with
+    // smaller CTAs faster than a better-filled last wave gains, so every launch uses the largest CTA of its class.
+    int threads = qt->threads;
+    if (const char *ev = getenv("ELX_QUAD_CTA")) {  // tuning knob: a smaller CTA
+      const int t = atoi(ev);
+      if (t >= 32 && t <= qt->threads && t % 32 == 0) threads = t;
+    }
+    e = h->rounds == 7 ? launch_quad_tiled_t<7>(qt->threads, qt->minb, threads, fa, g1 - g0, qt->smem, h->stream)
+                       : launch_quad_tiled_t<10>(qt->threads, qt->minb, threads, fa, g1 - g0, qt->smem, h->stream);
   } else {
     const int64_t g0 = a.site0 >> 2, g1 = (a.site0 + a.nsites + 3) >> 2;
     const unsigned blocks = (unsigned)((g1 - g0 + 127) / 128);
