@@ -819,10 +819,10 @@ int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16
 
 int32_t elx_quad_groups(const elx_handle *h) { return h ? quad_groups(h) : 0; }
 
-int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16) {
+int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24) {
   if (!h) return fail(nullptr, ELX_E_INVALID, "elx_quad_get: null handle");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  return quad_get(h, recs, qe32, qlo16);
+  return quad_get(h, recs, qe32, qlo24);
 }
 
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves, int64_t leaves_pitch,

@@ -10,12 +10,15 @@
 // cells per draw instead of 1 (pair mode) or 0.5 (node by node), and every per-draw cost of the hot loop shrinks alike.
 //
 // Draw specification (oracle/freerun_spec.c spec_freerun_quad executes it on the CPU; kernels must agree bit for bit):
-//   record g = (out[0..3] | r), site s, component c, state i of r:
-//     x32 = word (s & 3) of philox(s>>2 lo, s>>2 hi, out[0], TAG_NODE);  x32 = [t : 24][j : 8]
-//     e = qe32[g][c][i][j] = [q_hi : 24][alias : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
-//     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 16) < qlo16[g][c][i][j] ? j : alias
+//   record g = (out[0..3] | r), site s, component c, state i of r.  A draw is 24 bits: the 16 sites of a group s >> 4 share
+//   three Philox calls, 48 bytes B[0..47] = little-endian words of philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2:
+//     x24 = B[3d] | B[3d+1] << 8 | B[3d+2] << 16,  d = s & 15;   x24 = [t : 16][j : 8]
+//     e = qe32[g][c][i][j] = [q_hi : 16][alias : 8][0 : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
+//     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 8) < qlo24[g][c][i][j] ? j : alias
 //     state(out[k]) = (o >> 2k) & 3
-// The joint rows carry integer masses round(p / sum * 2^48) (Vose pairing in exact integer arithmetic, column capacity 2^40).
+// The joint rows carry integer masses round(p / sum * 2^48) (Vose pairing in exact integer arithmetic, column capacity
+// 2^40 = 16 high + 24 low threshold bits); ties come at 2^-16 per draw and are settled exactly.  24-bit draws instead of
+// 32-bit ones cut the Philox work -- 60 % of the hot loop -- by a quarter.
 //
 // Kernels: k1_quad_joint, k1_alias_quad (tables), k2_quad_generic (tables through L1/L2; the cross-check),
 // k2_quad_tiled (the hot kernel: one record + its 4 KB x C joint rows per stage, streamed through shared memory by a
@@ -63,7 +66,7 @@ struct QuadTables {
   QuadCapDev *d_caps = nullptr;
   double *d_joint = nullptr;    // [G][C][4][256]
   uint32_t *d_qe32 = nullptr;   // [G][C][4][256]
-  uint16_t *d_qlo16 = nullptr;  // [G][C][4][256]
+  uint32_t *d_qlo24 = nullptr;  // [G][C][4][256]
   uint8_t *d_ftab = nullptr;    // [G] x (32 B record + tb bytes of rows)
   int tiled = 0, threads = 0, minb = 1, nstage = 0, tb = 0, stage_bytes = 0;  // threads: the CTA class (MAXT)
   size_t smem = 0;
@@ -74,7 +77,7 @@ struct QuadArgs {
   int G;
   const QuadRecDev *recs;
   const uint32_t *qe32;
-  const uint16_t *qlo16;
+  const uint32_t *qlo24;
   const uint8_t *ftab;
   int tb, stage_bytes, nstage, slot_stride;
   PhiloxRoundKeys rk;  // of the call's seed
@@ -127,8 +130,8 @@ __global__ void k1_quad_joint(int G, int C, int K, const QuadCapDev *__restrict_
 }
 
 // Alias rows of 256 columns: integer masses m_o = round(p_o / sum * 2^48) (residual to the largest), Vose pairing, column
-// capacity 2^40; entry = [threshold bits 39..16 : 24][alias : 8], qlo16 = threshold bits 15..0.  One thread per row.
-__global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, uint32_t *__restrict__ e32, uint16_t *__restrict__ qlo16) {
+// capacity 2^40; entry = [threshold bits 39..24 : 16][alias : 8][0 : 8], qlo24 = threshold bits 23..0.  One thread per row.
+__global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, uint32_t *__restrict__ e32, uint32_t *__restrict__ qlo24) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   constexpr int KP = QUAD_COLS;
@@ -164,34 +167,44 @@ __global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, ui
     int64_t qq = q[j];
     int al = alias[j];
     if (qq >= CAP) { qq = CAP - 1; al = j; }  // a full column: always accept (alias = self)
-    e32[r * KP + j] = (uint32_t)(((qq >> 16) << 8) | (int64_t)al);
-    qlo16[r * KP + j] = (uint16_t)(qq & 0xffff);
+    e32[r * KP + j] = (uint32_t)(((qq >> 24) << 16) | ((int64_t)al << 8));
+    qlo24[r * KP + j] = (uint32_t)(qq & 0xffffff);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 quad mode, generic: any C, tables through L1/L2, one thread per 4 consecutive sites (one Philox call per record).
+// K2 quad mode, generic: any C, tables through L1/L2, one thread per site (it recomputes the three Philox calls of its
+// 16-site group for every record: the cross-check of the tiled kernel, not a fast path).
 // ---------------------------------------------------------------------------------------------
+template <int ROUNDS>
+__device__ __forceinline__ uint32_t quad_draw24(uint64_t s, uint32_t node0, uint2 key) {
+  const uint64_t grp = s >> 4;
+  const int d = (int)(s & 15), byte0 = 3 * d, call = byte0 >> 4, call2 = (byte0 + 2) >> 4;
+  const uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), node0, 4u * (uint32_t)call), key);
+  uint4 y = x;
+  if (call2 != call) y = philox4x32<ROUNDS>(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), node0, 4u * (uint32_t)call2), key);
+  const uint32_t wx[4] = {x.x, x.y, x.z, x.w}, wy[4] = {y.x, y.y, y.z, y.w};
+  uint32_t v = 0;
+  for (int b = 0; b < 3; ++b) {
+    const int pos = byte0 + b;
+    const uint32_t word = (pos >> 4) == call ? wx[(pos >> 2) & 3] : wy[(pos >> 2) & 3];
+    v |= ((word >> (8 * (pos & 3))) & 0xffu) << (8 * b);
+  }
+  return v;
+}
+
 template <int ROUNDS>
 __global__ void k2_quad_generic(QuadArgs fa) {
   const SimArgs &a = fa.s;
-  const int64_t g4 = (a.site0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t sbase = g4 << 2;
-  if (sbase >= a.site0 + a.nsites) return;
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.nsites) return;
+  const uint64_t s = (uint64_t)(a.site0 + col);
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-  uint32_t slot[QUAD_MAX_SLOTS];
-  uint32_t CB = 0, R0 = 0;
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag, (uint64_t)sbase + d, key.x, key.y);
-    const uint32_t c = cr & 0xffffu, root = cr >> 16;
-    CB |= (c * 4u) << (8 * d);
-    R0 |= (c * 4u + root) << (8 * d);
-    const int64_t col = sbase + d - a.site0;
-    if (a.comps && col >= 0 && col < a.nsites) a.comps[col] = (int32_t)c;
-  }
-  slot[0] = R0;
-  constexpr uint32_t SM = 0x03030303u;
+  uint8_t slot[QUAD_MAX_SLOTS];
+  const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag, s, key.x, key.y);
+  const uint32_t c = cr & 0xffffu, root = cr >> 16;
+  if (a.comps) a.comps[col] = (int32_t)c;
+  slot[0] = (uint8_t)root;
   for (int g = 0; g < fa.G; ++g) {
     const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(fa.recs + g));
     const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(fa.recs + g) + 1);
@@ -199,37 +212,22 @@ __global__ void k2_quad_generic(QuadArgs fa) {
     const int dst[4] = {(int)(int8_t)((h0.y >> 8) & 0xffu), (int)(int8_t)((h0.y >> 16) & 0xffu), (int)(int8_t)(h0.y >> 24),
                         (int)(int8_t)(h0.z & 0xffu)};
     const int leaf[4] = {(int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
-    const uint32_t Rv = slot[src];
-    const uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)g4, (uint32_t)((uint64_t)g4 >> 32), h0.x, TAG_NODE), key);
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-    uint32_t W = 0;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const uint32_t rowid = (Rv >> (8 * d)) & 0xffu, j = w[d] & 0xffu;
-      const int64_t idx = (((int64_t)g * a.C * 4 + rowid) << 8) | j;
-      const uint32_t e = __ldg(fa.qe32 + idx), t = w[d] >> 8, qh = e >> 8;
-      uint32_t o;
-      if (t < qh) o = j;
-      else if (t > qh) o = e & 0xffu;
-      else {
-        const uint64_t s = (uint64_t)sbase + d;
-        const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), h0.x, TAG_REFINE), key);
-        o = (z.x >> 16) < (uint32_t)__ldg(fa.qlo16 + idx) ? j : (e & 0xffu);
-      }
-      W |= o << (8 * d);
+    const uint32_t x24 = quad_draw24<ROUNDS>(s, h0.x, key);
+    const uint32_t j = x24 & 0xffu, t = x24 >> 8;
+    const int64_t idx = ((((int64_t)g * a.C + c) * 4 + slot[src]) << 8) | j;
+    const uint32_t e = __ldg(fa.qe32 + idx), qh = e >> 16, al = (e >> 8) & 0xffu;
+    uint32_t o;
+    if (t < qh) o = j;
+    else if (t > qh) o = al;
+    else {
+      const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), h0.x, TAG_REFINE), key);
+      o = (z.x >> 8) < __ldg(fa.qlo24 + idx) ? j : al;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t v = (W >> (2 * k)) & SM;
-      if (leaf[k] >= 0) {
-        uint8_t *dstp = a.leaves + (int64_t)leaf[k] * a.leaves_pitch + (sbase - a.site0);
-        for (int d = 0; d < 4; ++d) {
-          const int64_t col = sbase + d - a.site0;
-          if (col >= 0 && col < a.nsites) dstp[d] = (uint8_t)(v >> (8 * d));
-        }
-      } else if (dst[k] >= 0) {
-        slot[dst[k]] = v | CB;
-      }
+      const uint8_t v = (uint8_t)((o >> (2 * k)) & 3u);
+      if (leaf[k] >= 0) a.leaves[(int64_t)leaf[k] * a.leaves_pitch + col] = v;
+      else if (dst[k] >= 0) slot[dst[k]] = v;
     }
   }
 }
@@ -284,7 +282,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
                                              const int64_t col0, uint8_t *leaf_base, const int store_mode, const int lane) {
   const SimArgs &a = fa.s;
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-  const uint64_t G0 = (uint64_t)sbase >> 2;  // a multiple of 4: the four counters of a record differ in the low 2 bits
+  const uint64_t G0 = (uint64_t)sbase >> 4;  // the thread's 16-site group
   const uint32_t G0lo = (uint32_t)G0, Ghi = (uint32_t)(G0 >> 32);
   constexpr uint32_t SM = 0x03030303u;
   const uint32_t slot_base_m = slot_base - 0x80000000u;  // + (0x80000000 | offset) = slot_base + offset
@@ -303,50 +301,59 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
 #endif
     const uint4 rv = lds_v4(slot_base + h0.y);
     const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
+    // 48 random bytes = 16 draws of 24 bits
+    uint32_t X[12];
+#pragma unroll
+    for (int cl = 0; cl < 3; ++cl) {
+      const uint4 x = philox4x32_rk<ROUNDS>(make_uint4(G0lo, Ghi, node0, 4u * (uint32_t)cl), fa.rk);
+      X[4 * cl] = x.x; X[4 * cl + 1] = x.y; X[4 * cl + 2] = x.z; X[4 * cl + 3] = x.w;
+    }
     uint32_t W[4];
     uint32_t m = 0xffffffffu;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 x = philox4x32_rk<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), fa.rk);
-      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
       uint32_t c[4], t[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        // entry index = row << 8 | j in ONE byte permute: byte 0 = j (low byte of the draw), byte 1 = row byte of site
-        // 4q+i, bytes 2,3 = that byte's sign replicated = 0 (rows are < 128)
-        const uint32_t idx = i == 0 ? prmt<0xcc40u>(w[i], Rq[q]) : i == 1 ? prmt<0xdd50u>(w[i], Rq[q])
-                           : i == 2 ? prmt<0xee60u>(w[i], Rq[q]) : prmt<0xff70u>(w[i], Rq[q]);
+        const int d = 4 * q + i, wa = (3 * d) >> 2, off = (3 * d) & 3;
+        // draw d in the upper three bytes (the low byte is don't-care): [t : 16][j : 8][x : 8]
+        const uint32_t w = off == 0 ? prmt<0x2100u>(X[wa], 0u)
+                         : off == 1 ? X[wa]
+                         : off == 2 ? prmt<0x4320u>(X[wa], X[wa < 11 ? wa + 1 : wa])
+                                    : prmt<0x5430u>(X[wa], X[wa < 11 ? wa + 1 : wa]);
+        // entry index = row << 8 | j in ONE byte permute: byte 0 = j (byte 1 of the draw), byte 1 = row byte of site d,
+        // bytes 2,3 = that byte's sign replicated = 0 (rows are < 128)
+        const uint32_t idx = i == 0 ? prmt<0xcc41u>(w, Rq[q]) : i == 1 ? prmt<0xdd51u>(w, Rq[q])
+                           : i == 2 ? prmt<0xee61u>(w, Rq[q]) : prmt<0xff71u>(w, Rq[q]);
 #ifdef ELX_DEBUG_BOUNDS
         if (idx * 4u + 4u > (uint32_t)fa.tb) atomicExch(a.error_flag, -7);
 #endif
         const uint32_t e = lds_u32(tbl + idx * 4u);
-        c[i] = min(w[i], e);
-        t[i] = w[i] ^ e;
+        c[i] = min(w, e);
+        t[i] = w ^ e;
       }
       m = min(min(m, t[0]), min(t[1], min(t[2], t[3])));
-      W[q] = __byte_perm(__byte_perm(c[0], c[1], 0x0040u), __byte_perm(c[2], c[3], 0x0040u), 0x5410u);
+      W[q] = __byte_perm(__byte_perm(c[0], c[1], 0x0051u), __byte_perm(c[2], c[3], 0x0051u), 0x5410u);
     }
-    if (m < 256u) {
-      // exact path (2^-24 per draw): some draw hit its threshold's high 24 bits; redo this thread's 16 draws one by one
-      // and settle the tied ones with 16 more random bits.  Rolled, call-free and array-free on purpose (elx_fast.cu).
-#pragma unroll 1
-      for (int s = 0; s < 16; ++s) {
-        const int q = s >> 2, i = s & 3;
-        const uint4 x = philox4x32<ROUNDS>(make_uint4(G0lo | (uint32_t)q, Ghi, node0, TAG_NODE), key);
-        const uint32_t w = i == 0 ? x.x : (i == 1 ? x.y : (i == 2 ? x.z : x.w));
-        const uint32_t row = lds_u8(slot_base + h0.y + (uint32_t)s);
-        const uint32_t j = w & 0xffu, idx = (row << 8) | j;
+    if (m < 0x10000u) {
+      // exact path (2^-16 per draw): some draw hit its threshold's 16 high bits; settle the tied draws with 24 more
+      // random bits.  Unrolled with static register names: no calls, no dynamically indexed arrays (elx_fast.cu).
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const int wa = (3 * d) >> 2, off = (3 * d) & 3;
+        const uint32_t w = off == 0 ? prmt<0x2100u>(X[wa], 0u)
+                         : off == 1 ? X[wa]
+                         : off == 2 ? prmt<0x4320u>(X[wa], X[wa < 11 ? wa + 1 : wa])
+                                    : prmt<0x5430u>(X[wa], X[wa < 11 ? wa + 1 : wa]);
+        const uint32_t row = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
+        const uint32_t j = (w >> 8) & 0xffu, idx = (row << 8) | j;
         const uint32_t e = lds_u32(tbl + idx * 4u);
-        if ((w ^ e) < 256u) {
-          const uint64_t sg = (uint64_t)sbase + (uint64_t)s;
-          const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), key);
-          const uint32_t ql = (uint32_t)__ldg(fa.qlo16 + ((((int64_t)g * a.C * 4 + row) << 8) | j));
-          const uint32_t o = (z.x >> 16) < ql ? j : (e & 0xffu);
-          const uint32_t sh = 8u * (uint32_t)i, keep = ~(0xffu << sh);
-          if (q == 0) W[0] = (W[0] & keep) | (o << sh);
-          if (q == 1) W[1] = (W[1] & keep) | (o << sh);
-          if (q == 2) W[2] = (W[2] & keep) | (o << sh);
-          if (q == 3) W[3] = (W[3] & keep) | (o << sh);
+        if ((w ^ e) < 0x10000u) {
+          const uint64_t sg = (uint64_t)sbase + (uint64_t)d;
+          const uint4 z = philox4x32_rk<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), fa.rk);
+          const uint32_t ql = __ldg(fa.qlo24 + ((((int64_t)g * a.C * 4 + row) << 8) | j));
+          const uint32_t o = (z.x >> 8) < ql ? j : ((e >> 8) & 0xffu);
+          W[d >> 2] = (W[d >> 2] & ~(0xffu << (8 * (d & 3)))) | (o << (8 * (d & 3)));
         }
       }
     }
@@ -557,7 +564,7 @@ int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_caps, sizeof(QuadCapDev) * (size_t)G));
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_joint, sizeof(double) * ents));
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qe32, sizeof(uint32_t) * ents));
-  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qlo16, sizeof(uint16_t) * ents));
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qlo24, sizeof(uint32_t) * ents));
   QUAD_CUDA(h, cudaMemcpy(qt->d_recs, dev.data(), sizeof(QuadRecDev) * (size_t)G, cudaMemcpyHostToDevice));
   QUAD_CUDA(h, cudaMemcpy(qt->d_caps, caps.data(), sizeof(QuadCapDev) * (size_t)G, cudaMemcpyHostToDevice));
   if (qt->tiled) QUAD_CUDA(h, cudaMalloc((void **)&qt->d_ftab, (size_t)G * qt->stage_bytes));
@@ -572,7 +579,7 @@ int quad_tables_build(elx_handle *h) {
   h->launches++;
   QUAD_CUDA(h, cudaGetLastError());
   const int64_t rows = ents / QUAD_COLS;
-  k1_alias_quad<<<(unsigned)((rows + 63) / 64), 64, 0, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qlo16);
+  k1_alias_quad<<<(unsigned)((rows + 63) / 64), 64, 0, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qlo24);
   h->launches++;
   QUAD_CUDA(h, cudaGetLastError());
   if (qt->tiled) {
@@ -587,19 +594,19 @@ int quad_tables_build(elx_handle *h) {
 void quad_free(elx_handle *h) {
   QuadTables *qt = static_cast<QuadTables *>(h->quad);
   if (!qt) return;
-  cudaFree(qt->d_recs); cudaFree(qt->d_caps); cudaFree(qt->d_joint); cudaFree(qt->d_qe32); cudaFree(qt->d_qlo16); cudaFree(qt->d_ftab);
+  cudaFree(qt->d_recs); cudaFree(qt->d_caps); cudaFree(qt->d_joint); cudaFree(qt->d_qe32); cudaFree(qt->d_qlo24); cudaFree(qt->d_ftab);
   delete qt;
   h->quad = nullptr;
 }
 
-int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16) {
+int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24) {
   QuadTables *qt = static_cast<QuadTables *>(h->quad);
   if (!qt) return fail(h, ELX_E_INVALID, "elx_quad_get: this handle has no quad tables");
   if (recs)
     for (int g = 0; g < qt->G; ++g) quad_rec_to_ints(qt->prog.recs[g], recs + (size_t)g * ELX_QUAD_REC_INTS);
   const size_t n = (size_t)qt->G * h->C * 4 * QUAD_COLS;
   if (qe32) QUAD_CUDA(h, cudaMemcpyAsync(qe32, qt->d_qe32, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-  if (qlo16) QUAD_CUDA(h, cudaMemcpyAsync(qlo16, qt->d_qlo16, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+  if (qlo24) QUAD_CUDA(h, cudaMemcpyAsync(qlo24, qt->d_qlo24, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   QUAD_CUDA(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -628,7 +635,7 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
   QuadArgs fa;
   fa.s = a;
   fa.s.n_slots = qt->prog.n_slots;
-  fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qlo16 = qt->d_qlo16; fa.ftab = qt->d_ftab;
+  fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qlo24 = qt->d_qlo24; fa.ftab = qt->d_ftab;
   fa.tb = qt->tb; fa.stage_bytes = qt->stage_bytes; fa.nstage = qt->nstage; fa.slot_stride = qt->threads * 16;
   fa.rk = philox_round_keys(a.seed);
   cudaError_t e;
@@ -644,8 +651,7 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
     e = h->rounds == 7 ? launch_quad_tiled_t<7>(qt->threads, qt->minb, threads, fa, g1 - g0, qt->smem, h->stream)
                        : launch_quad_tiled_t<10>(qt->threads, qt->minb, threads, fa, g1 - g0, qt->smem, h->stream);
   } else {
-    const int64_t g0 = a.site0 >> 2, g1 = (a.site0 + a.nsites + 3) >> 2;
-    const unsigned blocks = (unsigned)((g1 - g0 + 127) / 128);
+    const unsigned blocks = (unsigned)((a.nsites + 127) / 128);
     if (h->rounds == 7) k2_quad_generic<7><<<blocks, 128, 0, h->stream>>>(fa);
     else k2_quad_generic<10><<<blocks, 128, 0, h->stream>>>(fa);
     e = cudaGetLastError();

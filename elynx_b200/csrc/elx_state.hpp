@@ -92,7 +92,7 @@ int quad_tables_build(elx_handle *h);
 void quad_free(elx_handle *h);
 int quad_groups(const elx_handle *h);
 void quad_rec_to_ints(const QuadRec &r, int32_t *o);  // ELX_QUAD_REC_INTS values, the layout include/elynx_b200.h documents
-int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16);
+int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
 int quad_simulate(elx_handle *h, SimArgs &a, int *used);
 
 // elx_core.cu

@@ -133,16 +133,16 @@ class Simulator:
         return node_a, node_b, pe16, pqlo
 
     def quad_tables(self):
-        """(recs[G][ELX_QUAD_REC_INTS], qe32[G][C][4][256], qlo16[G][C][4][256]) of the quad-mode records, or None."""
+        """(recs[G][ELX_QUAD_REC_INTS], qe32[G][C][4][256], qlo24[G][C][4][256]) of the quad-mode records, or None."""
         g = self.quad_groups
         if g == 0:
             return None
         recs = np.empty((g, L.ELX_QUAD_REC_INTS), dtype=np.int32)
         shape = (g, self.n_components, 4, 256)
         qe32 = np.empty(shape, dtype=np.uint32)
-        qlo16 = np.empty(shape, dtype=np.uint16)
-        L.check(L.lib().elx_quad_get(self._h, _ptr(recs), _ptr(qe32), _ptr(qlo16)), self._h)
-        return recs, qe32, qlo16
+        qlo24 = np.empty(shape, dtype=np.uint32)
+        L.check(L.lib().elx_quad_get(self._h, _ptr(recs), _ptr(qe32), _ptr(qlo24)), self._h)
+        return recs, qe32, qlo24
 
     # -- simulation ----------------------------------------------------------------------------
     def simulate(self, seed: int, nsites: int, site0: int = 0, want_comps: bool = False, keep_internal: bool = False):

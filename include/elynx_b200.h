@@ -143,11 +143,12 @@ int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16
  * [9..12] slot receiving out[k] (-1: none), [13] slot holding r, [14] number of cap nodes n, [15] 0, then n triples
  * [16+3i..] = (node, index of its parent in this list or -1 for r, frontier position or -1 for a summed-out node), parents
  * first.  elx_quad_groups: number of records (0: no quad tables); elx_quad_get: the records in walk order and their alias
- * rows qe32 / qlo16 [G][C][4][256] ([threshold bits 39..16 : 24][alias : 8] / threshold bits 15..0).
+ * rows qe32 / qlo24 [G][C][4][256] (uint32: [threshold bits 39..24 : 16][alias : 8][0 : 8] / threshold bits 23..0).  A draw is
+ * 24 bits ([t : 16][column : 8], three Philox calls per 16 sites); t == threshold high bits (2^-16) is settled with 24 more bits.
  * elx_tree_quad_walk_info: host-only, the records of a tree (recs may be NULL; it must hold ELX_QUAD_REC_INTS * n_nodes). */
 #define ELX_QUAD_REC_INTS 52
 int32_t elx_quad_groups(const elx_handle *h);
-int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint16_t *qlo16);
+int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
 int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
 
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------

@@ -22,9 +22,11 @@
  * Records come in walk order (a record's parent is drawn by an earlier record; node_b = -1 for a group of one).
  *
  * Quad mode (models with K <= 4, leaves only; elynx_b200/csrc/elx_quad.cu): record g = (out[0..3] | r) draws the states of up to
- * four frontier nodes below r at once from a 256-outcome joint row (inner nodes summed out), o = sum_k state(out[k]) << 2k:
- *   x32 = word (s & 3) of philox(s>>2 lo, s>>2 hi, out[0], 0);  j = x32 & 255; t = x32 >> 8; e = qe32[g][c][state of r][j]
- *   t < e>>8 -> o = j ;  t > e>>8 -> o = e & 255 ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 16) < qlo16[g][c][state of r][j] ? j : e & 255
+ * four frontier nodes below r at once from a 256-outcome joint row (inner nodes summed out), o = sum_k state(out[k]) << 2k.
+ * A draw is 24 bits; the 16 sites of a group s >> 4 share three Philox calls:
+ *   B[0..47] = little-endian bytes of philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2;  d = s & 15
+ *   x24 = B[3d] | B[3d+1] << 8 | B[3d+2] << 16;  j = x24 & 255; t = x24 >> 8; e = qe32[g][c][state of r][j] = [q_hi : 16][alias : 8][0 : 8]
+ *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < qlo24[g][c][state of r][j] ? j : alias
  * Records come in walk order (r is the root or a frontier node of an earlier record); recs = 52 int32 per record in the
  * layout include/elynx_b200.h documents.
  */
@@ -165,7 +167,7 @@ int spec_freerun_pair(int N, int K, int C, int is_mixture, int rounds, const int
 static int64_t quad_ties = 0;
 int64_t spec_quad_ties(void) { return quad_ties; } /* ties seen by the last spec_freerun_quad call */
 int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int32_t *leaf_row, const double *cumw,
-                      const double *cumpi, int G, const int32_t *recs, const uint32_t *qe32, const uint16_t *qlo16, uint64_t seed,
+                      const double *cumpi, int G, const int32_t *recs, const uint32_t *qe32, const uint32_t *qlo24, uint64_t seed,
                       int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch, int32_t *comps) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint8_t *st = (uint8_t *)malloc((size_t)N);
@@ -194,18 +196,24 @@ int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int
       const int32_t *r = recs + (size_t)g * QUAD_REC_INTS;
       const int rt = r[0], n0 = r[1];
       if (rt < 0 || rt >= N || !done[rt] || n0 < 0 || n0 >= N) { rc = -2; break; }  /* not in walk order */
-      uint64_t gg = s >> 2;
-      uint32_t y[4] = {(uint32_t)gg, (uint32_t)(gg >> 32), (uint32_t)n0, 0};
-      philox(rounds, y, k0, k1);
-      uint32_t x32 = y[s & 3], j = x32 & 255u, t = x32 >> 8;
+      uint64_t gg = s >> 4;
+      uint8_t B[48];
+      for (int call = 0; call < 3; ++call) {
+        uint32_t y[4] = {(uint32_t)gg, (uint32_t)(gg >> 32), (uint32_t)n0, 4u * (uint32_t)call};
+        philox(rounds, y, k0, k1);
+        for (int b = 0; b < 16; ++b) B[16 * call + b] = (uint8_t)(y[b >> 2] >> (8 * (b & 3)));
+      }
+      const int d = (int)(s & 15);
+      uint32_t x24 = (uint32_t)B[3 * d] | ((uint32_t)B[3 * d + 1] << 8) | ((uint32_t)B[3 * d + 2] << 16);
+      uint32_t j = x24 & 255u, t = x24 >> 8;
       int64_t idx = (((int64_t)g * C + c) * 4 + st[rt]) * 256 + j;
-      uint32_t e = qe32[idx], qh = e >> 8, al = e & 255u, o;
+      uint32_t e = qe32[idx], qh = e >> 16, al = (e >> 8) & 255u, o;
       if (t < qh) o = j;
       else if (t > qh) o = al;
       else {
         uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)n0, 1};
         philox(rounds, z, k0, k1);
-        o = (z[0] >> 16) < qlo16[idx] ? j : al;
+        o = (z[0] >> 8) < qlo24[idx] ? j : al;
         ++quad_ties;
       }
       for (int k = 0; k < 4; ++k) {

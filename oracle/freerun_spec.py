@@ -102,13 +102,13 @@ QUAD_REC_INTS = 52
 
 
 def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites, rounds=10):
-    """Quad mode (K <= 4, leaves only): quad = (recs[G][52], qe32[G][C][4][256], qlo16[G][C][4][256]) in walk order."""
+    """Quad mode (K <= 4, leaves only): quad = (recs[G][52], qe32[G][C][4][256], qlo24[G][C][4][256]) in walk order."""
     leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
     recs = np.ascontiguousarray(quad[0], dtype=np.int32)
     qe32 = np.ascontiguousarray(quad[1], dtype=np.uint32)
-    qlo16 = np.ascontiguousarray(quad[2], dtype=np.uint16)
+    qlo24 = np.ascontiguousarray(quad[2], dtype=np.uint32)
     g, c, four, cols = qe32.shape
-    assert four == 4 and cols == 256 and qlo16.shape == qe32.shape and recs.shape == (g, QUAD_REC_INTS)
+    assert four == 4 and cols == 256 and qlo24.shape == qe32.shape and recs.shape == (g, QUAD_REC_INTS)
     n = len(leaf_row)
     k = np.asarray(ds).reshape(c, -1).shape[1]
     cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
@@ -118,7 +118,7 @@ def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites
     comps = np.zeros(max(nsites, 1), dtype=np.int32)
     vp = C.c_void_p
     rc = lib().spec_freerun_quad(n, k, c, int(bool(is_mixture)), rounds, vp(leaf_row.ctypes.data), vp(cumw.ctypes.data),
-                                 vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(qe32.ctypes.data), vp(qlo16.ctypes.data),
+                                 vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(qe32.ctypes.data), vp(qlo24.ctypes.data),
                                  C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0), C.c_int64(nsites), vp(leaves.ctypes.data),
                                  C.c_int64(max(nsites, 1)), vp(comps.ctypes.data))
     if rc:

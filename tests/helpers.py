@@ -123,12 +123,14 @@ def check_pair_tables(p, pair, parent):
     assert np.max(np.abs(mass / float(1 << 48) - joint)) < 2.0 ** -44
 
 
-def quad_masses(qe32, qlo16):
-    """Integer outcome masses (sum 2^48 per row) encoded by quad alias rows qe32 = [q bits 39..16 : 24][alias : 8], qlo16."""
+def quad_masses(qe32, qlo24):
+    """Integer outcome masses (sum 2^48 per row) encoded by quad alias rows qe32 = [q bits 39..24 : 16][alias : 8][0 : 8], qlo24."""
     cap = 1 << 40
     e = qe32.astype(np.int64)
-    al = e & 255
-    q = ((e >> 8) << 16) | qlo16.astype(np.int64)
+    assert np.all((e & 255) == 0)
+    al = (e >> 8) & 255
+    q = ((e >> 16) << 24) | qlo24.astype(np.int64)
+    assert np.all(qlo24 < (1 << 24))
     q = np.where(al == np.arange(256), cap, q)
     flat_q = q.reshape(-1, 256)
     flat_al = al.reshape(-1, 256)
@@ -224,10 +226,10 @@ def quad_joint_reference(p, rec, k):
 
 def check_quad_tables(p, quad, parent, leaf_row, max_records=40):
     """The walk is valid and the alias rows carry integer masses (sum 2^48) equal to the caps' joint probabilities."""
-    recs, qe32, qlo16 = quad
+    recs, qe32, qlo24 = quad
     check_quad_walk(recs, parent, leaf_row)
     k = p.shape[2]
-    mass = quad_masses(qe32, qlo16)
+    mass = quad_masses(qe32, qlo24)
     assert np.all(mass[:, :, :k].sum(-1) == 1 << 48)
     pn = p / p.sum(-1, keepdims=True)
     step = max(1, len(recs) // max_records)
