@@ -80,6 +80,7 @@ struct QuadArgs {
   const uint32_t *qlo24;
   const uint8_t *ftab;
   int tb, stage_bytes, nstage, slot_stride;
+  uint32_t entry_bytes;  // 4 (see entry_addr)
   PhiloxRoundKeys rk;  // of the call's seed
 };
 
@@ -257,6 +258,13 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
   return d;
 }
+// base + idx * entry_bytes as an integer multiply-add: the FMA pipe has room, the ALU pipe has not.  entry_bytes (= 4)
+// arrives as a launch constant because ptxas turns a multiply by a literal 4 into an ALU-pipe LEA.
+__device__ __forceinline__ uint32_t entry_addr(uint32_t idx, uint32_t entry_bytes, uint32_t base) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(idx), "r"(entry_bytes), "r"(base));
+  return d;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -328,7 +336,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
 #ifdef ELX_DEBUG_BOUNDS
         if (idx * 4u + 4u > (uint32_t)fa.tb) atomicExch(a.error_flag, -7);
 #endif
-        const uint32_t e = lds_u32(tbl + idx * 4u);
+        const uint32_t e = lds_u32(entry_addr(idx, fa.entry_bytes, tbl));
         c[i] = min(w, e);
         t[i] = w ^ e;
       }
@@ -638,6 +646,7 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
   fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qlo24 = qt->d_qlo24; fa.ftab = qt->d_ftab;
   fa.tb = qt->tb; fa.stage_bytes = qt->stage_bytes; fa.nstage = qt->nstage; fa.slot_stride = qt->threads * 16;
   fa.rk = philox_round_keys(a.seed);
+  fa.entry_bytes = 4;
   cudaError_t e;
   if (qt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC)) {
     const int64_t g0 = a.site0 >> 4, g1 = (a.site0 + a.nsites + 15) >> 4;
