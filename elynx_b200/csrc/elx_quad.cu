@@ -548,9 +548,10 @@ int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
   QuadTables *qt = new QuadTables();
   compile_quad_walk(h->N, parent, leaf_row, qt->prog);
   const int G = qt->G = (int)qt->prog.recs.size();
-  // quad mode needs the tiled geometry (or at least the generic kernel's slot array); otherwise the handle stays in pair mode
+  // quad mode needs the tiled geometry; otherwise the handle stays in pair mode
   if (G == 0 || qt->prog.n_slots > QUAD_MAX_SLOTS || (int64_t)h->C * 4 > 127) { delete qt; return 0; }
-  quad_geometry(h->C, qt->prog.n_slots, qt);
+  // without a shared-memory geometry (very many components) the tiled pair kernel beats the generic quad kernel
+  if (!quad_geometry(h->C, qt->prog.n_slots, qt)) { delete qt; return 0; }
   h->quad = qt;
   std::vector<QuadRecDev> dev((size_t)G);
   std::vector<QuadCapDev> caps((size_t)G);

@@ -251,6 +251,43 @@ def test_quad_refinement_path_is_exercised():
         assert np.array_equal(sim.simulate(3, s)[0], l0)
 
 
+@pytest.mark.parametrize("k", [2, 3])
+def test_small_alphabets_quad_and_pair(k):
+    """K = 2 / 3 models run in quad and pair mode too (states >= K are zero-mass outcomes of the 2-bit fields): spec
+    parity on a random tree, and chi-square against exact pruning probabilities on a 4-taxon tree."""
+    from scipy import stats
+
+    rng = np.random.default_rng(40 + k)
+    pi = rng.dirichlet(np.ones(k) * 3)
+    ex = rng.uniform(0.3, 2.0, size=(k, k))
+    ex = (ex + ex.T) / 2
+    ex[np.arange(k), np.arange(k)] = 0
+    ds, es = pi[None], ex[None]
+    model = (False, np.ones(1), ds)
+    tree = random_tree(23, rng, multifurcate=True, zero_frac=0.1)
+    for kw in ({}, {"force_generic": True}, {"pair_draws": True}):
+        with eb.Simulator(None, ds, es, tree, is_mixture=False, **kw) as sim:
+            assert (sim.quad_groups > 0) == ("pair_draws" not in kw) and sim.pair_groups > 0
+            if sim.quad_groups:
+                check_quad_tables(sim.ptables(), sim.quad_tables(), tree.parent, tree.leaf_row)
+            leaves = sim.simulate(9, 5000, site0=3)[0]
+            l0, _, _ = spec_freerun(sim, model, tree, 9, 3, 5000)
+            assert np.array_equal(leaves, l0) and leaves.max() < k
+    t4 = om.parse_newick("((a:0.1,b:0.3):0.05,(c:0.02,d:0.7):0.2):0.15;")
+    s = 1_000_000
+    with eb.Simulator(None, ds, es, t4, is_mixture=False) as sim:
+        leaves = sim.simulate(77, s)[0]
+        probs = pruning.pattern_probabilities(False, np.ones(1), ds, sim.ptables(), t4.parent, t4.leaf_row)
+    idx = np.zeros(s, dtype=np.int64)
+    for t in range(4):
+        idx = idx * k + leaves[t]
+    obs = np.bincount(idx, minlength=k ** 4)
+    exp = probs * s
+    keep = exp >= 5
+    chi2 = float(((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum())
+    assert stats.chi2.sf(chi2, int(keep.sum()) - 1) > 1e-4
+
+
 def test_freerun_partition_invariance():
     """Output is a pure function of (seed, global site, node): any split of the site range gives the same bytes."""
     model = model_case("hky_g4")
