@@ -46,6 +46,15 @@ class elx_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("philox_rounds", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
+class elx_examine_result(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("n_sequences", C.c_int64), ("n_states", C.c_int32), ("reserved", C.c_int32),
+                ("n_constant", C.c_int64), ("n_constant_soft", C.c_int64), ("n_no_gaps", C.c_int64), ("n_only_std", C.c_int64),
+                ("n_std_chars", C.c_int64), ("n_gaps", C.c_int64), ("distribution", C.c_double * 64),
+                ("keff_entropy_mean", C.c_double), ("keff_entropy_mean_no_gaps", C.c_double),
+                ("keff_homoplasy_mean", C.c_double), ("keff_homoplasy_mean_no_gaps", C.c_double),
+                ("hamming_mean", C.c_double), ("hamming_var", C.c_double), ("hamming_min", C.c_double), ("hamming_max", C.c_double)]
+
+
 _VP, _I64, _U64, _I32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32
 _CSTRS = C.POINTER(C.c_char_p)
 
@@ -82,6 +91,8 @@ SIGNATURES = {
     "elx_fasta_pack_slice_device": (C.c_int, [_VP, _VP, _I64, _I64, C.c_char_p, _VP, _I64]),
     "elx_fasta_row_offset": (_I64, [_VP, _CSTRS, _I64, _I32]),
     "elx_histogram_device": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _VP]),
+    "elx_examine_device": (C.c_int, [_VP, _I64, _I32, _I64, _I32, C.POINTER(elx_examine_result), _VP, _VP, _VP, _VP]),
+    "elx_examine": (C.c_int, [_VP, _I64, _I32, _I64, _I32, C.POINTER(elx_examine_result), _VP, _VP, _VP]),
     "elx_launch_count": (_I64, [_VP]),
 }
 

@@ -1,4 +1,4 @@
-"""`python -m elynx_b200.cli simulate ...` -- thin native driver with the `slynx simulate` surface.
+"""`python -m elynx_b200.cli simulate|examine ...` -- thin native driver with the `slynx simulate` / `slynx examine` surface.
 
 Mirrors slynx/src/SLynx/Simulate/Options.hs:65-204 (arguments) and Simulate.hs:239-306 (simulateCmd): reads a Newick
 tree, assembles the phylogenetic model from the model string (+ EDM / site-profile files, weights, gamma rate
@@ -137,6 +137,88 @@ def simulate_cmd(args) -> int:
     return 0
 
 
+def read_fasta(text: bytes):
+    """[(name, description, characters)] -- elynx-seq Import/Fasta.hs:33-70 (`>name description`, sequence lines until the
+    next header); character validation against the alphabet happens in examine.encode."""
+    seqs, name, desc, chunks = [], None, b"", []
+    for line in text.splitlines():
+        if line.startswith(b">"):
+            if name is not None:
+                seqs.append((name, desc, b"".join(chunks)))
+            parts = line[1:].split(None, 1)
+            if not parts:
+                raise SystemExit("fasta: empty sequence header")
+            name, desc, chunks = parts[0], (parts[1] if len(parts) > 1 else b""), []
+        elif line.strip():
+            if name is None:
+                raise SystemExit("fasta: sequence data before the first header")
+            chunks.append(line.strip())
+    if name is not None:
+        seqs.append((name, desc, b"".join(chunks)))
+    if not seqs:
+        raise SystemExit("fasta: no sequences")
+    return seqs
+
+
+def summarize_sequences(seqs, alphabet: str) -> str:
+    """Seq.summarizeSequences (elynx-seq Sequence.hs:105-170, Defaults.hs:19-34): a table of the first 200 sequences."""
+    name_w, field_w, summary_len, summary_n = 23, 13, 60, 200
+    al = lambda n, x: x[:n].ljust(n)  # noqa: E731
+    ar = lambda n, x: x[:n].rjust(n)  # noqa: E731
+    lines = []
+    if len(seqs) > summary_n:
+        lines.append("%d out of %d sequences are shown." % (summary_n, len(seqs)))
+    lines += ["For each sequence, the %d first bases are shown." % summary_len, "List contains %d sequences." % len(seqs), "",
+              " ".join([al(name_w, "Name"), ar(field_w, "Code"), ar(field_w, "Length"), ar(field_w, "Gaps [%]"), "Sequence"])]
+    for name, _, chars in seqs[:summary_n]:
+        n_gaps = sum(chars.count(g) for g in (b"-", b"."))
+        pg = 100.0 * n_gaps / len(chars) if chars else float("nan")
+        shown = chars[:summary_len] + b"..." if len(chars) >= summary_len else chars
+        lines.append(" ".join([al(name_w, name.decode()), ar(field_w, alphabet), ar(field_w, str(len(chars))), ar(field_w, "%2.2f" % pg),
+                               shown.decode()]))
+    return "\n".join(lines) + "\n"
+
+
+def examine_cmd(args) -> int:
+    """examineCmd (slynx/src/SLynx/Examine/Examine.hs:187-196): `<base>.out` (or stdout) and, with --divergence, `<base>.div`."""
+    from . import examine as ex
+
+    if args.alphabet not in ex.ALPHABETS:
+        raise SystemExit("alphabet %s is not supported (IUPAC alphabets are out of scope); use one of %s" % (args.alphabet, ", ".join(ex.ALPHABETS)))
+    raw = (gzip.open if args.input_file.endswith(".gz") else open)(args.input_file, "rb").read()
+    seqs = read_fasta(raw)
+    text = summarize_sequences(seqs, args.alphabet)
+    k = len(ex.ALPHABETS[args.alphabet])
+    if len({len(c) for _, _, c in seqs}) == 1:  # M.fromSequences succeeds only for equal lengths (Alignment.hs:87-95)
+        a = ex.encode([c for _, _, c in seqs], args.alphabet)
+        r = ex.examine_alignment(a, k, per_site=args.per_site, divergence=args.divergence)
+        per_site = r.get("keff_entropy_per_site") if args.per_site else None
+        report = ex.format_report(r, args.alphabet)
+        if per_site is not None:
+            report += "Effective number of used states per site (measured using entropy):\n"
+            report += "[" + ",".join(double_dec(float(x)) for x in per_site) + "]\n"
+        text += "\n" + report
+        if args.divergence:
+            if not args.output_file_basename:
+                raise SystemExit("--divergence needs -o/--output-file-basename")
+            with open(args.output_file_basename + ".div", "w") as f:  # writeDivergenceMatrix (Examine.hs:170-177)
+                p = 0
+                for i in range(len(seqs)):
+                    for j in range(i + 1, len(seqs)):
+                        f.write("> %s, %s\n" % (seqs[i][0].decode(), seqs[j][0].decode()))
+                        m = r["divergence"][p]
+                        w = max(len(str(int(v))) for v in m.flat)
+                        f.write("%dx%d\n" % (k, k))                      # hmatrix dispf 0: dimensions, then the rows
+                        for row in m:
+                            f.write("  ".join(str(int(v)).rjust(w) for v in row) + "\n")
+                        p += 1
+    if args.output_file_basename:
+        open(args.output_file_basename + ".out", "w").write(text)
+    else:
+        sys.stdout.write(text)
+    return 0
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="slynx-b200", description="B200-native `slynx simulate` (alignment simulation on the GPU)")
     ap.add_argument("-v", "--verbosity", default="Info", choices=["Quiet", "Warn", "Info", "Debug"])
@@ -156,8 +238,13 @@ def main(argv=None) -> int:
     s.add_argument("-l", "--length", type=int, required=True)
     s.add_argument("-S", "--seed")
     s.add_argument("--device", type=int, default=-1)
+    e = sub.add_parser("examine", help="Examine sequences / alignments (slynx/src/SLynx/Examine/Options.hs)")
+    e.add_argument("-a", "--alphabet", required=True, help="DNA, DNAX, Protein or ProteinX")
+    e.add_argument("input_file", metavar="INPUT-FILE")
+    e.add_argument("--per-site", action="store_true", help="Report per site summary statistics")
+    e.add_argument("--divergence", action="store_true", help="Compute pairwise divergence matrices")
     args = ap.parse_args(argv)
-    return simulate_cmd(args)
+    return examine_cmd(args) if args.cmd == "examine" else simulate_cmd(args)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,372 @@
+// `slynx examine` core on the device: statistics of an alignment held as a [T][pitch] uint8 code matrix in HBM
+// (slynx/src/SLynx/Examine/Examine.hs:52-160, elynx-seq/src/ELynx/Sequence/Alignment.hs:209-300,
+// elynx-seq/src/ELynx/Alphabet/DistributionDiversity.hs:37-110, Sequence/Distance.hs:24-33, Sequence/Divergence.hs:38-64).
+//
+// Codes: 0..K-1 = standard characters in sorted order (what the simulator writes), K = '-', K+1 = '.' (the gap characters
+// of DNAX / ProteinX; toStd of a gap is [], so gaps never enter a frequency).  IUPAC alphabets are out of scope.
+//
+// Kernels
+//   k_examine_columns  one pass over the matrix (1 byte read per cell: HBM-read bound).  A thread owns 4 consecutive sites
+//                      and walks the T rows with 32-bit loads; per-site character counts live in shared memory as
+//                      [code][site-in-thread][thread] uint32 (conflict-free).  Per site: constant / soft-constant / gap-free
+//                      flags, frequencies, entropy -> kEff, homoplasy -> kEff; sums are reduced per warp and added to a
+//                      small accumulator block with atomics.
+//   k_examine_hamming  numbers of EQUAL characters of all sequence pairs: 32 x 32 pair tiles, both row tiles of a 512-site
+//                      chunk staged in shared memory (padded rows: conflict-free), packed byte compares (4 sites / word).
+//   k_examine_divergence  K x K count matrix of one sequence pair per CTA (shared-memory histogram), on request.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/elynx_b200.h"
+#include "elx_state.hpp"
+
+namespace elx {
+
+constexpr int EX_THREADS = 256;
+constexpr int EX_SPT = 4;                        // sites per thread
+constexpr int EX_BLOCK_SITES = EX_THREADS * EX_SPT;
+constexpr int EX_MAX_K = 62;                     // + 2 gap codes = 64 counter rows
+constexpr double EX_EPS = 1e-12;                 // DistributionDiversity.hs:37-38
+
+struct ExamineAcc {
+  unsigned long long n_constant, n_constant_soft, n_no_gaps, n_std, n_gap, n_bad;
+  double keff_e_all, keff_e_nogap, keff_h_all, keff_h_nogap;
+  unsigned long long n_h_inf_all;  // columns without any standard character: kEffHomoplasy = 1/0 = Infinity
+  double dist[64];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(EX_THREADS) k_examine_columns(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
+                                                                 ExamineAcc *__restrict__ acc, double *__restrict__ keff_site) {
+  extern __shared__ uint32_t cnt[];  // [(K + 2)][EX_SPT][EX_THREADS]
+  const int tid = threadIdx.x, R = K + 2;
+  const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 3) == 0);
+  unsigned n_const = 0, n_soft = 0, n_nogap = 0, n_hinf = 0;
+  unsigned long long n_std = 0, n_gap = 0, n_bad = 0;
+  double ke_all = 0, ke_ng = 0, kh_all = 0, kh_ng = 0;
+  for (int64_t base = (int64_t)blockIdx.x * EX_BLOCK_SITES; base < S; base += (int64_t)gridDim.x * EX_BLOCK_SITES) {
+    const int64_t s0 = base + (int64_t)tid * EX_SPT;
+    for (int r = 0; r < R * EX_SPT; ++r) cnt[r * EX_THREADS + tid] = 0;
+    uint32_t first = 0, differs = 0;  // per site byte lanes: code of row 0; 0xff where some row differs from it
+    const bool whole = aligned && s0 + EX_SPT <= S;
+    for (int t = 0; t < T; ++t) {
+      uint32_t w = 0;
+      const uint8_t *p = a + (int64_t)t * pitch + s0;
+      if (whole) {
+        w = __ldg(reinterpret_cast<const uint32_t *>(p));
+      } else {
+#pragma unroll
+        for (int d = 0; d < EX_SPT; ++d)
+          if (s0 + d < S) w |= (uint32_t)__ldg(p + d) << (8 * d);
+      }
+      if (t == 0) first = w;
+      differs |= __vcmpne4(w, first);
+#pragma unroll
+      for (int d = 0; d < EX_SPT; ++d) {
+        uint32_t code = (w >> (8 * d)) & 0xffu;
+        if (code >= (uint32_t)R) { code = (uint32_t)K; if (s0 + d < S) ++n_bad; }
+        cnt[(code * EX_SPT + d) * EX_THREADS + tid] += 1;
+      }
+    }
+    double dist_part[EX_SPT];
+#pragma unroll
+    for (int d = 0; d < EX_SPT; ++d) {
+      const bool live = s0 + d < S;
+      unsigned sum = 0, kinds = 0;
+      for (int k = 0; k < K; ++k) {
+        const unsigned c = cnt[(k * EX_SPT + d) * EX_THREADS + tid];
+        sum += c;
+        kinds += c ? 1u : 0u;
+      }
+      const unsigned gaps = cnt[(K * EX_SPT + d) * EX_THREADS + tid] + cnt[((K + 1) * EX_SPT + d) * EX_THREADS + tid];
+      double e = 0.0, h = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const unsigned c = cnt[(k * EX_SPT + d) * EX_THREADS + tid];
+        const double f = sum ? (double)c / (double)sum : 0.0;  // saveDivision (DistributionDiversity.hs:92-94)
+        if (!(EX_EPS > f)) e -= f * log(f);                     // xLogX (:41-45), entropy (:48-57)
+        h += f * f;                                             // homoplasy (:67-68)
+      }
+      const double keff_e = e < EX_EPS ? 1.0 : exp(e);          // kEffEntropy (:61-62)
+      if (live) {
+        const bool nogap = gaps == 0;
+        n_const += ((differs >> (8 * d)) & 0xffu) == 0;                   // filterColsConstant (Alignment.hs:217-218)
+        n_soft += kinds == 1;                                            // filterColsConstantSoft (:222-228)
+        n_nogap += nogap;                                                // filterColsNoGaps (:247-248)
+        n_std += sum; n_gap += gaps;
+        ke_all += keff_e;
+        if (nogap) ke_ng += keff_e;
+        if (h > 0.0) { kh_all += 1.0 / h; if (nogap) kh_ng += 1.0 / h; } else ++n_hinf;  // kEffHomoplasy (:72-73)
+        if (keff_site) keff_site[s0 + d] = keff_e;
+      }
+      dist_part[d] = live && sum ? 1.0 / (double)sum : 0.0;
+    }
+    // distribution (Alignment.hs:275-283): sum over sites of the per-site frequencies, one warp reduction per character
+    for (int k = 0; k < K; ++k) {
+      double v = 0.0;
+#pragma unroll
+      for (int d = 0; d < EX_SPT; ++d) v += (double)cnt[(k * EX_SPT + d) * EX_THREADS + tid] * dist_part[d];
+      v = warp_sum(v);
+      if ((tid & 31) == 0 && v != 0.0) atomicAdd(&acc->dist[k], v);
+    }
+  }
+  ke_all = warp_sum(ke_all); ke_ng = warp_sum(ke_ng); kh_all = warp_sum(kh_all); kh_ng = warp_sum(kh_ng);
+  n_const = warp_sum_u(n_const); n_soft = warp_sum_u(n_soft); n_nogap = warp_sum_u(n_nogap); n_hinf = warp_sum_u(n_hinf);
+  atomicAdd(&acc->n_std, n_std);
+  atomicAdd(&acc->n_gap, n_gap);
+  if (n_bad) atomicAdd(&acc->n_bad, n_bad);
+  if ((tid & 31) == 0) {
+    atomicAdd(&acc->n_constant, (unsigned long long)n_const);
+    atomicAdd(&acc->n_constant_soft, (unsigned long long)n_soft);
+    atomicAdd(&acc->n_no_gaps, (unsigned long long)n_nogap);
+    atomicAdd(&acc->n_h_inf_all, (unsigned long long)n_hinf);
+    atomicAdd(&acc->keff_e_all, ke_all);
+    atomicAdd(&acc->keff_e_nogap, ke_ng);
+    atomicAdd(&acc->keff_h_all, kh_all);
+    atomicAdd(&acc->keff_h_nogap, kh_ng);
+  }
+}
+
+// eq[i][j] += number of sites where sequences i and j carry the same character (any code, gaps included: Distance.hs:24-33
+// compares characters).  Tile = 32 x 32 pairs; grid = (tile pairs, site slices); thread (r, c) owns pairs (r + 8 m, c).
+constexpr int HM_TILE = 32, HM_CHUNK = 512, HM_STRIDE = HM_CHUNK + 4;  // padded rows: word stride 129 = 1 mod 32
+__global__ void __launch_bounds__(256) k_examine_hamming(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int n_tiles,
+                                                         int n_slices, unsigned long long *__restrict__ eq) {
+  __shared__ __align__(16) uint8_t rows_i[HM_TILE * HM_STRIDE];
+  __shared__ __align__(16) uint8_t rows_j[HM_TILE * HM_STRIDE];
+  const int ti = blockIdx.x / n_tiles, tj = blockIdx.x % n_tiles;
+  if (tj < ti) return;
+  const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;
+  unsigned long long acc[4] = {0, 0, 0, 0};
+  const int64_t n_chunks = (S + HM_CHUNK - 1) / HM_CHUNK;
+  for (int64_t ch = blockIdx.y; ch < n_chunks; ch += n_slices) {
+    const int64_t s0 = ch * HM_CHUNK;
+    __syncthreads();
+    for (int i = tid; i < HM_TILE * HM_CHUNK; i += 256) {
+      const int row = i / HM_CHUNK, col = i % HM_CHUNK;
+      const int64_t s = s0 + col;
+      const int gi = ti * HM_TILE + row, gj = tj * HM_TILE + row;
+      // out-of-range cells get codes that never compare equal
+      rows_i[row * HM_STRIDE + col] = (gi < T && s < S) ? __ldg(a + (int64_t)gi * pitch + s) : (uint8_t)0xfe;
+      rows_j[row * HM_STRIDE + col] = (gj < T && s < S) ? __ldg(a + (int64_t)gj * pitch + s) : (uint8_t)0xfd;
+    }
+    __syncthreads();
+    unsigned part[4] = {0, 0, 0, 0};
+    const uint32_t *yj = reinterpret_cast<const uint32_t *>(rows_j + c * HM_STRIDE);
+#pragma unroll 4
+    for (int w = 0; w < HM_CHUNK / 4; ++w) {
+      const uint32_t y = yj[w];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const uint32_t x = reinterpret_cast<const uint32_t *>(rows_i + (r + 8 * m) * HM_STRIDE)[w];
+        part[m] += __popc(__vcmpeq4(x, y));  // 8 bits per equal byte
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[m] += part[m] >> 3;
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int gi = ti * HM_TILE + r + 8 * m, gj = tj * HM_TILE + c;
+    if (gi < T && gj < T && acc[m]) atomicAdd(&eq[(int64_t)gi * T + gj], acc[m]);
+  }
+}
+
+// divergence (Divergence.hs:38-64): out[pair][x][y] = number of sites with standard characters x in sequence i and y in j,
+// pairs (i < j) in the order of `tuples` (Examine.hs:165-167): (0,1), (0,2), ..., (1,2), ...
+__global__ void __launch_bounds__(256) k_examine_divergence(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
+                                                            unsigned long long *__restrict__ out) {
+  extern __shared__ unsigned hist[];  // [K][K]
+  // pair index -> (i, j)
+  int64_t p = blockIdx.x;
+  int i = 0;
+  while (p >= T - 1 - i) { p -= T - 1 - i; ++i; }
+  const int j = i + 1 + (int)p;
+  for (int x = threadIdx.x; x < K * K; x += blockDim.x) hist[x] = 0;
+  __syncthreads();
+  const uint8_t *ri = a + (int64_t)i * pitch, *rj = a + (int64_t)j * pitch;
+  unsigned long long *o = out + (int64_t)blockIdx.x * K * K;
+  for (int64_t s0 = 0; s0 < S; s0 += (int64_t)1 << 30) {  // flush the 32-bit bins before they can overflow
+    const int64_t s1 = s0 + ((int64_t)1 << 30) < S ? s0 + ((int64_t)1 << 30) : S;
+    for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+      const unsigned x = __ldg(ri + s), y = __ldg(rj + s);
+      if (x < (unsigned)K && y < (unsigned)K) atomicAdd(&hist[x * K + y], 1u);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < K * K; x += blockDim.x) { o[x] += hist[x]; hist[x] = 0; }
+    __syncthreads();
+  }
+}
+
+}  // namespace elx
+
+using namespace elx;
+
+extern "C" {
+
+int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequences, int64_t n_sites, int32_t n_states,
+                       elx_examine_result *out, double *d_keff_entropy_per_site, int64_t *d_equal_counts, int64_t *d_divergence,
+                       void *stream_) {
+  if (!out) return fail(nullptr, ELX_E_INVALID, "elx_examine: result is NULL");
+  memset(out, 0, sizeof *out);
+  const int T = n_sequences, K = n_states;
+  const int64_t S = n_sites;
+  if (T < 1 || S < 0 || K < 2 || K > EX_MAX_K) return fail(nullptr, ELX_E_INVALID, "elx_examine: need n_sequences >= 1, n_sites >= 0, 2 <= n_states <= 62");
+  if (!d_states && S > 0) return fail(nullptr, ELX_E_INVALID, "elx_examine: states buffer is NULL");
+  if (pitch < S) return fail(nullptr, ELX_E_INVALID, "elx_examine: pitch < n_sites");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, ELX_E_CUDA, "no CUDA device available (elynx_b200 has no CPU fallback)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+#define EX_CUDA(expr)                                                                                              \
+  do {                                                                                                             \
+    cudaError_t _e = (expr);                                                                                       \
+    if (_e != cudaSuccess) { cudaFree(d_acc); return fail(nullptr, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+  ExamineAcc *d_acc = nullptr;
+  EX_CUDA(cudaMalloc((void **)&d_acc, sizeof(ExamineAcc)));
+  EX_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(ExamineAcc), stream));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  out->n_sites = S; out->n_sequences = T; out->n_states = K;
+  ExamineAcc h;
+  memset(&h, 0, sizeof h);
+  if (S > 0) {
+    const size_t smem = (size_t)(K + 2) * EX_SPT * EX_THREADS * sizeof(uint32_t);
+    EX_CUDA(cudaFuncSetAttribute(k_examine_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t nb = (S + EX_BLOCK_SITES - 1) / EX_BLOCK_SITES;
+    int per_sm = (int)((size_t)200 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const unsigned grid = (unsigned)(nb < (int64_t)sms * per_sm ? nb : (int64_t)sms * per_sm);
+    k_examine_columns<<<grid, EX_THREADS, smem, stream>>>(d_states, pitch, T, S, K, d_acc, d_keff_entropy_per_site);
+    EX_CUDA(cudaGetLastError());
+  }
+  std::vector<unsigned long long> eq;
+  unsigned long long *d_eq = reinterpret_cast<unsigned long long *>(d_equal_counts), *d_eq_own = nullptr;
+  if (T >= 2 && S > 0) {
+    if (!d_eq) {
+      EX_CUDA(cudaMalloc((void **)&d_eq_own, sizeof(unsigned long long) * (size_t)T * T));
+      d_eq = d_eq_own;
+    }
+    cudaError_t e = cudaMemsetAsync(d_eq, 0, sizeof(unsigned long long) * (size_t)T * T, stream);
+    const int n_tiles = (T + HM_TILE - 1) / HM_TILE;
+    const int64_t n_chunks = (S + HM_CHUNK - 1) / HM_CHUNK;
+    const int64_t tile_pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
+    int64_t slices = ((int64_t)sms * 8 + tile_pairs - 1) / tile_pairs;  // enough CTAs to fill the GPU, few atomics
+    if (slices > n_chunks) slices = n_chunks;
+    if (slices < 1) slices = 1;
+    if (slices > 65535) slices = 65535;
+    if (e == cudaSuccess) {
+      k_examine_hamming<<<dim3((unsigned)(n_tiles * n_tiles), (unsigned)slices), 256, 0, stream>>>(d_states, pitch, T, S, n_tiles, (int)slices, d_eq);
+      e = cudaGetLastError();
+    }
+    eq.resize((size_t)T * T);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(eq.data(), d_eq, sizeof(unsigned long long) * (size_t)T * T, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) { cudaFree(d_eq_own); cudaFree(d_acc); return fail(nullptr, ELX_E_CUDA, std::string("elx_examine (hamming): ") + cudaGetErrorString(e)); }
+  }
+  if (d_divergence && T >= 2) {
+    const int64_t pairs = (int64_t)T * (T - 1) / 2;
+    if (pairs > 0x7fffffff) { cudaFree(d_eq_own); cudaFree(d_acc); return fail(nullptr, ELX_E_UNSUPPORTED, "elx_examine: too many sequence pairs for divergence matrices"); }
+    cudaError_t e = cudaMemsetAsync(d_divergence, 0, sizeof(int64_t) * (size_t)pairs * K * K, stream);
+    if (e == cudaSuccess && S > 0) {
+      k_examine_divergence<<<(unsigned)pairs, 256, sizeof(unsigned) * K * K, stream>>>(d_states, pitch, T, S, K,
+                                                                                         reinterpret_cast<unsigned long long *>(d_divergence));
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { cudaFree(d_eq_own); cudaFree(d_acc); return fail(nullptr, ELX_E_CUDA, std::string("elx_examine (divergence): ") + cudaGetErrorString(e)); }
+  }
+  cudaError_t e = cudaMemcpyAsync(&h, d_acc, sizeof h, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d_eq_own);
+  cudaFree(d_acc);
+  if (e != cudaSuccess) return fail(nullptr, ELX_E_CUDA, std::string("elx_examine: ") + cudaGetErrorString(e));
+#undef EX_CUDA
+  if (h.n_bad) return fail(nullptr, ELX_E_INVALID, "elx_examine: the matrix holds codes above n_states + 1");
+  out->n_constant = (int64_t)h.n_constant; out->n_constant_soft = (int64_t)h.n_constant_soft;
+  out->n_no_gaps = (int64_t)h.n_no_gaps; out->n_only_std = (int64_t)h.n_no_gaps;
+  out->n_std_chars = (int64_t)h.n_std; out->n_gaps = (int64_t)h.n_gap;
+  const double nan = std::nan(""), inf = INFINITY;
+  for (int k = 0; k < K; ++k) out->distribution[k] = S ? h.dist[k] / (double)S : 0.0;
+  out->keff_entropy_mean = S ? h.keff_e_all / (double)S : nan;
+  out->keff_entropy_mean_no_gaps = h.n_no_gaps ? h.keff_e_nogap / (double)h.n_no_gaps : nan;
+  out->keff_homoplasy_mean = S ? (h.n_h_inf_all ? inf : h.keff_h_all / (double)S) : nan;
+  out->keff_homoplasy_mean_no_gaps = h.n_no_gaps ? h.keff_h_nogap / (double)h.n_no_gaps : nan;
+  // pairwise Hamming distances per site: mean / maximum-likelihood variance / min / max over all pairs (Examine.hs:121-131)
+  out->hamming_mean = out->hamming_var = out->hamming_min = out->hamming_max = nan;
+  if (T >= 2 && S > 0) {
+    double sum = 0, mn = inf, mx = -inf;
+    const double np = (double)T * (T - 1) / 2;
+    for (int i = 0; i < T; ++i)
+      for (int j = i + 1; j < T; ++j) {
+        const double d = (double)(S - (int64_t)eq[(size_t)i * T + j]) / (double)S;
+        sum += d; mn = d < mn ? d : mn; mx = d > mx ? d : mx;
+      }
+    const double mean = sum / np;
+    double var = 0;
+    for (int i = 0; i < T; ++i)
+      for (int j = i + 1; j < T; ++j) {
+        const double d = (double)(S - (int64_t)eq[(size_t)i * T + j]) / (double)S - mean;
+        var += d * d;
+      }
+    out->hamming_mean = mean; out->hamming_var = var / np; out->hamming_min = mn; out->hamming_max = mx;
+  }
+  return 0;
+}
+
+int elx_examine(const uint8_t *states, int64_t pitch, int32_t n_sequences, int64_t n_sites, int32_t n_states,
+                elx_examine_result *out, double *keff_entropy_per_site, int64_t *equal_counts, int64_t *divergence) {
+  if (!out) return fail(nullptr, ELX_E_INVALID, "elx_examine: result is NULL");
+  if (n_sequences < 1 || n_sites < 0 || pitch < n_sites || (!states && n_sites > 0))
+    return fail(nullptr, ELX_E_INVALID, "elx_examine: bad matrix description");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, ELX_E_CUDA, "no CUDA device available (elynx_b200 has no CPU fallback)");
+  const int T = n_sequences, K = n_states;
+  const int64_t S = n_sites, dp = (S + 127) / 128 * 128;
+  uint8_t *d_a = nullptr;
+  double *d_ke = nullptr;
+  int64_t *d_eq = nullptr, *d_div = nullptr;
+  const int64_t pairs = (int64_t)T * (T - 1) / 2;
+  auto done = [&](int rc) { cudaFree(d_a); cudaFree(d_ke); cudaFree(d_eq); cudaFree(d_div); return rc; };
+  auto bad = [&](cudaError_t e) { return done(fail(nullptr, ELX_E_CUDA, std::string("elx_examine: ") + cudaGetErrorString(e))); };
+  cudaError_t e = cudaMalloc((void **)&d_a, (size_t)(dp > 0 ? dp : 128) * T);
+  if (e != cudaSuccess) return bad(e);
+  if (S > 0) {
+    e = cudaMemcpy2D(d_a, (size_t)dp, states, (size_t)pitch, (size_t)S, (size_t)T, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bad(e);
+  }
+  if (keff_entropy_per_site && S > 0 && (e = cudaMalloc((void **)&d_ke, sizeof(double) * (size_t)S)) != cudaSuccess) return bad(e);
+  if (equal_counts && (e = cudaMalloc((void **)&d_eq, sizeof(int64_t) * (size_t)T * T)) != cudaSuccess) return bad(e);
+  if (divergence && pairs > 0 && K >= 2 && K <= EX_MAX_K &&
+      (e = cudaMalloc((void **)&d_div, sizeof(int64_t) * (size_t)pairs * K * K)) != cudaSuccess)
+    return bad(e);
+  int rc = elx_examine_device(d_a, dp, n_sequences, n_sites, n_states, out, d_ke, d_eq, d_div, nullptr);
+  if (rc) return done(rc);
+  if (d_ke && (e = cudaMemcpy(keff_entropy_per_site, d_ke, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost)) != cudaSuccess) return bad(e);
+  if (d_eq) {
+    if (T >= 2 && S > 0) e = cudaMemcpy(equal_counts, d_eq, sizeof(int64_t) * (size_t)T * T, cudaMemcpyDeviceToHost);
+    else memset(equal_counts, 0, sizeof(int64_t) * (size_t)T * T);
+    if (e != cudaSuccess) return bad(e);
+  }
+  if (d_div && (e = cudaMemcpy(divergence, d_div, sizeof(int64_t) * (size_t)pairs * K * K, cudaMemcpyDeviceToHost)) != cudaSuccess) return bad(e);
+  return done(0);
+}
+
+}  // extern "C"

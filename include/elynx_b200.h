@@ -206,6 +206,39 @@ int64_t elx_fasta_row_offset(const elx_handle *h, const char *const *names, int6
 int elx_histogram_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_pitch, int64_t nsites,
                          int64_t *d_state_counts, int64_t *d_pattern_counts);
 
+/* ---- alignment statistics: the core of `slynx examine` on the device ------------------
+ * Replaces, for an alignment held as a code matrix, examineAlignment (slynx/src/SLynx/Examine/Examine.hs:52-160) and what it
+ * calls: filterColsConstant / ConstantSoft / NoGaps / OnlyStd, toFrequencyData, distribution, kEffEntropy, kEffHomoplasy,
+ * countGaps (elynx-seq Alignment.hs:209-300), entropy / homoplasy (DistributionDiversity.hs:37-110), hamming
+ * (Distance.hs:24-33) and divergence (Divergence.hs:38-64).
+ *   states [T][pitch] uint8 codes: 0..K-1 standard characters in sorted order (what elx_simulate writes), K = '-', K+1 = '.'
+ *   (the gap characters of DNAX / ProteinX: they never enter a frequency).  IUPAC alphabets are out of scope.
+ *   keff_entropy_per_site [n_sites] doubles or NULL (`slynx examine --per-site`).
+ *   equal_counts [T][T] int64 or NULL: upper triangle (i < j) = number of sites where sequences i and j carry the same
+ *   character; the Hamming distance is n_sites - equal_counts[i][j].
+ *   divergence [T(T-1)/2][K][K] int64 or NULL: count matrices of the pairs (0,1), (0,2), ..., (1,2), ... (`--divergence`).
+ * The _device variant takes device pointers, enqueues on `stream` (a cudaStream_t, may be NULL) and synchronises it before it
+ * returns; elx_examine takes host pointers.  Errors: elx_last_error(NULL). */
+typedef struct {
+  int64_t n_sites, n_sequences;
+  int32_t n_states, reserved;
+  int64_t n_constant;      /* columns whose characters are all equal */
+  int64_t n_constant_soft; /* ... counting only standard characters, at least one of them */
+  int64_t n_no_gaps;       /* columns without gaps */
+  int64_t n_only_std;      /* columns with standard characters only (= n_no_gaps without IUPAC codes) */
+  int64_t n_std_chars, n_gaps;
+  double distribution[64]; /* mean over the columns of the per-column frequencies of the standard characters */
+  double keff_entropy_mean, keff_entropy_mean_no_gaps;     /* mean effective number of states, exp(entropy) per column */
+  double keff_homoplasy_mean, keff_homoplasy_mean_no_gaps; /* ... 1 / sum f^2 per column */
+  double hamming_mean, hamming_var, hamming_min, hamming_max; /* pairwise, per site; variance = maximum likelihood */
+} elx_examine_result;
+
+int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequences, int64_t n_sites, int32_t n_states,
+                       elx_examine_result *out, double *d_keff_entropy_per_site, int64_t *d_equal_counts, int64_t *d_divergence,
+                       void *stream);
+int elx_examine(const uint8_t *states, int64_t pitch, int32_t n_sequences, int64_t n_sites, int32_t n_states,
+                elx_examine_result *out, double *keff_entropy_per_site, int64_t *equal_counts, int64_t *divergence);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t elx_launch_count(const elx_handle *h);
 
