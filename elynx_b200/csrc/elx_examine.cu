@@ -54,36 +54,46 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
 
 __global__ void __launch_bounds__(EX_THREADS) k_examine_columns(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
                                                                  ExamineAcc *__restrict__ acc, double *__restrict__ keff_site) {
-  extern __shared__ uint32_t cnt[];  // [(K + 2)][EX_SPT][EX_THREADS]
+  extern __shared__ uint32_t cnt[];  // [(K + 3)][EX_SPT][EX_THREADS]: K characters, two gap codes, one row for invalid codes
   const int tid = threadIdx.x, R = K + 2;
   const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 3) == 0);
   unsigned n_const = 0, n_soft = 0, n_nogap = 0, n_hinf = 0;
   unsigned long long n_std = 0, n_gap = 0, n_bad = 0;
   double ke_all = 0, ke_ng = 0, kh_all = 0, kh_ng = 0;
+  constexpr int UNROLL = 8;  // rows in flight per thread: the loop is load-latency bound otherwise
   for (int64_t base = (int64_t)blockIdx.x * EX_BLOCK_SITES; base < S; base += (int64_t)gridDim.x * EX_BLOCK_SITES) {
     const int64_t s0 = base + (int64_t)tid * EX_SPT;
-    for (int r = 0; r < R * EX_SPT; ++r) cnt[r * EX_THREADS + tid] = 0;
-    uint32_t first = 0, differs = 0;  // per site byte lanes: code of row 0; 0xff where some row differs from it
+    for (int r = 0; r < (R + 1) * EX_SPT; ++r) cnt[r * EX_THREADS + tid] = 0;
     const bool whole = aligned && s0 + EX_SPT <= S;
-    for (int t = 0; t < T; ++t) {
-      uint32_t w = 0;
+    auto load_row = [&](int t) -> uint32_t {
       const uint8_t *p = a + (int64_t)t * pitch + s0;
-      if (whole) {
-        w = __ldg(reinterpret_cast<const uint32_t *>(p));
-      } else {
+      if (whole) return __ldg(reinterpret_cast<const uint32_t *>(p));
+      uint32_t w = 0;
 #pragma unroll
-        for (int d = 0; d < EX_SPT; ++d)
-          if (s0 + d < S) w |= (uint32_t)__ldg(p + d) << (8 * d);
-      }
-      if (t == 0) first = w;
-      differs |= __vcmpne4(w, first);
+      for (int d = 0; d < EX_SPT; ++d)
+        if (s0 + d < S) w |= (uint32_t)__ldg(p + d) << (8 * d);
+      return w;
+    };
+    const uint32_t first = load_row(0);  // per site byte lanes: code of row 0
+    uint32_t differs = 0;                // 0xff where some row differs from it
+    for (int t0 = 0; t0 < T; t0 += UNROLL) {
+      uint32_t w[UNROLL];
 #pragma unroll
-      for (int d = 0; d < EX_SPT; ++d) {
-        uint32_t code = (w >> (8 * d)) & 0xffu;
-        if (code >= (uint32_t)R) { code = (uint32_t)K; if (s0 + d < S) ++n_bad; }
-        cnt[(code * EX_SPT + d) * EX_THREADS + tid] += 1;
+      for (int u = 0; u < UNROLL; ++u) w[u] = t0 + u < T ? load_row(t0 + u) : first;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (t0 + u >= T) break;
+        differs |= __vcmpne4(w[u], first);
+#pragma unroll
+        for (int d = 0; d < EX_SPT; ++d) {
+          const uint32_t code = min((w[u] >> (8 * d)) & 0xffu, (uint32_t)R);
+          cnt[(code * EX_SPT + d) * EX_THREADS + tid] += 1;
+        }
       }
     }
+#pragma unroll
+    for (int d = 0; d < EX_SPT; ++d)
+      if (s0 + d < S) n_bad += cnt[(R * EX_SPT + d) * EX_THREADS + tid];
     double dist_part[EX_SPT];
 #pragma unroll
     for (int d = 0; d < EX_SPT; ++d) {
@@ -248,7 +258,7 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
   ExamineAcc h;
   memset(&h, 0, sizeof h);
   if (S > 0) {
-    const size_t smem = (size_t)(K + 2) * EX_SPT * EX_THREADS * sizeof(uint32_t);
+    const size_t smem = (size_t)(K + 3) * EX_SPT * EX_THREADS * sizeof(uint32_t);
     EX_CUDA(cudaFuncSetAttribute(k_examine_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nb = (S + EX_BLOCK_SITES - 1) / EX_BLOCK_SITES;
     int per_sm = (int)((size_t)200 * 1024 / (smem + 1024));
