@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -52,7 +53,7 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
   return v;
 }
 
-__global__ void __launch_bounds__(EX_THREADS) k_examine_columns(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
+__global__ void __launch_bounds__(EX_THREADS, 4) k_examine_columns(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
                                                                  ExamineAcc *__restrict__ acc, double *__restrict__ keff_site) {
   extern __shared__ uint32_t cnt[];  // [(K + 3)][EX_SPT][EX_THREADS]: K characters, two gap codes, one row for invalid codes
   const int tid = threadIdx.x, R = K + 2;
@@ -75,22 +76,48 @@ __global__ void __launch_bounds__(EX_THREADS) k_examine_columns(const uint8_t *_
       return w;
     };
     const uint32_t first = load_row(0);  // per site byte lanes: code of row 0
-    uint32_t differs = 0;                // 0xff where some row differs from it
-    for (int t0 = 0; t0 < T; t0 += UNROLL) {
-      uint32_t w[UNROLL];
+    uint32_t differs = 0;                // nonzero byte lanes where some row differs from it
+    const uint32_t rmax4 = (uint32_t)R * 0x01010101u, rchk4 = (uint32_t)(128 - R) * 0x01010101u;
+    const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(cnt) + (uint32_t)tid * 4u;
+    // NR rows at once: loads first (NR requests in flight), validity check, then the counters
+    const uint8_t *col = a + s0;
+    auto rows = [&](auto NRc, auto WHOLEc, int t0) {
+      constexpr int NR = decltype(NRc)::value;
+      constexpr bool WHOLE = decltype(WHOLEc)::value;
+      uint32_t w[NR];
+      const uint8_t *p = col + (int64_t)t0 * pitch;
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) w[u] = t0 + u < T ? load_row(t0 + u) : first;
+      for (int u = 0; u < NR; ++u) {  // a running pointer: one 64-bit add per row instead of a 64-bit multiply-add
+        w[u] = WHOLE ? __ldg(reinterpret_cast<const uint32_t *>(p)) : load_row(t0 + u);
+        p += pitch;
+      }
+      // a byte is a valid code iff it is < R: bit 7 of b | (b + 128 - R) is clear (no carries between valid bytes)
+      uint32_t chk = 0;
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        if (t0 + u >= T) break;
-        differs |= __vcmpne4(w[u], first);
+      for (int u = 0; u < NR; ++u) chk |= w[u] | (w[u] + rchk4);
+      if (chk & 0x80808080u) {
+#pragma unroll
+        for (int u = 0; u < NR; ++u) w[u] = __vminu4(w[u], rmax4);  // invalid codes land in the extra row R (and are reported)
+      }
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        differs |= w[u] ^ first;
 #pragma unroll
         for (int d = 0; d < EX_SPT; ++d) {
-          const uint32_t code = min((w[u] >> (8 * d)) & 0xffu, (uint32_t)R);
-          cnt[(code * EX_SPT + d) * EX_THREADS + tid] += 1;
+          // one byte permute for the code, one multiply-add for the address, one shared-memory reduction (fire and forget:
+          // every thread owns its counters, but a load / add / store chain would be serialised by possible aliasing)
+          const uint32_t code = __byte_perm(w[u], 0u, 0x4440u + (uint32_t)d);
+          const uint32_t addr = code * (uint32_t)(EX_SPT * EX_THREADS * 4) + (cnt_s + (uint32_t)(d * EX_THREADS * 4));
+          asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
         }
       }
-    }
+    };
+    int t0 = 0;
+    if (whole)
+      for (; t0 + UNROLL <= T; t0 += UNROLL) rows(std::integral_constant<int, UNROLL>{}, std::true_type{}, t0);
+    else
+      for (; t0 + UNROLL <= T; t0 += UNROLL) rows(std::integral_constant<int, UNROLL>{}, std::false_type{}, t0);
+    for (; t0 < T; ++t0) rows(std::integral_constant<int, 1>{}, std::false_type{}, t0);
 #pragma unroll
     for (int d = 0; d < EX_SPT; ++d)
       if (s0 + d < S) n_bad += cnt[(R * EX_SPT + d) * EX_THREADS + tid];
@@ -197,6 +224,79 @@ __global__ void __launch_bounds__(256) k_examine_hamming(const uint8_t *__restri
   }
 }
 
+// Gap-free alignments over at most 4 characters (what the DNA simulator writes): 2 bits per site, 16 sites per word, and
+// a pair of words is compared with XOR / OR-shift / mask / POPC -- 5 instructions per 16 sites instead of 7 per 4.
+__global__ void k_examine_pack2(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int64_t W, uint32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)T * W) return;
+  const int t = (int)(i / W);
+  const int64_t w = i % W, s0 = w * 16;
+  const uint8_t *p = a + (int64_t)t * pitch + s0;
+  uint32_t v = 0;
+  if (s0 + 16 <= S && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t b = x[k] & 0x03030303u;  // four 2-bit codes in byte lanes -> 8 contiguous bits
+      v |= ((b | (b >> 6) | (b >> 12) | (b >> 18)) & 0xffu) << (8 * k);
+    }
+  } else {
+    for (int d = 0; d < 16; ++d)
+      if (s0 + d < S) v |= (uint32_t)(__ldg(p + d) & 3u) << (2 * d);  // cells beyond S stay 0 in every row: they compare equal
+  }
+  out[i] = v;
+}
+
+constexpr int H2_CHUNK = 256, H2_STRIDE = H2_CHUNK + 1;  // words per row and chunk; padded: conflict-free
+__global__ void __launch_bounds__(256) k_examine_hamming2(const uint32_t *__restrict__ a, int T, int64_t W, int n_tiles, int n_slices,
+                                                          unsigned long long *__restrict__ eq) {
+  extern __shared__ uint32_t h2_rows[];  // [2][HM_TILE][H2_STRIDE]
+  uint32_t *rows_i = h2_rows, *rows_j = h2_rows + HM_TILE * H2_STRIDE;
+  const int ti = blockIdx.x / n_tiles, tj = blockIdx.x % n_tiles;
+  if (tj < ti) return;
+  const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;
+  unsigned long long acc[4] = {0, 0, 0, 0};
+  const int64_t n_chunks = (W + H2_CHUNK - 1) / H2_CHUNK;
+  for (int64_t ch = blockIdx.y; ch < n_chunks; ch += n_slices) {
+    const int64_t w0 = ch * H2_CHUNK;
+    __syncthreads();
+    for (int i = tid; i < HM_TILE * H2_CHUNK; i += 256) {
+      const int row = i / H2_CHUNK, col = i % H2_CHUNK;
+      const int64_t w = w0 + col;
+      const int gi = ti * HM_TILE + row, gj = tj * HM_TILE + row;
+      // words beyond W (or rows beyond T) are 0 in the i tile and all-ones in the j tile: 16 mismatches, no equal site
+      rows_i[row * H2_STRIDE + col] = (gi < T && w < W) ? __ldg(a + (int64_t)gi * W + w) : 0u;
+      rows_j[row * H2_STRIDE + col] = (gj < T && w < W) ? __ldg(a + (int64_t)gj * W + w) : 0xffffffffu;
+    }
+    __syncthreads();
+    unsigned mis[4] = {0, 0, 0, 0};
+    const uint32_t *yj = rows_j + c * H2_STRIDE;
+#pragma unroll 4
+    for (int w = 0; w < H2_CHUNK; ++w) {
+      const uint32_t y = yj[w];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const uint32_t z = rows_i[(r + 8 * m) * H2_STRIDE + w] ^ y;
+        mis[m] += __popc((z | (z >> 1)) & 0x55555555u);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[m] += (unsigned)(16 * H2_CHUNK) - mis[m];
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int gi = ti * HM_TILE + r + 8 * m, gj = tj * HM_TILE + c;
+    if (gi < T && gj < T && acc[m]) atomicAdd(&eq[(int64_t)gi * T + gj], acc[m]);
+  }
+}
+
+// the padding cells of the last word compare equal in every pair: take them out again
+__global__ void k_examine_sub_pad(unsigned long long *__restrict__ eq, int T, unsigned long long pad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)T * T) eq[i] -= eq[i] >= pad ? pad : eq[i];
+}
+
 // divergence (Divergence.hs:38-64): out[pair][x][y] = number of sites with standard characters x in sequence i and y in j,
 // pairs (i < j) in the order of `tuples` (Examine.hs:165-167): (0,1), (0,2), ..., (1,2), ...
 __global__ void __launch_bounds__(256) k_examine_divergence(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
@@ -283,7 +383,38 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
     if (slices > n_chunks) slices = n_chunks;
     if (slices < 1) slices = 1;
     if (slices > 65535) slices = 65535;
-    if (e == cudaSuccess) {
+    // gap-free alignments over <= 4 characters take the 2-bit path; whether there are gaps is known after the column pass
+    bool two_bit = false;
+    if (e == cudaSuccess && K <= 4) {
+      ExamineAcc probe;
+      e = cudaMemcpyAsync(&probe, d_acc, sizeof probe, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+      two_bit = e == cudaSuccess && probe.n_gap == 0 && probe.n_bad == 0;
+    }
+    uint32_t *d_packed = nullptr;
+    if (e == cudaSuccess && two_bit) {
+      const int64_t W = (S + 15) / 16;
+      e = cudaMalloc((void **)&d_packed, sizeof(uint32_t) * (size_t)T * W);
+      if (e == cudaSuccess) {
+        const int64_t n = (int64_t)T * W;
+        k_examine_pack2<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_states, pitch, T, S, W, d_packed);
+        const int64_t chunks2 = (W + H2_CHUNK - 1) / H2_CHUNK;
+        int64_t sl = slices < chunks2 ? slices : chunks2;
+        if (sl < 1) sl = 1;
+        const size_t smem2 = sizeof(uint32_t) * 2 * HM_TILE * H2_STRIDE;
+        e = cudaFuncSetAttribute(k_examine_hamming2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e == cudaSuccess) {
+          k_examine_hamming2<<<dim3((unsigned)(n_tiles * n_tiles), (unsigned)sl), 256, smem2, stream>>>(d_packed, T, W, n_tiles, (int)sl, d_eq);
+          // every chunk counts 16 * H2_CHUNK cells per pair: the cells past S (zero padding of the last word, and the
+          // words past W of the last chunk, which never compare equal) -- only the former are equal
+          const unsigned long long pad = (unsigned long long)(16 * W - S);
+          if (pad) k_examine_sub_pad<<<(unsigned)(((int64_t)T * T + 255) / 256), 256, 0, stream>>>(d_eq, T, pad);
+          e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(d_packed);
+      }
+    } else if (e == cudaSuccess) {
       k_examine_hamming<<<dim3((unsigned)(n_tiles * n_tiles), (unsigned)slices), 256, 0, stream>>>(d_states, pitch, T, S, n_tiles, (int)slices, d_eq);
       e = cudaGetLastError();
     }
