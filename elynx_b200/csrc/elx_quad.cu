@@ -265,6 +265,17 @@ __device__ __forceinline__ uint32_t entry_addr(uint32_t idx, uint32_t entry_byte
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(idx), "r"(entry_bytes), "r"(base));
   return d;
 }
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -419,7 +430,10 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) k2_quad_tiled(QuadArgs fa) {
       int buf = 0;
       uint32_t phase = 1;  // the first pass over the ring finds every buffer free
       for (int g = 0; g < fa.G; ++g) {
-        if (g >= nstage) mbar_wait(smem_u32(&empty_bar[buf]), phase);
+        // the ring gives this warp three records of slack: poll the empty barrier with a back-off.  A tight try_wait loop
+        // was 12 % of all issued instructions, all on this warp's sub-partition (top scheduling priority: highest warp
+        // id), and the two consumer warps it starved there set the pace of the whole CTA through the ring.
+        if (g >= nstage) mbar_wait_backoff(smem_u32(&empty_bar[buf]), phase, 256);
         mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
         tma_bulk_g2s(stage_smem + (uint32_t)(buf * fa.stage_bytes), fa.ftab + (size_t)g * fa.stage_bytes, (uint32_t)fa.stage_bytes,
                      smem_u32(&full_bar[buf]));
