@@ -288,6 +288,26 @@ def test_small_alphabets_quad_and_pair(k):
     assert stats.chi2.sf(chi2, int(keep.sum()) - 1) > 1e-4
 
 
+def test_quad_large_tree_many_components_and_far_site_offsets():
+    """Quad mode away from the small fixtures: a 3000-taxon birth-death tree (~1100 records, 8+ slots), GTR + Gamma(8)
+    (32 KB of rows per record: a two-stage ring), site ranges that start beyond 2^32 and 2^40 (high counter words) at
+    odd offsets, tiled and generic kernels against the executable spec."""
+    from elynx_b200 import model as pm
+
+    tree = pm.birth_death_tree(3000, 1.0, 0.5, seed=11)
+    model = pm.get_phylo_model("GTR4[1,2,3,4,5,6]{0.2,0.3,0.4,0.1}", gamma=(8, 0.7))
+    mt = (True, model.weights, model.pi)
+    for fg in (False, True):
+        with eb.Simulator(model.weights, model.pi, model.exch, tree, is_mixture=True, force_generic=fg) as sim:
+            assert sim.quad_groups > 1000 and sim.n_components == 8
+            if not fg:
+                check_quad_tables(sim.ptables(), sim.quad_tables(), tree.parent, tree.leaf_row, max_records=12)
+            for site0, s in ((0, 4099), ((1 << 32) + 5, 3001), ((1 << 40) - 7, 2050)):
+                leaves, comps, _ = sim.simulate(17, s, site0=site0, want_comps=True)
+                l0, c0, _ = spec_freerun(sim, mt, tree, 17, site0, s)
+                assert np.array_equal(leaves, l0) and np.array_equal(comps, c0), (fg, site0)
+
+
 def test_freerun_partition_invariance():
     """Output is a pure function of (seed, global site, node): any split of the site range gives the same bytes."""
     model = model_case("hky_g4")
