@@ -23,4 +23,5 @@ SIGNATURES = {
     "elx_flat_tree_arrays": (C.c_int, [_VP, _VP, _VP, _VP]),
     "elx_flat_tree_name": (C.c_char_p, [_VP, C.c_int]),
     "elx_flat_tree_to_newick": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "elx_gzip_write": (C.c_int, [C.c_char_p, _VP, _I64, _I32, _I32, _I64]),
 }

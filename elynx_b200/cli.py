@@ -74,6 +74,16 @@ def site_dists(comps, model) -> bytes:
     return "\n".join("%d %s" % (i + 1, rows[c]) for i, c in enumerate(comps)).encode()
 
 
+def write_gz(path: str, data: bytes, threads: int = 0) -> None:
+    """writeGZFile (elynx-tools InputOutput.hs:80-83) through the parallel multi-member writer elx_gzip_write."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+    L.check(L.lib().elx_gzip_write(path.encode(), C.cast(buf, C.c_void_p) if buf is not None else None, len(data), threads, 6, 0))
+
+
 def simulate_cmd(args) -> int:
     t0 = time.time()
     log = (lambda *a: None) if args.verbosity == "Quiet" else (lambda *a: print(*a, file=sys.stderr))
@@ -127,7 +137,10 @@ def simulate_cmd(args) -> int:
         fasta, cs = sim.simulate_fasta(seed, args.length, tree.leaf_names(), model.alphabet_chars, want_comps=model.is_mixture)
     if args.output_file_basename:
         fn = args.output_file_basename + ".fasta"
-        (gzip.open if fn.endswith(".gz") else open)(fn, "wb").write(fasta)
+        if fn.endswith(".gz"):
+            write_gz(fn, fasta)
+        else:
+            open(fn, "wb").write(fasta)
         log("Wrote simulated multi sequence alignment to '%s'." % fn)
         if model.is_mixture and model.alphabet == pm.PROTEIN:
             open(args.output_file_basename + ".sitedists", "wb").write(site_dists(cs, model))

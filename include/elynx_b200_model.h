@@ -69,6 +69,12 @@ const char *elx_flat_tree_name(const elx_flat_tree *t, int node);
 /* toNewick (elynx-tree Export/Newick.hs:49-65): returns a malloc'ed NUL-terminated string (elx_free) */
 int elx_flat_tree_to_newick(const elx_flat_tree *t, char **out);
 
+/* writeGZFile (elynx-tools/src/ELynx/Tools/InputOutput.hs:80-83) for big outputs: gzip `data` into `path` with n_threads
+ * worker threads (<= 0: all host cores).  The file is a sequence of gzip members, one per block_bytes of input (<= 0: 4 MiB),
+ * which gunzip, Python's gzip module and the reference's `decompress` (InputOutput.hs:73-76) read back as one stream.
+ * level: zlib 0..9 (anything else: 6).  Host-only. */
+int elx_gzip_write(const char *path, const uint8_t *data, int64_t size, int32_t n_threads, int32_t level, int64_t block_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,3 +283,34 @@ def test_quad_walk_program():
             assert ns.value <= 24
         if binary and n > 3:
             assert ng.value <= (nleaves + 1) // 2, (nleaves, ng.value)
+
+
+def test_parallel_gzip_writer(tmp_path):
+    """elx_gzip_write (writeGZFile, elynx-tools InputOutput.hs:80-83): multi-member gzip that every gzip reader returns
+    byte for byte; independent of the thread count; empty input gives one empty member."""
+    import ctypes as C
+    import gzip
+    import subprocess
+
+    rng = np.random.default_rng(3)
+    data = (b">seq%d\n" % 7) + bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=3_000_001).tobytes()) + b"\n"
+    outs = []
+    for threads, block in ((1, 1 << 20), (4, 1 << 20), (3, 777_777)):
+        path = str(tmp_path / ("t%d_%d.gz" % (threads, block)))
+        buf = (C.c_char * len(data)).from_buffer_copy(data)
+        L.check(L.lib().elx_gzip_write(path.encode(), C.cast(buf, C.c_void_p), len(data), threads, 6, block))
+        raw = open(path, "rb").read()
+        assert gzip.decompress(raw) == data
+        assert raw.count(b"\x1f\x8b\x08") >= (len(data) + block - 1) // block
+        assert subprocess.run(["gzip", "-dc", path], capture_output=True, check=True).stdout == data
+        outs.append(raw)
+    assert outs[0] == outs[1]                      # block size fixes the bytes, the thread count does not
+    empty = str(tmp_path / "empty.gz")
+    L.check(L.lib().elx_gzip_write(empty.encode(), None, 0, 2, 6, 0))
+    assert gzip.decompress(open(empty, "rb").read()) == b""
+    from elynx_b200 import cli
+    p2 = str(tmp_path / "cli.gz")
+    cli.write_gz(p2, data)
+    assert gzip.decompress(open(p2, "rb").read()) == data
+    with pytest.raises(L.ElxError):
+        L.check(L.lib().elx_gzip_write(str(tmp_path / "nodir" / "x.gz").encode(), None, 0, 1, 6, 0))
