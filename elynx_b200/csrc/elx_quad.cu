@@ -300,7 +300,6 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
                                              const uint32_t CB1, const uint32_t CB2, const uint32_t CB3, const int64_t sbase,
                                              const int64_t col0, uint8_t *leaf_base, const int store_mode, const int lane) {
   const SimArgs &a = fa.s;
-  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
   const uint64_t G0 = (uint64_t)sbase >> 4;  // the thread's 16-site group
   const uint32_t G0lo = (uint32_t)G0, Ghi = (uint32_t)(G0 >> 32);
   constexpr uint32_t SM = 0x03030303u;
@@ -537,7 +536,7 @@ static bool quad_geometry(int C, int n_slots, QuadTables *qt) {
   int want_threads = 0, want_stages = 0, want_minb = 0;
   if (const char *e = getenv("ELX_QUAD_THREADS")) want_threads = atoi(e);  // tuning knobs
   if (const char *e = getenv("ELX_QUAD_NSTAGE")) want_stages = atoi(e);
-  if (const char *e = getenv("ELX_QUAD_MINB")) want_minb = atoi(e);
+  if (const char *e = getenv("ELX_QUAD_MINB")) want_minb = atoi(e);        // 1 or 2 CTAs per SM
   const int cand[3][2] = {{256, 2}, {512, 1}, {256, 1}};
   for (int ci = 0; ci < 3; ++ci) {
     const int th = cand[ci][0], minb = cand[ci][1];
