@@ -308,6 +308,22 @@ def test_quad_large_tree_many_components_and_far_site_offsets():
                 assert np.array_equal(leaves, l0) and np.array_equal(comps, c0), (fg, site0)
 
 
+def test_quad_tables_of_the_benchmark_configuration_are_exact():
+    """BASELINE config 2 (HKY + Gamma(4) on the 1000-taxon birth-death tree bench.py uses): EVERY record's alias rows carry
+    the integer masses of the cap's joint distribution (brute-force sums over the summed-out nodes), and the walk covers
+    the tree -- with spec parity this makes the benchmarked stream an exact sampler of the reference's leaf distribution."""
+    from elynx_b200 import model as pm
+
+    tree = pm.birth_death_tree(1000, 1.0, 0.5, seed=1)
+    model = pm.get_phylo_model("HKY[6.0]{0.2,0.3,0.3,0.2}", gamma=(4, 0.5))
+    with eb.Simulator(model.weights, model.pi, model.exch, tree, is_mixture=True) as sim:
+        quad = sim.quad_tables()
+        assert 330 <= sim.quad_groups <= 400
+        check_quad_tables(sim.ptables(), quad, tree.parent, tree.leaf_row, max_records=10 ** 9)
+        frontier = (quad[0][:, 1:5] >= 0).sum(axis=1)
+        assert frontier.max() == 4 and frontier.sum() >= 1000  # leaves + kept internal nodes
+
+
 def test_freerun_partition_invariance():
     """Output is a pure function of (seed, global site, node): any split of the site range gives the same bytes."""
     model = model_case("hky_g4")
