@@ -194,7 +194,7 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
   std::vector<int> cost((size_t)N * (W + 1), INF), nn((size_t)N * (W + 1), 0);
   auto C_ = [&](int v, int w) -> int & { return cost[(size_t)v * (W + 1) + w]; };
   auto N_ = [&](int v, int w) -> int & { return nn[(size_t)v * (W + 1) + w]; };
-  struct Part { int cost = INF, nodes = 0; std::vector<int8_t> kw; std::vector<int32_t> grp; };
+  struct Part { int cost = INF, nodes = 0; std::vector<int8_t> kw; };
   for (int v = N - 1; v >= 0; --v) {
     const std::vector<int> &k = kids[v];
     if (k.empty()) { C_(v, 1) = 0; N_(v, 1) = 1; continue; }
@@ -220,36 +220,50 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
           C_(v, w) = comb[w].cost; N_(v, w) = comb[w].nodes + 1; ch[v].kw[w] = comb[w].kw;
         }
     }
-    // v closed: its kids are packed, in order, into caps of at most W frontier nodes (state = frontier size of the cap being filled)
-    Part dp[W + 1];
-    dp[0].cost = 0;
+    // v closed: its kids are packed, in order, into caps of at most W frontier nodes (state = frontier size of the cap
+    // being filled).  Back-pointers instead of per-state copies of the choices: linear in the number of kids, also for a
+    // star with 10^5 leaves.
+    struct Step { int8_t prev, w; bool fresh; };  // how state s after kid i was reached
+    std::vector<Step> steps((k.size() + 1) * (W + 1), Step{-1, 0, false});
+    int dcost[W + 1], dnodes[W + 1];
+    for (int s = 0; s <= W; ++s) { dcost[s] = INF; dnodes[s] = 0; }
+    dcost[0] = 0;
     for (size_t i = 0; i < k.size(); ++i) {
-      Part nx[W + 1];
+      int ncost[W + 1], nnodes[W + 1];
+      for (int s = 0; s <= W; ++s) { ncost[s] = INF; nnodes[s] = 0; }
+      Step *st_i = &steps[(i + 1) * (W + 1)];
       for (int s0 = 0; s0 <= W; ++s0) {
-        if (dp[s0].cost >= INF) continue;
+        if (dcost[s0] >= INF) continue;
         for (int w = 1; w <= W; ++w) {
           if (C_(k[i], w) >= INF) continue;
-          const int grp0 = dp[s0].grp.empty() ? -1 : dp[s0].grp.back();
-          if (s0 > 0 && s0 + w <= W && dp[s0].nodes + N_(k[i], w) <= QUAD_MAX_CAP) {  // joins the cap being filled
-            const int val = dp[s0].cost + C_(k[i], w);
-            Part &t = nx[s0 + w];
-            if (val < t.cost) {
-              t = dp[s0]; t.cost = val; t.nodes += N_(k[i], w); t.kw.push_back((int8_t)w); t.grp.push_back(grp0);
-            }
+          if (s0 > 0 && s0 + w <= W && dnodes[s0] + N_(k[i], w) <= QUAD_MAX_CAP) {  // joins the cap being filled
+            const int val = dcost[s0] + C_(k[i], w);
+            if (val < ncost[s0 + w]) { ncost[s0 + w] = val; nnodes[s0 + w] = dnodes[s0] + N_(k[i], w); st_i[s0 + w] = Step{(int8_t)s0, (int8_t)w, false}; }
           }
-          const int val = dp[s0].cost + C_(k[i], w) + 1;  // starts a new cap
-          Part &t = nx[w];
-          if (val < t.cost) {
-            t = dp[s0]; t.cost = val; t.nodes = N_(k[i], w); t.kw.push_back((int8_t)w); t.grp.push_back(grp0 + 1);
-          }
+          const int val = dcost[s0] + C_(k[i], w) + 1;  // starts a new cap
+          if (val < ncost[w]) { ncost[w] = val; nnodes[w] = N_(k[i], w); st_i[w] = Step{(int8_t)s0, (int8_t)w, true}; }
         }
       }
-      for (int s = 0; s <= W; ++s) dp[s] = nx[s];
+      for (int s = 0; s <= W; ++s) { dcost[s] = ncost[s]; dnodes[s] = nnodes[s]; }
     }
     int best = 1;
-    for (int s = 1; s <= W; ++s) if (dp[s].cost < dp[best].cost) best = s;
-    ch[v].ckw = dp[best].kw; ch[v].cgrp = dp[best].grp;
-    if (dp[best].cost < C_(v, 1)) { C_(v, 1) = dp[best].cost; N_(v, 1) = 1; ch[v].closed1 = true; } else ch[v].closed1 = false;
+    for (int s = 1; s <= W; ++s) if (dcost[s] < dcost[best]) best = s;
+    {
+      std::vector<int8_t> kw(k.size());
+      std::vector<char> fresh(k.size());
+      int s = best;
+      for (size_t i = k.size(); i-- > 0;) {
+        const Step &t = steps[(i + 1) * (W + 1) + s];
+        kw[i] = t.w; fresh[i] = t.fresh ? 1 : 0;
+        s = t.prev;
+      }
+      ch[v].ckw = kw;
+      ch[v].cgrp.assign(k.size(), 0);
+      int grp = -1;
+      for (size_t i = 0; i < k.size(); ++i) { if (fresh[i]) ++grp; ch[v].cgrp[i] = grp; }
+    }
+    struct { int cost; } dpb{dcost[best]};
+    if (dpb.cost < C_(v, 1)) { C_(v, 1) = dpb.cost; N_(v, 1) = 1; ch[v].closed1 = true; } else ch[v].closed1 = false;
   }
 
   // ---- records, depth first (light caps and light frontier nodes first), slots
@@ -260,17 +274,17 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
     if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
     return high++;
   };
-  struct Frame { int v, slot, gi, n_groups; std::vector<std::pair<int, int>> pending; size_t pi; };
+  struct Frame { int v, slot, gi, n_groups; std::vector<std::pair<int, int>> pending; size_t pi; size_t kid0 = 0; };  // kid0: first kid of cap gi
   std::vector<Frame> st;
   auto n_groups = [&](int v) { return ch[v].cgrp.empty() ? 0 : (int)ch[v].cgrp.back() + 1; };
-  st.push_back(Frame{0, alloc(), 0, n_groups(0), {}, 0});
+  st.push_back(Frame{0, alloc(), 0, n_groups(0), {}, 0, 0});
   struct Visit { int x, w, par; };
   std::vector<Visit> vs;
   while (!st.empty()) {
     Frame &f = st.back();
     if (f.pi < f.pending.size()) {
       const std::pair<int, int> nb = f.pending[f.pi++];
-      st.push_back(Frame{nb.first, nb.second, 0, n_groups(nb.first), {}, 0});  // invalidates f
+      st.push_back(Frame{nb.first, nb.second, 0, n_groups(nb.first), {}, 0, 0});  // invalidates f
       continue;
     }
     if (f.gi == f.n_groups) { st.pop_back(); continue; }
@@ -280,8 +294,10 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
     int nf = 0;
     vs.clear();
     const std::vector<int> &k = kids[f.v];
-    for (size_t i = k.size(); i-- > 0;)
-      if (ch[f.v].cgrp[i] == f.gi) vs.push_back(Visit{k[i], ch[f.v].ckw[i], -1});
+    size_t kid1 = f.kid0;  // the caps of a node are runs of its kids
+    while (kid1 < k.size() && ch[f.v].cgrp[kid1] == f.gi) ++kid1;
+    for (size_t i = kid1; i-- > f.kid0;) vs.push_back(Visit{k[i], ch[f.v].ckw[i], -1});
+    f.kid0 = kid1;
     std::vector<int> boundary;
     while (!vs.empty()) {
       const Visit t = vs.back();

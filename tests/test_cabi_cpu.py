@@ -248,6 +248,7 @@ def test_quad_walk_program():
         cur = len(parent) - 1
     cases.append((np.array(parent), np.array(leaf_row), True))
     cases.append((np.array([-1] + [0] * 1000), np.array([-1] + list(range(1000))), False))
+    cases.append((np.array([-1] + [0] * 30001), np.array([-1] + list(range(30001))), False))  # a wide star: the compiler must stay linear
     cases.append((np.array([-1] + list(range(40)) + [40, 40]), np.array([-1] * 41 + [0, 1]), False))
     for _ in range(30):
         parent = [-1]
