@@ -33,6 +33,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
         assert s in L.SIGNATURES, "no ctypes signature for " + s
     assert lib.elx_version() >= 100
+    from elynx_b200 import _model_sigs
+
+    msyms = declared_symbols("elynx_b200_model.h")
+    assert len(msyms) >= 15
+    for s in msyms:
+        assert hasattr(lib, s), s
+        assert s in _model_sigs.SIGNATURES, "no ctypes signature for " + s
 
 
 class T3:
