@@ -179,6 +179,129 @@ __global__ void __launch_bounds__(EX_THREADS, 4) k_examine_columns(const uint8_t
   }
 }
 
+// K == 4 and no gaps (what the DNA simulator writes): the same statistics without shared memory.  A thread owns 8
+// consecutive sites (one 64-bit load per row, 16 rows in flight); the counts of the four codes live in the BYTE LANES of
+// registers -- one shift and four 3-input logic operations turn a word into four one-hot words, four adds accumulate
+// them (2.6 instructions per cell with the checks); byte lanes are folded into 16-bit lanes every 240 rows (T <= 65535).
+// A byte >= 4 anywhere (gap or invalid code: one OR per word to find out) raises `fallback` and the host reruns the
+// generic kernel.  Per-site arithmetic is the generic kernel's, operation for operation.
+constexpr int D4_SPT = 8, D4_BLOCK_SITES = EX_THREADS * D4_SPT;
+__global__ void __launch_bounds__(EX_THREADS, 2) k_examine_columns_k4(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S,
+                                                                    ExamineAcc *__restrict__ acc, double *__restrict__ keff_site,
+                                                                    int *__restrict__ fallback) {
+  constexpr int K = 4, UNROLL = 16;
+  constexpr uint32_t M = 0x01010101u, L16 = 0x00ff00ffu;
+  const int tid = threadIdx.x;
+  const bool aligned = ((pitch & 7) == 0) && ((reinterpret_cast<uintptr_t>(a) & 7) == 0);
+  unsigned n_const = 0;
+  unsigned long long n_std = 0;
+  double ke_all = 0, kh_all = 0;
+  uint32_t hi = 0;
+  for (int64_t base = (int64_t)blockIdx.x * D4_BLOCK_SITES; base < S; base += (int64_t)gridDim.x * D4_BLOCK_SITES) {
+    const int64_t s0 = base + (int64_t)tid * D4_SPT;
+    const bool whole = aligned && s0 + D4_SPT <= S;
+    const uint8_t *col = a + s0;
+    auto load_slow = [&](int t) -> uint2 {
+      const uint8_t *p = col + (int64_t)t * pitch;
+      uint32_t w[2] = {0, 0};
+#pragma unroll
+      for (int d = 0; d < D4_SPT; ++d)
+        if (s0 + d < S) w[d >> 2] |= (uint32_t)__ldg(p + d) << (8 * (d & 3));
+      return make_uint2(w[0], w[1]);
+    };
+    const uint2 first = whole ? __ldg(reinterpret_cast<const uint2 *>(col)) : load_slow(0);
+    uint32_t c8[4][2] = {}, c16[4][2][2] = {}, differs[2] = {0, 0};
+    int pending = 0;  // rows accumulated in the byte lanes
+    auto fold = [&]() {
+#pragma unroll
+      for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { c16[k][wi][0] += c8[k][wi] & L16; c16[k][wi][1] += (c8[k][wi] >> 8) & L16; c8[k][wi] = 0; }
+      pending = 0;
+    };
+    auto rows = [&](auto NRc, auto WHOLEc, int t0) {
+      constexpr int NR = decltype(NRc)::value;
+      constexpr bool WHOLE = decltype(WHOLEc)::value;
+      uint2 w[NR];
+      const uint8_t *p = col + (int64_t)t0 * pitch;
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        w[u] = WHOLE ? __ldg(reinterpret_cast<const uint2 *>(p)) : load_slow(t0 + u);
+        p += pitch;
+      }
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        const uint32_t x[2] = {w[u].x, w[u].y};
+        const uint32_t f[2] = {first.x, first.y};
+#pragma unroll
+        for (int wi = 0; wi < 2; ++wi) {
+          const uint32_t s1 = x[wi] >> 1;
+          c8[3][wi] += x[wi] & s1 & M;
+          c8[2][wi] += s1 & ~x[wi] & M;
+          c8[1][wi] += x[wi] & ~s1 & M;
+          c8[0][wi] += ~(x[wi] | s1) & M;
+          differs[wi] |= x[wi] ^ f[wi];
+          hi |= x[wi];
+        }
+      }
+      pending += NR;
+      if (pending > 239) fold();
+    };
+    int t0 = 0;
+    if (whole)
+      for (; t0 + UNROLL <= T; t0 += UNROLL) rows(std::integral_constant<int, UNROLL>{}, std::true_type{}, t0);
+    else
+      for (; t0 + UNROLL <= T; t0 += UNROLL) rows(std::integral_constant<int, UNROLL>{}, std::false_type{}, t0);
+    for (; t0 < T; ++t0) rows(std::integral_constant<int, 1>{}, std::false_type{}, t0);
+    fold();
+    double dist_k[K] = {0, 0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < D4_SPT; ++d) {
+      if (s0 + d >= S) continue;
+      const int wi = d >> 2, b = d & 3, sh = 16 * (b >> 1), hl = b & 1;
+      unsigned cnt[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) cnt[k] = (c16[k][wi][hl] >> sh) & 0xffffu;
+      unsigned sum = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) sum += cnt[k];
+      double e = 0.0, h = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double f = sum ? (double)cnt[k] / (double)sum : 0.0;  // as in k_examine_columns
+        if (!(EX_EPS > f)) e -= f * log(f);
+        h += f * f;
+      }
+      const double keff_e = e < EX_EPS ? 1.0 : exp(e);
+      n_const += ((differs[wi] >> (8 * b)) & 0xffu) == 0;  // without gaps: constant <=> soft-constant
+      n_std += sum;
+      ke_all += keff_e;
+      kh_all += 1.0 / h;                                   // sum = T >= 1: h > 0
+      if (keff_site) keff_site[s0 + d] = keff_e;
+      const double inv = 1.0 / (double)sum;
+#pragma unroll
+      for (int k = 0; k < K; ++k) dist_k[k] += (double)cnt[k] * inv;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double v = warp_sum(dist_k[k]);
+      if ((tid & 31) == 0 && v != 0.0) atomicAdd(&acc->dist[k], v);
+    }
+  }
+  if (hi & 0xfcfcfcfcu) atomicExch(fallback, 1);
+  ke_all = warp_sum(ke_all); kh_all = warp_sum(kh_all);
+  n_const = warp_sum_u(n_const);
+  atomicAdd(&acc->n_std, n_std);
+  if ((tid & 31) == 0) {
+    atomicAdd(&acc->n_constant, (unsigned long long)n_const);
+    atomicAdd(&acc->n_constant_soft, (unsigned long long)n_const);
+    atomicAdd(&acc->keff_e_all, ke_all);
+    atomicAdd(&acc->keff_e_nogap, ke_all);
+    atomicAdd(&acc->keff_h_all, kh_all);
+    atomicAdd(&acc->keff_h_nogap, kh_all);
+  }
+}
+
 // eq[i][j] += number of sites where sequences i and j carry the same character (any code, gaps included: Distance.hs:24-33
 // compares characters).  Tile = 32 x 32 pairs; grid = (tile pairs, site slices); thread (r, c) owns pairs (r + 8 m, c).
 constexpr int HM_TILE = 32, HM_CHUNK = 512, HM_STRIDE = HM_CHUNK + 4;  // padded rows: word stride 129 = 1 mod 32
@@ -368,8 +491,28 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     const unsigned grid = (unsigned)(nb < (int64_t)sms * per_sm ? nb : (int64_t)sms * per_sm);
-    k_examine_columns<<<grid, EX_THREADS, smem, stream>>>(d_states, pitch, T, S, K, d_acc, d_keff_entropy_per_site);
-    EX_CUDA(cudaGetLastError());
+    bool generic = true;
+    if (K == 4 && T <= 65535) {
+      // gap-free DNA: the register-only kernel; a gap or an invalid code makes it raise a flag instead of a result
+      int *d_flag = reinterpret_cast<int *>(&d_acc->n_bad);  // scratch: cleared again before the generic kernel runs
+      const int64_t nb4 = (S + D4_BLOCK_SITES - 1) / D4_BLOCK_SITES;
+      const unsigned grid4 = (unsigned)(nb4 < (int64_t)sms * 2 ? nb4 : (int64_t)sms * 2);
+      k_examine_columns_k4<<<grid4, EX_THREADS, 0, stream>>>(d_states, pitch, T, S, d_acc, d_keff_entropy_per_site, d_flag);
+      EX_CUDA(cudaGetLastError());
+      ExamineAcc probe4;
+      EX_CUDA(cudaMemcpyAsync(&probe4, d_acc, sizeof probe4, cudaMemcpyDeviceToHost, stream));
+      EX_CUDA(cudaStreamSynchronize(stream));
+      generic = probe4.n_bad != 0;
+      if (generic) EX_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(ExamineAcc), stream));
+      else {
+        const unsigned long long ns = (unsigned long long)S;
+        EX_CUDA(cudaMemcpyAsync(&d_acc->n_no_gaps, &ns, sizeof ns, cudaMemcpyHostToDevice, stream));  // every column is gap-free
+      }
+    }
+    if (generic) {
+      k_examine_columns<<<grid, EX_THREADS, smem, stream>>>(d_states, pitch, T, S, K, d_acc, d_keff_entropy_per_site);
+      EX_CUDA(cudaGetLastError());
+    }
   }
   std::vector<unsigned long long> eq;
   unsigned long long *d_eq = reinterpret_cast<unsigned long long *>(d_equal_counts), *d_eq_own = nullptr;
