@@ -324,6 +324,34 @@ def test_quad_tables_of_the_benchmark_configuration_are_exact():
         assert frontier.max() == 4 and frontier.sum() >= 1000  # leaves + kept internal nodes
 
 
+def test_quad_and_pair_mode_agree_statistically():
+    """Two exact samplers of the same leaf distribution (quad mode sums internal nodes out, pair mode draws every node):
+    two-sample chi-square on the joint states of random leaf pairs and triples of a 150-taxon tree."""
+    from scipy import stats
+
+    from elynx_b200 import model as pm
+
+    tree = pm.birth_death_tree(150, 1.0, 0.5, seed=21)
+    model = pm.get_phylo_model("GTR4[1,2,3,4,5,6]{0.2,0.3,0.4,0.1}", gamma=(4, 0.5))
+    s = 1_500_000
+    with eb.Simulator(model.weights, model.pi, model.exch, tree, is_mixture=True) as sim:
+        assert sim.quad_groups > 0
+        q = sim.simulate(5, s)[0]
+    with eb.Simulator(model.weights, model.pi, model.exch, tree, is_mixture=True, pair_draws=True) as sim:
+        assert sim.quad_groups == 0
+        p = sim.simulate(6, s)[0]
+    rng = np.random.default_rng(0)
+    pvals = []
+    for _ in range(40):
+        rows = rng.choice(150, size=3, replace=False)
+        hq = np.bincount((q[rows[0]].astype(np.int64) * 4 + q[rows[1]]) * 4 + q[rows[2]], minlength=64)
+        hp = np.bincount((p[rows[0]].astype(np.int64) * 4 + p[rows[1]]) * 4 + p[rows[2]], minlength=64)
+        keep = (hq + hp) >= 10
+        pvals.append(stats.chi2_contingency(np.stack([hq[keep], hp[keep]]))[1])
+    pvals = np.array(pvals)
+    assert pvals.min() > 1e-5 and (pvals < 0.01).sum() <= 3, pvals
+
+
 def test_freerun_partition_invariance():
     """Output is a pure function of (seed, global site, node): any split of the site range gives the same bytes."""
     model = model_case("hky_g4")
