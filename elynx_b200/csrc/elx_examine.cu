@@ -53,8 +53,19 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
   return v;
 }
 
+// tab[c] = log c and tab[T + 1 + c] = c log c (0 for c = 0), c = 0..T: the entropy of a column with counts c_k (sum s) is
+// log s - (sum_k c_k log c_k) / s, so the per-site epilogue costs K table look-ups instead of K logarithms (xLogX's
+// "0 below 1e-12" rule, DistributionDiversity.hs:41-45, can only fire for c_k = 0: frequencies are >= 1 / T).
+__global__ void k_examine_tables(int T, double *__restrict__ tab) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > T) return;
+  const double l = c ? log((double)c) : 0.0;
+  tab[c] = l;
+  tab[T + 1 + c] = (double)c * l;
+}
+
 __global__ void __launch_bounds__(EX_THREADS, 4) k_examine_columns(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S, int K,
-                                                                 ExamineAcc *__restrict__ acc, double *__restrict__ keff_site) {
+                                                                 ExamineAcc *__restrict__ acc, double *__restrict__ keff_site, const double *__restrict__ tab) {
   extern __shared__ uint32_t cnt[];  // [(K + 3)][EX_SPT][EX_THREADS]: K characters, two gap codes, one row for invalid codes
   const int tid = threadIdx.x, R = K + 2;
   const bool aligned = ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 3) == 0);
@@ -132,13 +143,17 @@ __global__ void __launch_bounds__(EX_THREADS, 4) k_examine_columns(const uint8_t
         kinds += c ? 1u : 0u;
       }
       const unsigned gaps = cnt[(K * EX_SPT + d) * EX_THREADS + tid] + cnt[((K + 1) * EX_SPT + d) * EX_THREADS + tid];
-      double e = 0.0, h = 0.0;
+      // entropy (DistributionDiversity.hs:41-57) = log s - (sum c log c) / s and homoplasy (:67-68) = (sum c^2) / s^2 of the
+      // frequencies c / s (saveDivision, :92-94: all zero when the column has no standard character)
+      double clc = 0.0;
+      unsigned long long c2 = 0;
       for (int k = 0; k < K; ++k) {
         const unsigned c = cnt[(k * EX_SPT + d) * EX_THREADS + tid];
-        const double f = sum ? (double)c / (double)sum : 0.0;  // saveDivision (DistributionDiversity.hs:92-94)
-        if (!(EX_EPS > f)) e -= f * log(f);                     // xLogX (:41-45), entropy (:48-57)
-        h += f * f;                                             // homoplasy (:67-68)
+        clc += __ldg(tab + T + 1 + c);
+        c2 += (unsigned long long)c * c;
       }
+      const double e = sum ? __ldg(tab + sum) - clc / (double)sum : 0.0;
+      const double h = sum ? (double)c2 / ((double)sum * (double)sum) : 0.0;
       const double keff_e = e < EX_EPS ? 1.0 : exp(e);          // kEffEntropy (:61-62)
       if (live) {
         const bool nogap = gaps == 0;
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(EX_THREADS, 4) k_examine_columns(const uint8_t
 constexpr int D4_SPT = 8, D4_BLOCK_SITES = EX_THREADS * D4_SPT;
 __global__ void __launch_bounds__(EX_THREADS, 2) k_examine_columns_k4(const uint8_t *__restrict__ a, int64_t pitch, int T, int64_t S,
                                                                     ExamineAcc *__restrict__ acc, double *__restrict__ keff_site,
-                                                                    int *__restrict__ fallback) {
+                                                                    int *__restrict__ fallback, const double *__restrict__ tab) {
   constexpr int K = 4, UNROLL = 16;
   constexpr uint32_t M = 0x01010101u, L16 = 0x00ff00ffu;
   const int tid = threadIdx.x;
@@ -265,13 +280,15 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_examine_columns_k4(const uint
       unsigned sum = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) sum += cnt[k];
-      double e = 0.0, h = 0.0;
+      double clc = 0.0;  // as in k_examine_columns
+      unsigned long long c2 = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const double f = sum ? (double)cnt[k] / (double)sum : 0.0;  // as in k_examine_columns
-        if (!(EX_EPS > f)) e -= f * log(f);
-        h += f * f;
+        clc += __ldg(tab + T + 1 + cnt[k]);
+        c2 += (unsigned long long)cnt[k] * cnt[k];
       }
+      const double e = __ldg(tab + sum) - clc / (double)sum;
+      const double h = (double)c2 / ((double)sum * (double)sum);
       const double keff_e = e < EX_EPS ? 1.0 : exp(e);
       n_const += ((differs[wi] >> (8 * b)) & 0xffu) == 0;  // without gaps: constant <=> soft-constant
       n_std += sum;
@@ -472,9 +489,10 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
 #define EX_CUDA(expr)                                                                                              \
   do {                                                                                                             \
     cudaError_t _e = (expr);                                                                                       \
-    if (_e != cudaSuccess) { cudaFree(d_acc); return fail(nullptr, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } \
+    if (_e != cudaSuccess) { cudaFree(d_acc); cudaFree(d_tab); return fail(nullptr, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } \
   } while (0)
   ExamineAcc *d_acc = nullptr;
+  double *d_tab = nullptr;  // log c, c log c (k_examine_tables)
   EX_CUDA(cudaMalloc((void **)&d_acc, sizeof(ExamineAcc)));
   EX_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(ExamineAcc), stream));
   int dev = 0, sms = 148;
@@ -484,6 +502,8 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
   ExamineAcc h;
   memset(&h, 0, sizeof h);
   if (S > 0) {
+    EX_CUDA(cudaMalloc((void **)&d_tab, sizeof(double) * 2 * ((size_t)T + 1)));
+    k_examine_tables<<<(unsigned)((T + 256) / 256), 256, 0, stream>>>(T, d_tab);
     const size_t smem = (size_t)(K + 3) * EX_SPT * EX_THREADS * sizeof(uint32_t);
     EX_CUDA(cudaFuncSetAttribute(k_examine_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nb = (S + EX_BLOCK_SITES - 1) / EX_BLOCK_SITES;
@@ -497,7 +517,7 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
       int *d_flag = reinterpret_cast<int *>(&d_acc->n_bad);  // scratch: cleared again before the generic kernel runs
       const int64_t nb4 = (S + D4_BLOCK_SITES - 1) / D4_BLOCK_SITES;
       const unsigned grid4 = (unsigned)(nb4 < (int64_t)sms * 2 ? nb4 : (int64_t)sms * 2);
-      k_examine_columns_k4<<<grid4, EX_THREADS, 0, stream>>>(d_states, pitch, T, S, d_acc, d_keff_entropy_per_site, d_flag);
+      k_examine_columns_k4<<<grid4, EX_THREADS, 0, stream>>>(d_states, pitch, T, S, d_acc, d_keff_entropy_per_site, d_flag, d_tab);
       EX_CUDA(cudaGetLastError());
       ExamineAcc probe4;
       EX_CUDA(cudaMemcpyAsync(&probe4, d_acc, sizeof probe4, cudaMemcpyDeviceToHost, stream));
@@ -510,7 +530,7 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
       }
     }
     if (generic) {
-      k_examine_columns<<<grid, EX_THREADS, smem, stream>>>(d_states, pitch, T, S, K, d_acc, d_keff_entropy_per_site);
+      k_examine_columns<<<grid, EX_THREADS, smem, stream>>>(d_states, pitch, T, S, K, d_acc, d_keff_entropy_per_site, d_tab);
       EX_CUDA(cudaGetLastError());
     }
   }
@@ -566,23 +586,24 @@ int elx_examine_device(const uint8_t *d_states, int64_t pitch, int32_t n_sequenc
     }
     eq.resize((size_t)T * T);
     if (e == cudaSuccess) e = cudaMemcpyAsync(eq.data(), d_eq, sizeof(unsigned long long) * (size_t)T * T, cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) { cudaFree(d_eq_own); cudaFree(d_acc); return fail(nullptr, ELX_E_CUDA, std::string("elx_examine (hamming): ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaFree(d_eq_own); cudaFree(d_acc); cudaFree(d_tab); return fail(nullptr, ELX_E_CUDA, std::string("elx_examine (hamming): ") + cudaGetErrorString(e)); }
   }
   if (d_divergence && T >= 2) {
     const int64_t pairs = (int64_t)T * (T - 1) / 2;
-    if (pairs > 0x7fffffff) { cudaFree(d_eq_own); cudaFree(d_acc); return fail(nullptr, ELX_E_UNSUPPORTED, "elx_examine: too many sequence pairs for divergence matrices"); }
+    if (pairs > 0x7fffffff) { cudaFree(d_eq_own); cudaFree(d_acc); cudaFree(d_tab); return fail(nullptr, ELX_E_UNSUPPORTED, "elx_examine: too many sequence pairs for divergence matrices"); }
     cudaError_t e = cudaMemsetAsync(d_divergence, 0, sizeof(int64_t) * (size_t)pairs * K * K, stream);
     if (e == cudaSuccess && S > 0) {
       k_examine_divergence<<<(unsigned)pairs, 256, sizeof(unsigned) * K * K, stream>>>(d_states, pitch, T, S, K,
                                                                                          reinterpret_cast<unsigned long long *>(d_divergence));
       e = cudaGetLastError();
     }
-    if (e != cudaSuccess) { cudaFree(d_eq_own); cudaFree(d_acc); return fail(nullptr, ELX_E_CUDA, std::string("elx_examine (divergence): ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaFree(d_eq_own); cudaFree(d_acc); cudaFree(d_tab); return fail(nullptr, ELX_E_CUDA, std::string("elx_examine (divergence): ") + cudaGetErrorString(e)); }
   }
   cudaError_t e = cudaMemcpyAsync(&h, d_acc, sizeof h, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   cudaFree(d_eq_own);
   cudaFree(d_acc);
+  cudaFree(d_tab);
   if (e != cudaSuccess) return fail(nullptr, ELX_E_CUDA, std::string("elx_examine: ") + cudaGetErrorString(e));
 #undef EX_CUDA
   if (h.n_bad) return fail(nullptr, ELX_E_INVALID, "elx_examine: the matrix holds codes above n_states + 1");
