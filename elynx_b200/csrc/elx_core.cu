@@ -401,12 +401,28 @@ __global__ void k2_freerun_generic(SimArgs a) {
 // K3: FASTA packer.  states -> alphabet characters, written into the whole-file image.
 // Algorithmic bytes: 2 per cell (1 read + 1 written).
 // ---------------------------------------------------------------------------------------------
+// Four state bytes -> four characters.  With at most 8 characters the alphabet sits in two registers and ONE byte permute
+// is the look-up (its selector = the four states packed into nibbles: three logic/shift pairs); bigger alphabets go
+// through the shared-memory table byte by byte.
+__device__ __forceinline__ uint32_t k3_map4(uint32_t v, bool small, uint32_t lut_lo, uint32_t lut_hi, const uint8_t *slut) {
+  if (small) {
+    const uint32_t x = v & 0x07070707u;
+    const uint32_t y = x | (x >> 4);                            // byte 0: s0 | s1 << 4, byte 2: s2 | s3 << 4
+    const uint32_t sel = (y & 0xffu) | ((y >> 8) & 0xff00u);  // nibbles s0, s1, s2, s3
+    return __byte_perm(lut_lo, lut_hi, sel);
+  }
+  return (uint32_t)slut[v & 63] | ((uint32_t)slut[(v >> 8) & 63] << 8) | ((uint32_t)slut[(v >> 16) & 63] << 16) |
+         ((uint32_t)slut[(v >> 24) & 63] << 24);
+}
+
 __global__ void k3_fasta_body(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t site0, int64_t nsites,
                               const int64_t *__restrict__ seq_off, const uint8_t *__restrict__ lut, int K,
                               uint8_t *__restrict__ out) {
-  __shared__ uint8_t slut[64];
+  __shared__ __align__(8) uint8_t slut[64];
   if (threadIdx.x < 64) slut[threadIdx.x] = threadIdx.x < K ? lut[threadIdx.x] : (uint8_t)'?';
   __syncthreads();
+  const bool small = K <= 8;
+  const uint32_t lut_lo = reinterpret_cast<const uint32_t *>(slut)[0], lut_hi = reinterpret_cast<const uint32_t *>(slut)[1];
   int t = blockIdx.y;
   const uint8_t *src = leaves + (int64_t)t * pitch;
   uint8_t *dst = out + seq_off[t] + site0;
@@ -417,16 +433,24 @@ __global__ void k3_fasta_body(const uint8_t *__restrict__ leaves, int64_t pitch,
   int64_t hi = chunk == 0 ? mis : lo + 16;
   if (hi > nsites) hi = nsites;
   if (lo >= hi) return;
-  if (hi - lo == 16) {
-    uint32_t wv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t v = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) v |= (uint32_t)slut[src[lo + q * 4 + b] & 63] << (8 * b);
-      wv[q] = v;
+  // the source window [lo, lo + 16) is misaligned by m bytes -- the same m for every chunk of the row: two aligned
+  // 128-bit loads and four funnel shifts instead of sixteen byte loads
+  const int m = (int)(reinterpret_cast<uintptr_t>(src + lo) & 15);
+  if (hi - lo == 16 && lo - m >= 0 && lo - m + 32 <= pitch) {
+    const uint4 A = __ldg(reinterpret_cast<const uint4 *>(src + lo - m));
+    const uint4 B = m ? __ldg(reinterpret_cast<const uint4 *>(src + lo - m + 16)) : A;
+    const uint32_t sh = 8u * (uint32_t)(m & 3);
+    uint32_t in[4];
+    switch (m >> 2) {  // uniform over the CTA
+      case 0: in[0] = __funnelshift_r(A.x, A.y, sh); in[1] = __funnelshift_r(A.y, A.z, sh); in[2] = __funnelshift_r(A.z, A.w, sh); in[3] = __funnelshift_r(A.w, B.x, sh); break;
+      case 1: in[0] = __funnelshift_r(A.y, A.z, sh); in[1] = __funnelshift_r(A.z, A.w, sh); in[2] = __funnelshift_r(A.w, B.x, sh); in[3] = __funnelshift_r(B.x, B.y, sh); break;
+      case 2: in[0] = __funnelshift_r(A.z, A.w, sh); in[1] = __funnelshift_r(A.w, B.x, sh); in[2] = __funnelshift_r(B.x, B.y, sh); in[3] = __funnelshift_r(B.y, B.z, sh); break;
+      default: in[0] = __funnelshift_r(A.w, B.x, sh); in[1] = __funnelshift_r(B.x, B.y, sh); in[2] = __funnelshift_r(B.y, B.z, sh); in[3] = __funnelshift_r(B.z, B.w, sh); break;
     }
-    *reinterpret_cast<uint4 *>(dst + lo) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    uint4 o;
+    o.x = k3_map4(in[0], small, lut_lo, lut_hi, slut); o.y = k3_map4(in[1], small, lut_lo, lut_hi, slut);
+    o.z = k3_map4(in[2], small, lut_lo, lut_hi, slut); o.w = k3_map4(in[3], small, lut_lo, lut_hi, slut);
+    __stcs(reinterpret_cast<uint4 *>(dst + lo), o);
   } else {
     for (int64_t i = lo; i < hi; ++i) dst[i] = slut[src[i] & 63];
   }
@@ -435,9 +459,11 @@ __global__ void k3_fasta_body(const uint8_t *__restrict__ leaves, int64_t pitch,
 // slice mode: [T][out_pitch] characters, no frame
 __global__ void k3_fasta_slice(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, const uint8_t *__restrict__ lut,
                                int K, uint8_t *__restrict__ out, int64_t out_pitch) {
-  __shared__ uint8_t slut[64];
+  __shared__ __align__(8) uint8_t slut[64];
   if (threadIdx.x < 64) slut[threadIdx.x] = threadIdx.x < K ? lut[threadIdx.x] : (uint8_t)'?';
   __syncthreads();
+  const bool small = K <= 8;
+  const uint32_t lut_lo = reinterpret_cast<const uint32_t *>(slut)[0], lut_hi = reinterpret_cast<const uint32_t *>(slut)[1];
   int t = blockIdx.y;
   const uint8_t *src = leaves + (int64_t)t * pitch;
   uint8_t *dst = out + (int64_t)t * out_pitch;
@@ -445,14 +471,11 @@ __global__ void k3_fasta_slice(const uint8_t *__restrict__ leaves, int64_t pitch
   if (hi > nsites) hi = nsites;
   if (lo >= hi) return;
   if (hi - lo == 16 && ((reinterpret_cast<uintptr_t>(dst + lo) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src + lo) & 15) == 0)) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(src + lo);
-    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-    uint32_t wv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      wv[q] = (uint32_t)slut[in[q] & 63] | ((uint32_t)slut[(in[q] >> 8) & 63] << 8) | ((uint32_t)slut[(in[q] >> 16) & 63] << 16) |
-              ((uint32_t)slut[(in[q] >> 24) & 63] << 24);
-    *reinterpret_cast<uint4 *>(dst + lo) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + lo));
+    uint4 o;
+    o.x = k3_map4(v.x, small, lut_lo, lut_hi, slut); o.y = k3_map4(v.y, small, lut_lo, lut_hi, slut);
+    o.z = k3_map4(v.z, small, lut_lo, lut_hi, slut); o.w = k3_map4(v.w, small, lut_lo, lut_hi, slut);
+    *reinterpret_cast<uint4 *>(dst + lo) = o;
   } else {
     for (int64_t i = lo; i < hi; ++i) dst[i] = slut[src[i] & 63];
   }
