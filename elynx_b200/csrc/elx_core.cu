@@ -499,17 +499,43 @@ __global__ void k3_fasta_frame(int T, const int64_t *__restrict__ seq_off, const
 // ---------------------------------------------------------------------------------------------
 // Validation histograms (accumulated into caller buffers; summed across GPUs with one NCCL all-reduce).
 // ---------------------------------------------------------------------------------------------
+// Per-taxon state counts.  Every thread owns one counter per state in shared memory ([state][thread]: conflict-free,
+// bumped with fire-and-forget reductions) and reads 16 sites per 128-bit load; states >= K land in an overflow row that
+// is never reported.  1 algorithmic byte read per cell.
 __global__ void k_state_counts(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, int K,
                                unsigned long long *__restrict__ counts) {
-  __shared__ unsigned int h[64];
-  if (threadIdx.x < 64) h[threadIdx.x] = 0;
-  __syncthreads();
-  int t = blockIdx.y;
+  extern __shared__ uint32_t hc[];  // [K + 1][blockDim.x]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 0; k <= K; ++k) hc[k * nt + tid] = 0;
+  const int t = blockIdx.y;
   const uint8_t *src = leaves + (int64_t)t * pitch;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsites; i += (int64_t)gridDim.x * blockDim.x)
-    atomicAdd(&h[src[i] & 63], 1u);
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(hc) + (uint32_t)tid * 4u, stride = (uint32_t)nt * 4u;
+  auto bump = [&](uint32_t code) {
+    code = min(code, (uint32_t)K);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + code * stride) : "memory");
+  };
+  for (int64_t i = ((int64_t)blockIdx.x * nt + tid) * 16; i < nsites; i += (int64_t)gridDim.x * nt * 16) {
+    if (aligned && i + 16 <= nsites) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + i));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        bump(w[q] & 0xffu); bump((w[q] >> 8) & 0xffu); bump((w[q] >> 16) & 0xffu); bump(w[q] >> 24);
+      }
+    } else {
+      for (int64_t j = i; j < nsites && j < i + 16; ++j) bump(src[j]);
+    }
+  }
   __syncthreads();
-  if (threadIdx.x < K && h[threadIdx.x]) atomicAdd(&counts[(int64_t)t * K + threadIdx.x], (unsigned long long)h[threadIdx.x]);
+  // one warp per state: sum the threads' counters
+  for (int k = tid >> 5; k < K; k += nt >> 5) {
+    unsigned long long sum = 0;
+    for (int j = tid & 31; j < nt; j += 32) sum += hc[k * nt + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((tid & 31) == 0 && sum) atomicAdd(&counts[(int64_t)t * K + k], sum);
+  }
 }
 
 __global__ void k_pattern_counts(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, int T, int K,
@@ -1145,10 +1171,12 @@ int elx_histogram_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves_
   if (nsites == 0) return 0;
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (d_state_counts) {
-    int64_t bx = (nsites + 256 * 64 - 1) / (256 * 64);
+    int64_t bx = (nsites + 256 * 128 - 1) / (256 * 128);
     if (bx > 1024) bx = 1024;
     dim3 grid((unsigned)bx, (unsigned)h->T);
-    k_state_counts<<<grid, 256, 0, h->stream>>>(d_leaves, leaves_pitch, nsites, h->K, (unsigned long long *)d_state_counts);
+    const size_t smem = sizeof(uint32_t) * 256 * (size_t)(h->K + 1);
+    if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_state_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_state_counts<<<grid, 256, smem, h->stream>>>(d_leaves, leaves_pitch, nsites, h->K, (unsigned long long *)d_state_counts);
     h->launches++;
   }
   if (d_pattern_counts) {
