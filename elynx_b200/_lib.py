@@ -94,6 +94,8 @@ SIGNATURES = {
     "elx_examine_device": (C.c_int, [_VP, _I64, _I32, _I64, _I32, C.POINTER(elx_examine_result), _VP, _VP, _VP, _VP]),
     "elx_examine": (C.c_int, [_VP, _I64, _I32, _I64, _I32, C.POINTER(elx_examine_result), _VP, _VP, _VP]),
     "elx_launch_count": (_I64, [_VP]),
+    "elx_d2h_bytes": (_I64, [_VP]),
+    "elx_unpack2_rows": (_I32, [_VP, _I64, _VP, _I64, _I64, _I64, C.c_char_p, C.c_int32]),
 }
 
 _lib = None

@@ -6,11 +6,16 @@
 //   jump = categorical (p ! i) elynx-markov/src/ELynx/Simulate/MarkovProcess.hs:48-49
 //   walk / draw order          elynx-markov/src/ELynx/Simulate/MarkovProcessAlongTree.hs:57-63,88-98,163-173,195-208
 //   FASTA layout               elynx-seq/src/ELynx/Sequence/Export/Fasta.hs:24-36
+#include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -830,6 +835,7 @@ int32_t elx_n_components(const elx_handle *h) { return h ? h->C : 0; }
 int32_t elx_alias_columns(const elx_handle *h) { return h ? h->KP : 0; }
 void *elx_stream(const elx_handle *h) { return h ? (void *)h->stream : nullptr; }
 int64_t elx_launch_count(const elx_handle *h) { return h ? h->launches : 0; }
+int64_t elx_d2h_bytes(const elx_handle *h) { return h ? h->d2h_bytes : 0; }
 
 int elx_ptables_get(elx_handle *h, double *out, int cumulative) {
   if (!h || !out) return fail(h, ELX_E_INVALID, "elx_ptables_get: NULL argument");
@@ -937,12 +943,254 @@ int elx_simulate_injected_device(elx_handle *h, const double *d_U, int64_t u_pit
   return 0;
 }
 
+// ---- 2-bit transport for the host-buffer calls (K <= 4) ---------------------------------------------------------
+// The host-buffer result path is PCIe-bound (1 byte per cell).  States of a <= 4-letter alphabet need 2 bits: the batch is
+// packed on the device (k_pack2), crosses PCIe at a quarter of the size into pinned staging buffers owned by the library,
+// and host threads expand it into the caller's buffer (elx_io.cpp:unpack2_rows) while the next chunks are in flight.
+__global__ void k_pack2(const uint8_t *__restrict__ src, int64_t spitch, uint8_t *__restrict__ dst, int64_t dpitch, int64_t n16,
+                        int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / n16, g = idx - r * n16;
+    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + r * spitch + g * 16));
+    auto p = [](uint32_t w) { w &= 0x03030303u; return (w | (w >> 6) | (w >> 12) | (w >> 18)) & 0xffu; };
+    *reinterpret_cast<uint32_t *>(dst + r * dpitch + g * 4) = p(v.x) | (p(v.y) << 8) | (p(v.z) << 16) | (p(v.w) << 24);
+  }
+}
+
+namespace {
+constexpr int PIN_STAGES = 4;
+constexpr size_t PIN_STAGE_BYTES = (size_t)32 << 20;
+std::mutex g_pin_mu;
+std::vector<uint8_t *> g_pin_free;  // staging sets of PIN_STAGES x PIN_STAGE_BYTES, kept across handles (pinning is slow)
+
+uint8_t *pin_acquire() {
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_free.empty()) {
+      uint8_t *p = g_pin_free.back();
+      g_pin_free.pop_back();
+      return p;
+    }
+  }
+  uint8_t *p = nullptr;
+  if (cudaHostAlloc((void **)&p, PIN_STAGES * PIN_STAGE_BYTES, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void pin_release(uint8_t *p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_free.size() < 2) {
+      g_pin_free.push_back(p);
+      return;
+    }
+  }
+  cudaFreeHost(p);
+}
+
+struct PackedChunk {
+  int stage = 0;
+  const uint8_t *src = nullptr;  // pinned staging rows
+  uint8_t *dst = nullptr;        // caller's buffer + first site of the batch; row r of the chunk starts at dst + row_off[r]
+  const int64_t *row_off = nullptr;
+  const uint8_t *lut4 = nullptr;
+  int64_t rows = 0, ppitch = 0, nb = 0, ncol = 0, units = 0;
+  std::atomic<int> ready{0};  // set by a host callback on the copy stream once the chunk sits in its staging buffer
+  std::atomic<int64_t> next{0}, done{0};
+};
+struct TransportSync {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<int> abort_flag{0};
+};
+struct ChunkReady { TransportSync *sync; PackedChunk *chunk; };
+void CUDART_CB chunk_ready_cb(void *p) {
+  ChunkReady *r = static_cast<ChunkReady *>(p);
+  {
+    std::lock_guard<std::mutex> lk(r->sync->mu);
+    r->chunk->ready.store(1, std::memory_order_release);
+  }
+  r->sync->cv.notify_all();
+}
+constexpr int64_t UNPACK_COLS = 65536;  // sites per work unit of the unpack threads
+}  // namespace
+
+// leaves / internal: base pointers; row r of a matrix starts at base + off[r].  lut4: nullptr = state codes, else the
+// alphabet (FASTA sequence lines).
+static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves,
+                                const int64_t *leaves_off, int32_t *comps, uint8_t *internal, const int64_t *internal_off,
+                                const uint8_t *lut4) {
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int64_t BATCH = 1 << 20;
+  const int NB = 2;
+  const int64_t nbatch = (nsites + BATCH - 1) / BATCH;
+  const int64_t bmax = nsites < BATCH ? nsites : BATCH;
+  const int64_t bpitch = (bmax + 15) & ~(int64_t)15, ppitch = bpitch / 4;  // ppitch: of a full batch; a ragged last batch packs tighter
+  const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)PIN_STAGE_BYTES / ppitch);
+  const int nbuf = nbatch > 1 ? NB : 1;
+  uint8_t *d_leaves[NB] = {nullptr, nullptr}, *d_internal[NB] = {nullptr, nullptr}, *d_pl[NB] = {nullptr, nullptr},
+          *d_pi[NB] = {nullptr, nullptr};
+  int32_t *d_comps[NB] = {nullptr, nullptr};
+  cudaEvent_t sim_done[NB] = {nullptr, nullptr}, copy_done[NB] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  uint8_t *pin = nullptr;
+  TransportSync sync;
+  std::vector<std::thread> workers;
+  // every chunk of the call is known up front: (batch, matrix, row range)
+  struct Plan { int64_t batch; int which; int64_t r0, r1; };
+  std::vector<Plan> plan;
+  for (int64_t b = 0; b < nbatch; ++b)
+    for (int which = 0; which < (internal ? 2 : 1); ++which) {
+      const int64_t R = which ? h->N : h->T;
+      for (int64_t r0 = 0; r0 < R; r0 += rows_per_chunk) plan.push_back({b, which, r0, std::min(R, r0 + rows_per_chunk)});
+    }
+  std::vector<PackedChunk> chunks(plan.size());
+  std::vector<ChunkReady> ready_args(plan.size());
+  auto cleanup = [&]() {
+    {
+      std::lock_guard<std::mutex> lk(sync.mu);
+      sync.abort_flag.store(1);
+    }
+    sync.cv.notify_all();
+    for (auto &t : workers) t.join();
+    workers.clear();
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < NB; ++i) {
+      cudaFree(d_leaves[i]); cudaFree(d_internal[i]); cudaFree(d_comps[i]); cudaFree(d_pl[i]); cudaFree(d_pi[i]);
+      if (sim_done[i]) cudaEventDestroy(sim_done[i]);
+      if (copy_done[i]) cudaEventDestroy(copy_done[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    pin_release(pin);
+  };
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  pin = pin_acquire();
+  if (!pin) { cleanup(); return fail(h, ELX_E_CUDA, "cannot allocate the pinned staging buffers"); }
+  CT(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < nbuf; ++i) {
+    CT(cudaMalloc((void **)&d_leaves[i], (size_t)h->T * bpitch));
+    CT(cudaMalloc((void **)&d_pl[i], (size_t)h->T * ppitch));
+    if (internal) {
+      CT(cudaMalloc((void **)&d_internal[i], (size_t)h->N * bpitch));
+      CT(cudaMalloc((void **)&d_pi[i], (size_t)h->N * ppitch));
+    }
+    if (comps) CT(cudaMalloc((void **)&d_comps[i], sizeof(int32_t) * (size_t)bpitch));
+    CT(cudaEventCreateWithFlags(&sim_done[i], cudaEventDisableTiming));
+    CT(cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming));
+  }
+
+  // all cores but two (this thread feeds the streams, the driver runs the callbacks); waits are blocking: spinning
+  // workers were measured to starve the dispatcher (16 spinning threads on 16 cores: 160 ms for cfg2, 8: 122 ms)
+  int nt = (int)std::thread::hardware_concurrency() - 2;
+  if (const char *e = getenv("ELX_HOST_THREADS")) nt = atoi(e);
+  nt = std::max(1, std::min(nt, 32));
+  for (int w = 0; w < nt; ++w)
+    workers.emplace_back([&chunks, &sync]() {
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        PackedChunk &ch = chunks[c];
+        if (!ch.ready.load(std::memory_order_acquire)) {
+          std::unique_lock<std::mutex> lk(sync.mu);
+          sync.cv.wait(lk, [&]() { return ch.ready.load(std::memory_order_acquire) || sync.abort_flag.load(); });
+        }
+        if (sync.abort_flag.load()) return;
+        for (;;) {
+          const int64_t u = ch.next.fetch_add(1, std::memory_order_relaxed);
+          if (u >= ch.units) break;
+          const int64_t r = u / ch.ncol, k = u - r * ch.ncol;
+          const int64_t c0 = k * UNPACK_COLS, c1 = std::min(ch.nb, c0 + UNPACK_COLS);
+          elx::unpack2_rows(ch.src + r * ch.ppitch + c0 / 4, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut4);
+          if (ch.done.fetch_add(1, std::memory_order_acq_rel) + 1 == ch.units) {  // the stage can be refilled
+            { std::lock_guard<std::mutex> lk(sync.mu); }
+            sync.cv.notify_all();
+          }
+        }
+      }
+    });
+
+  auto issue_batch = [&](int64_t b) -> int {
+    const int i = (int)(b % nbuf);
+    const int64_t b0 = b * BATCH, nb = std::min(BATCH, nsites - b0);
+    if (b >= nbuf) CT(cudaStreamWaitEvent(h->stream, copy_done[i], 0));  // staging set i has left the device
+    int rc = elx_simulate_device(h, seed, site0 + b0, nb, d_leaves[i], bpitch, d_comps[i], d_internal[i], bpitch);
+    if (rc) { cleanup(); return rc; }
+    const int64_t n16 = (nb + 15) / 16, pp = n16 * 4;
+    k_pack2<<<(unsigned)std::min<int64_t>((h->T * n16 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(d_leaves[i], bpitch, d_pl[i], pp, n16, h->T * n16);
+    h->launches++;
+    if (internal) {
+      k_pack2<<<(unsigned)std::min<int64_t>((h->N * n16 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(d_internal[i], bpitch, d_pi[i], pp, n16, h->N * n16);
+      h->launches++;
+    }
+    CT(cudaGetLastError());
+    CT(cudaEventRecord(sim_done[i], h->stream));
+    return 0;
+  };
+
+  int rc = issue_batch(0);
+  if (rc) return rc;
+  size_t c = 0;
+  for (int64_t b = 0; b < nbatch; ++b) {
+    const int i = (int)(b % nbuf);
+    const int64_t b0 = b * BATCH, nb = std::min(BATCH, nsites - b0);
+    if (b + 1 < nbatch && (rc = issue_batch(b + 1))) return rc;
+    CT(cudaStreamWaitEvent(copy_stream, sim_done[i], 0));
+    if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps[i], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, copy_stream));
+    const int64_t pp = (nb + 15) / 16 * 4;  // packed pitch of this batch
+    for (; c < plan.size() && plan[c].batch == b; ++c) {
+      const Plan &pl = plan[c];
+      PackedChunk &ch = chunks[c];
+      ch.stage = (int)(c % PIN_STAGES);
+      if (c >= (size_t)PIN_STAGES) {  // the stage is free once chunk c - PIN_STAGES is unpacked
+        PackedChunk &old = chunks[c - PIN_STAGES];
+        std::unique_lock<std::mutex> lk(sync.mu);
+        sync.cv.wait(lk, [&]() { return old.done.load(std::memory_order_acquire) >= old.units; });
+      }
+      uint8_t *stage = pin + (size_t)ch.stage * PIN_STAGE_BYTES;
+      const size_t bytes = (size_t)(pl.r1 - pl.r0) * pp;
+      CT(cudaMemcpyAsync(stage, (pl.which ? d_pi[i] : d_pl[i]) + pl.r0 * pp, bytes, cudaMemcpyDeviceToHost, copy_stream));
+      h->d2h_bytes += (int64_t)bytes;
+      ch.src = stage;
+      ch.dst = (pl.which ? internal : leaves) + b0;
+      ch.row_off = (pl.which ? internal_off : leaves_off) + pl.r0;
+      ch.lut4 = lut4;
+      ch.rows = pl.r1 - pl.r0; ch.ppitch = pp; ch.nb = nb;
+      ch.ncol = (nb + UNPACK_COLS - 1) / UNPACK_COLS;
+      ch.units = ch.rows * ch.ncol;
+      ready_args[c] = {&sync, &ch};
+      CT(cudaLaunchHostFunc(copy_stream, chunk_ready_cb, &ready_args[c]));
+    }
+    CT(cudaEventRecord(copy_done[i], copy_stream));
+    if (comps) h->d2h_bytes += (int64_t)sizeof(int32_t) * nb;
+  }
+  CT(cudaStreamSynchronize(copy_stream));  // every callback has run (or the stream failed and cleanup() releases the workers)
+  for (auto &t : workers) t.join();
+  workers.clear();
+#undef CT
+  cleanup();
+  return check_error_flag(h);
+}
+
 // host-buffer variants: device staging + copies, then synchronise
 static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int64_t site0, const double *U, int64_t u_pitch,
                                 int64_t nsites, uint8_t *leaves, int64_t lp, int32_t *comps, uint8_t *internal, int64_t ip) {
   int rc = check_sim_args(h, site0, nsites, leaves, lp, internal, ip);
   if (rc) return rc;
   if (nsites == 0) return 0;
+  {
+    // 2-bit transport: worth its thread start-up from a few MB of result on
+    const char *e = getenv("ELX_PACKED_D2H");
+    const bool want = e ? atoi(e) != 0 : (int64_t)(h->T + (internal ? h->N : 0)) * nsites >= ((int64_t)8 << 20);
+    if (!injected && h->K <= 4 && want) {
+      std::vector<int64_t> lo(h->T), io(internal ? h->N : 0);
+      for (int t = 0; t < h->T; ++t) lo[t] = t * lp;
+      for (size_t n = 0; n < io.size(); ++n) io[n] = (int64_t)n * ip;
+      return simulate_host_packed(h, seed, site0, nsites, leaves, lo.data(), comps, internal, io.data(), nullptr);
+    }
+  }
   CUDA_TRY(h, cudaSetDevice(h->device));
   // Site batches through two device staging sets: the kernels of batch b+1 (compute stream) overlap the device-to-host
   // copies of batch b (copy stream).  The result path is PCIe-bound: 1 byte per cell has to cross to the host.
@@ -996,6 +1244,7 @@ static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int
     if (internal) CT(cudaMemcpy2DAsync(internal + b0, ip, d_internal[i], bpitch, nb, h->N, cudaMemcpyDeviceToHost, copy_stream));
     if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps[i], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, copy_stream));
     CT(cudaEventRecord(copy_done[i], copy_stream));
+    h->d2h_bytes += nb * (int64_t)(h->T + (internal ? h->N : 0)) + (comps ? (int64_t)sizeof(int32_t) * nb : 0);
   }
   CT(cudaStreamSynchronize(copy_stream));
 #undef CT
@@ -1137,6 +1386,30 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
   if (!h || !out || !alphabet) return fail(h, ELX_E_INVALID, "simulate_fasta: NULL argument");
   int64_t need = elx_fasta_size(h, names, total_sites);
   if (need < 0 || out_capacity < need) return fail(h, ELX_E_INVALID, "simulate_fasta: output buffer too small");
+  {
+    // <= 4 letters: sequence lines cross PCIe at 2 bits per character and are expanded to characters by host threads, the
+    // `>name` lines are written here (same bytes as K3 writes on the device)
+    const char *e = getenv("ELX_PACKED_D2H");
+    const bool want = e ? atoi(e) != 0 : (int64_t)h->T * total_sites >= ((int64_t)8 << 20);
+    if (h->K <= 4 && want && total_sites > 0) {
+      if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
+      std::vector<int64_t> seq_off(h->T);
+      int64_t pos = 0;
+      for (int t = 0; t < h->T; ++t) {
+        const char *nm = names && names[t] ? names[t] : "";
+        const size_t len = strlen(nm);
+        out[pos] = '>';
+        memcpy(out + pos + 1, nm, len);
+        out[pos + 1 + len] = '\n';
+        seq_off[t] = pos + 1 + (int64_t)len + 1;
+        pos = seq_off[t] + total_sites + 1;
+        out[pos - 1] = '\n';
+      }
+      uint8_t lut4[4] = {'?', '?', '?', '?'};
+      memcpy(lut4, alphabet, (size_t)h->K);
+      return simulate_host_packed(h, seed, 0, total_sites, out, seq_off.data(), comps, nullptr, nullptr, lut4);
+    }
+  }
   CUDA_TRY(h, cudaSetDevice(h->device));
   uint8_t *d_out = nullptr, *d_leaves = nullptr;
   int32_t *d_comps = nullptr;

@@ -14,6 +14,9 @@
 #include <vector>
 
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/elynx_b200.h"
 #include "../../include/elynx_b200_model.h"
@@ -44,9 +47,94 @@ bool deflate_member(const uint8_t *src, size_t n, int level, std::string &out, s
   return true;
 }
 
+// ---- 2-bit transport decoding -------------------------------------------------------------------------------------
+// Alignments over <= 4 states cross PCIe packed four sites to a byte (site 4i+k in bits 2k..2k+1, elx_core.cu:k_pack2);
+// the host expands them to one byte per site -- state codes, or alphabet characters when a 4-entry table is given.
+void unpack2_scalar(const uint8_t *src, uint8_t *dst, int64_t n, const uint8_t *lut4) {
+  for (int64_t i = 0; i < n; ++i) {
+    const uint8_t st = (uint8_t)((src[i >> 2] >> (2 * (i & 3))) & 3);
+    dst[i] = lut4 ? lut4[st] : st;
+  }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void unpack2_avx2(const uint8_t *src, uint8_t *dst, int64_t n, const uint8_t *lut4) {
+  int64_t i = 0;
+  // scalar head (in steps of 4 sites) until dst is 32-byte aligned, if it ever is
+  const uintptr_t mis = (uintptr_t)dst & 31;
+  const bool can_align = (mis & 3) == 0;
+  if (can_align && mis) {
+    int64_t head = (int64_t)(32 - mis);
+    if (head > n) head = n;
+    unpack2_scalar(src, dst, head, lut4);
+    if (head & 3) return;  // n exhausted inside the head
+    i = head;
+  }
+  const __m256i rep = _mm256_setr_epi8(0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7);
+  const __m256i m0 = _mm256_set1_epi32(0x00000003), m1 = _mm256_set1_epi32(0x00000300), m2 = _mm256_set1_epi32(0x00030000),
+                m3 = _mm256_set1_epi32(0x03000000);
+  __m256i lutv = _mm256_setzero_si256();
+  if (lut4) {
+    uint32_t w;
+    memcpy(&w, lut4, 4);
+    lutv = _mm256_set1_epi32((int)w);  // bytes 0..3 of each lane; indices are 0..3
+  }
+  auto expand = [&](const uint8_t *p) __attribute__((target("avx2"))) -> __m256i {
+    const __m128i q = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(p));  // 8 packed bytes = 32 sites
+    const __m256i x = _mm256_shuffle_epi8(_mm256_broadcastsi128_si256(q), rep);
+    __m256i r = _mm256_and_si256(x, m0);
+    r = _mm256_or_si256(r, _mm256_and_si256(_mm256_srli_epi32(x, 2), m1));
+    r = _mm256_or_si256(r, _mm256_and_si256(_mm256_srli_epi32(x, 4), m2));
+    r = _mm256_or_si256(r, _mm256_and_si256(_mm256_srli_epi32(x, 6), m3));
+    return lut4 ? _mm256_shuffle_epi8(lutv, r) : r;
+  };
+  if (can_align) {
+    for (; i + 64 <= n; i += 64) {  // one cache line of output per iteration, streaming stores (no read for ownership)
+      const __m256i a = expand(src + (i >> 2)), b = expand(src + (i >> 2) + 8);
+      _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+      _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+    }
+    _mm_sfence();
+  } else {
+    for (; i + 32 <= n; i += 32) _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i), expand(src + (i >> 2)));
+  }
+  unpack2_scalar(src + (i >> 2), dst + i, n - i, lut4);
+}
+#endif
+
 }  // namespace
 
+namespace elx {
+void unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t row0, int64_t row1,
+                  int64_t nsites, const uint8_t *lut4) {
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) {
+    for (int64_t r = row0; r < row1; ++r) unpack2_avx2(packed + r * packed_pitch, dst + r * dst_pitch, nsites, lut4);
+    return;
+  }
+#endif
+  for (int64_t r = row0; r < row1; ++r) unpack2_scalar(packed + r * packed_pitch, dst + r * dst_pitch, nsites, lut4);
+}
+}  // namespace elx
+
 extern "C" {
+
+int elx_unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t rows, int64_t nsites,
+                     const char *lut4, int32_t n_threads) {
+  if (rows < 0 || nsites < 0 || ((!packed || !dst) && rows > 0 && nsites > 0)) return elx::fail(nullptr, ELX_E_INVALID, "elx_unpack2_rows: bad argument");
+  if (packed_pitch < (nsites + 3) / 4 || dst_pitch < nsites) return elx::fail(nullptr, ELX_E_INVALID, "elx_unpack2_rows: pitch too small");
+  if (lut4 && strlen(lut4) < 4) return elx::fail(nullptr, ELX_E_INVALID, "elx_unpack2_rows: the character table needs 4 entries");
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > rows) nt = (int)(rows > 0 ? rows : 1);
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nt; ++w)
+    pool.emplace_back([=]() { elx::unpack2_rows(packed, packed_pitch, dst, dst_pitch, rows * w / nt, rows * (w + 1) / nt, nsites, (const uint8_t *)lut4); });
+  elx::unpack2_rows(packed, packed_pitch, dst, dst_pitch, 0, rows / nt, nsites, (const uint8_t *)lut4);
+  for (auto &t : pool) t.join();
+  return 0;
+}
 
 int elx_gzip_write(const char *path, const uint8_t *data, int64_t size, int32_t n_threads, int32_t level, int64_t block_bytes) {
   if (!path || size < 0 || (!data && size > 0)) return elx::fail(nullptr, ELX_E_INVALID, "elx_gzip_write: bad argument");

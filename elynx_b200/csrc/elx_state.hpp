@@ -30,6 +30,7 @@ struct elx_handle {
   // quad mode (K <= 4): one draw per cap of up to 4 frontier nodes, inner nodes summed out; owned by elx_quad.cu
   void *quad = nullptr;
   int64_t launches = 0;
+  int64_t d2h_bytes = 0;  // bytes the host-buffer calls moved device -> host so far
   std::string last_error;
 };
 
@@ -71,6 +72,9 @@ struct SimArgs {
 };
 
 int fail(elx_handle *h, int code, const std::string &msg);
+// elx_io.cpp: expand rows [row0, row1) of a 2-bit packed matrix (4 sites per byte) to one byte per site
+void unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t row0, int64_t row1,
+                  int64_t nsites, const uint8_t *lut4);
 
 // elx_fast.cu: tiled shared-memory kernels for the shapes that fit (DNA / protein with few components)
 int fast_tables_build(elx_handle *h);

@@ -99,6 +99,11 @@ class Simulator:
     def launch_count(self) -> int:
         return int(L.lib().elx_launch_count(self._h))
 
+    @property
+    def d2h_bytes(self) -> int:
+        """Bytes the host-buffer calls have copied device -> host so far (2 bits per cell for alphabets of <= 4 states)."""
+        return int(L.lib().elx_d2h_bytes(self._h))
+
     # -- parity hooks ------------------------------------------------------------------------
     def ptables(self, cumulative: bool = False) -> np.ndarray:
         """[N][C][K][K] transition probabilities (probMatrix, MarkovProcess.hs:33-41) or their row-cumulative sums."""

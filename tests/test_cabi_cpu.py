@@ -322,3 +322,33 @@ def test_parallel_gzip_writer(tmp_path):
     assert gzip.decompress(open(p2, "rb").read()) == data
     with pytest.raises(L.ElxError):
         L.check(L.lib().elx_gzip_write(str(tmp_path / "nodir" / "x.gz").encode(), None, 0, 1, 6, 0))
+
+
+def test_unpack2_rows_all_alignments():
+    """elx_unpack2_rows -- the host half of the 2-bit transport of elx_simulate: every destination alignment, ragged lengths,
+    state codes and the 4-character table, any thread count; bytes outside [0, nsites) of a row stay untouched."""
+    import ctypes as C
+
+    rng = np.random.default_rng(11)
+    for rows, n, off, threads, lut in ((1, 0, 0, 1, None), (3, 1, 0, 1, None), (5, 7, 3, 2, b"ACGT"), (4, 257, 4, 3, None),
+                                       (7, 1000, 28, 4, b"ACGT"), (6, 4099, 0, 2, None), (3, 70001, 13, 8, b"TGCA"),
+                                       (33, 513, 32, 0, None)):
+        states = rng.integers(0, 4, size=(rows, n), dtype=np.uint8)
+        ppitch = (n + 3) // 4 + 5
+        packed = rng.integers(0, 256, size=(rows, ppitch), dtype=np.uint8)  # garbage in the padding
+        padded = np.zeros((rows, (n + 3) // 4 * 4), dtype=np.uint8)
+        padded[:, :n] = states
+        padded[:, n:] = rng.integers(0, 4, size=(rows, padded.shape[1] - n), dtype=np.uint8)  # pad sites of the last byte
+        q = padded.reshape(rows, -1, 4)
+        packed[:, :(n + 3) // 4] = q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)
+        dpitch = n + off + 9
+        raw = np.full(rows * dpitch + 64, 0xEE, dtype=np.uint8)
+        base = (-raw.ctypes.data) % 32 + off  # destination of row 0: `off` bytes past a 32-byte boundary
+        L.check(L.lib().elx_unpack2_rows(C.c_void_p(packed.ctypes.data), ppitch, C.c_void_p(raw.ctypes.data + base), dpitch, rows, n, lut, threads))
+        want = np.full_like(raw, 0xEE)
+        ref = states if lut is None else np.frombuffer(lut, dtype=np.uint8)[states]
+        for r in range(rows):
+            want[base + r * dpitch: base + r * dpitch + n] = ref[r]
+        assert np.array_equal(raw, want), (rows, n, off, threads)
+    with pytest.raises(L.ElxError):
+        L.check(L.lib().elx_unpack2_rows(C.c_void_p(packed.ctypes.data), 1, C.c_void_p(raw.ctypes.data), 100, 2, 100, None, 1))

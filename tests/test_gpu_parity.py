@@ -366,6 +366,64 @@ def test_freerun_partition_invariance():
         assert np.array_equal(whole, sim2.simulate(11, 5000)[0])
 
 
+@pytest.mark.parametrize("keep_internal", [False, True])
+def test_host_buffer_call_packed_transport_is_byte_identical(keep_internal, monkeypatch):
+    """elx_simulate with host buffers: alignments over <= 4 states cross PCIe packed to 2 bits per site (k_pack2) and are
+    expanded by host threads; the bytes must equal the plain 1-byte transport for multi-batch, ragged site ranges, with the
+    component vector and the internal states, and the packed call must move a quarter of the bytes."""
+    model = model_case("hky_g4")
+    tree = tree_from_file("Newick.tree")
+    nsites = 2 * (1 << 20) + 12345  # three device batches, the last one ragged (not a multiple of 4)
+    with make_sim(model, tree) as sim:
+        monkeypatch.setenv("ELX_PACKED_D2H", "0")
+        b0 = sim.d2h_bytes
+        plain = sim.simulate(5, nsites, site0=77, want_comps=True, keep_internal=keep_internal)
+        b1 = sim.d2h_bytes
+        rows = tree.n_leaves + (tree.n_nodes if keep_internal else 0)
+        assert b1 - b0 == nsites * (rows + 4)
+        for threads in ("1", "5"):
+            monkeypatch.setenv("ELX_PACKED_D2H", "1")
+            monkeypatch.setenv("ELX_HOST_THREADS", threads)
+            b1 = sim.d2h_bytes
+            packed = sim.simulate(5, nsites, site0=77, want_comps=True, keep_internal=keep_internal)
+            moved = sim.d2h_bytes - b1
+            assert np.array_equal(plain[0], packed[0]) and np.array_equal(plain[1], packed[1])
+            if keep_internal:
+                assert np.array_equal(plain[2], packed[2])
+            assert moved < 0.26 * nsites * rows + 4 * nsites + (1 << 16)
+        monkeypatch.delenv("ELX_HOST_THREADS")
+        monkeypatch.delenv("ELX_PACKED_D2H")
+        if keep_internal:  # (calls that keep the internal states draw sibling pairs: another stream than leaves-only calls)
+            return
+        small = sim.simulate(5, 1000, site0=77)[0]   # below the size threshold: plain transport
+        assert np.array_equal(small, plain[0][:, :1000])
+        auto = sim.simulate(5, nsites, site0=77)[0]   # above it: packed by default
+        assert np.array_equal(auto, plain[0])
+        # a caller's pitch and an unaligned destination
+        import ctypes as C
+        from elynx_b200 import _lib as L
+        pitch = nsites + 13
+        raw = np.full(tree.n_leaves * pitch + 64, 0xEE, dtype=np.uint8)
+        L.check(L.lib().elx_simulate(sim.handle, C.c_uint64(5), 77, nsites, C.c_void_p(raw.ctypes.data + 3), pitch, None, None, 0), sim.handle)
+        view = raw[3:3 + tree.n_leaves * pitch].reshape(tree.n_leaves, pitch)
+        assert np.array_equal(view[:, :nsites], plain[0])
+        assert (view[:-1, nsites:] == 0xEE).all() and (raw[:3] == 0xEE).all()
+        # FASTA through host buffers: 2 bits per character over PCIe, `>name` lines and characters written on the host
+        names = tree.leaf_names()
+        alphabet = om.ALPHABET_CHARS[model[4]]
+        for packed_env in ("0", "1"):
+            monkeypatch.setenv("ELX_PACKED_D2H", packed_env)
+            fasta, fc = sim.simulate_fasta(5, nsites, names, alphabet, want_comps=True)
+            assert fasta == om.sequences_to_fasta(names, sim.simulate(5, nsites)[0], model[4]), packed_env
+            assert np.array_equal(fc, sim.simulate(5, nsites, want_comps=True)[1])
+        monkeypatch.delenv("ELX_PACKED_D2H")
+        # a page-locked destination
+        import torch
+        host = torch.full((tree.n_leaves, nsites), 0xEE, dtype=torch.uint8).pin_memory()
+        L.check(L.lib().elx_simulate(sim.handle, C.c_uint64(5), 77, nsites, C.c_void_p(host.data_ptr()), nsites, None, None, 0), sim.handle)
+        assert np.array_equal(host.numpy(), plain[0])
+
+
 @pytest.mark.parametrize("name", ["jc", "hky_g4", "mixture_dna"])
 def test_freerun_chi_square_vs_exact_pattern_probabilities(name):
     """Free-running output vs exact Felsenstein-pruning pattern probabilities on a 4-taxon tree (256 patterns)."""
