@@ -8,6 +8,7 @@
 //   FASTA layout               elynx-seq/src/ELynx/Sequence/Export/Fasta.hs:24-36
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -1089,13 +1090,23 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   int nt = (int)std::thread::hardware_concurrency() - 2;
   if (const char *e = getenv("ELX_HOST_THREADS")) nt = atoi(e);
   nt = std::max(1, std::min(nt, 32));
+  const bool debug = getenv("ELX_TRANSPORT_DEBUG") != nullptr;  // prints where the call's time went
+  const auto t_start = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+  std::atomic<int64_t> wait_us{0}, first_ready_us{-1};
   for (int w = 0; w < nt; ++w)
-    workers.emplace_back([&chunks, &sync]() {
+    workers.emplace_back([&chunks, &sync, &wait_us, &first_ready_us, t_start, debug]() {
       for (size_t c = 0; c < chunks.size(); ++c) {
         PackedChunk &ch = chunks[c];
         if (!ch.ready.load(std::memory_order_acquire)) {
+          const auto t0 = std::chrono::steady_clock::now();
           std::unique_lock<std::mutex> lk(sync.mu);
           sync.cv.wait(lk, [&]() { return ch.ready.load(std::memory_order_acquire) || sync.abort_flag.load(); });
+          if (debug) {
+            wait_us.fetch_add(std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
+            int64_t expect = -1;
+            if (c == 0) first_ready_us.compare_exchange_strong(expect, std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count());
+          }
         }
         if (sync.abort_flag.load()) return;
         for (;;) {
@@ -1166,9 +1177,15 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
     CT(cudaEventRecord(copy_done[i], copy_stream));
     if (comps) h->d2h_bytes += (int64_t)sizeof(int32_t) * nb;
   }
+  const double t_issued = since(t_start);
   CT(cudaStreamSynchronize(copy_stream));  // every callback has run (or the stream failed and cleanup() releases the workers)
+  const double t_copied = since(t_start);
   for (auto &t : workers) t.join();
   workers.clear();
+  if (debug)
+    fprintf(stderr, "[elx transport] %zu chunks, %d threads: first chunk ready %.1f ms, all issued %.1f ms, all copied %.1f ms, all unpacked %.1f ms; "
+            "workers waited %.1f ms each on average\n", chunks.size(), nt, first_ready_us.load() / 1e3, t_issued, t_copied, since(t_start),
+            wait_us.load() / 1e3 / nt);
 #undef CT
   cleanup();
   return check_error_flag(h);
