@@ -259,7 +259,7 @@ def run_product(args):
         if world > 1:  # keep the pinned host buffers of all ranks of the box together under ~24 GB
             e2e_sites = max(16, min(e2e_sites, int(24e9 / (T * world)) // 16 * 16))
         if world > 1 and "ELX_HOST_THREADS" not in os.environ:  # the ranks of a box share its cores
-            os.environ["ELX_HOST_THREADS"] = str(max(1, ((os.cpu_count() or 2) - 2) // world))
+            os.environ["ELX_HOST_THREADS"] = str(max(1, ((os.cpu_count() or 3) - 3) // world))
         host = torch.empty((T, e2e_sites), dtype=torch.uint8, pin_memory=True)
         hnp = host.numpy()
         import ctypes as C
@@ -295,8 +295,8 @@ def run_product(args):
                "d2h_bytes_per_step": int(d2h), "sites_per_gpu": e2e_sites, "ms_per_step": float(te.item()) * 1e3,
                "result_bytes_per_step": int(T * e2e_sites), "steps": k_e2e, "ms_steps": [round(x, 2) for x in step_ms],
                "statistic": "median step",
-               "transport": ("2 bits per cell over PCIe (k_pack2), expanded into the caller's buffer by host threads" if d2h < T * e2e_sites
-                             else "1 byte per cell over PCIe"),
+               "transport": ("%d bits per cell over PCIe (k_pack%d), expanded into the caller's buffer by host threads"
+                             % ((2, 2) if model.n_states <= 4 else (5, 5)) if d2h < T * e2e_sites else "1 byte per cell over PCIe"),
                "includes": "elx_create (eigensystems, H2D of model+tree, K1 tables) + simulation + D2H + the caller's [T][S] uint8 host "
                            "buffer completely written + destroy"}
         del host

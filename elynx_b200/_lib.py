@@ -96,6 +96,7 @@ SIGNATURES = {
     "elx_launch_count": (_I64, [_VP]),
     "elx_d2h_bytes": (_I64, [_VP]),
     "elx_unpack2_rows": (_I32, [_VP, _I64, _VP, _I64, _I64, _I64, C.c_char_p, C.c_int32]),
+    "elx_unpack5_rows": (_I32, [_VP, _I64, _VP, _I64, _I64, _I64, C.c_char_p, C.c_int32]),
 }
 
 _lib = None

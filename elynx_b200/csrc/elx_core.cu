@@ -958,11 +958,33 @@ __global__ void k_pack2(const uint8_t *__restrict__ src, int64_t spitch, uint8_t
   }
 }
 
+// 5-bit form for alphabets of 5..32 states: 32 sites (two 128-bit loads) -> 20 bytes (five 32-bit stores) per thread;
+// site i of a row sits in bits 5i..5i+4 of the row's little-endian bit stream.
+__global__ void k_pack5(const uint8_t *__restrict__ src, int64_t spitch, uint8_t *__restrict__ dst, int64_t dpitch, int64_t n32,
+                        int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / n32, g = idx - r * n32;
+    const uint4 *p = reinterpret_cast<const uint4 *>(src + r * spitch + g * 32);
+    const uint4 a = __ldcs(p), b = __ldcs(p + 1);
+    auto p4 = [](uint32_t w) {  // 4 sites -> 20 bits
+      w &= 0x1f1f1f1fu;
+      return (w & 0x1fu) | ((w >> 3) & 0x3e0u) | ((w >> 6) & 0x7c00u) | ((w >> 9) & 0xf8000u);
+    };
+    const uint64_t q0 = (uint64_t)p4(a.x) | ((uint64_t)p4(a.y) << 20), q1 = (uint64_t)p4(a.z) | ((uint64_t)p4(a.w) << 20),
+                   q2 = (uint64_t)p4(b.x) | ((uint64_t)p4(b.y) << 20), q3 = (uint64_t)p4(b.z) | ((uint64_t)p4(b.w) << 20);
+    uint32_t *o = reinterpret_cast<uint32_t *>(dst + r * dpitch + g * 20);
+    o[0] = (uint32_t)q0;
+    o[1] = (uint32_t)(q0 >> 32) | (uint32_t)(q1 << 8);
+    o[2] = (uint32_t)(q1 >> 24) | (uint32_t)(q2 << 16);
+    o[3] = (uint32_t)(q2 >> 16) | (uint32_t)(q3 << 24);
+    o[4] = (uint32_t)(q3 >> 8);
+  }
+}
+
 namespace {
-constexpr int PIN_STAGES = 4;
-constexpr size_t PIN_STAGE_BYTES = (size_t)32 << 20;
+constexpr size_t PIN_BYTES = (size_t)128 << 20;  // one staging set, cut into stages (ELX_STAGE_MB, default 8 MB each)
 std::mutex g_pin_mu;
-std::vector<uint8_t *> g_pin_free;  // staging sets of PIN_STAGES x PIN_STAGE_BYTES, kept across handles (pinning is slow)
+std::vector<uint8_t *> g_pin_free;  // staging sets of PIN_BYTES, kept across handles (pinning is slow)
 
 uint8_t *pin_acquire() {
   {
@@ -974,7 +996,7 @@ uint8_t *pin_acquire() {
     }
   }
   uint8_t *p = nullptr;
-  if (cudaHostAlloc((void **)&p, PIN_STAGES * PIN_STAGE_BYTES, cudaHostAllocPortable) != cudaSuccess) {
+  if (cudaHostAlloc((void **)&p, PIN_BYTES + 64, cudaHostAllocPortable) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -998,39 +1020,41 @@ struct PackedChunk {
   const uint8_t *src = nullptr;  // pinned staging rows
   uint8_t *dst = nullptr;        // caller's buffer + first site of the batch; row r of the chunk starts at dst + row_off[r]
   const int64_t *row_off = nullptr;
-  const uint8_t *lut4 = nullptr;
+  const uint8_t *lut = nullptr;
+  int bits = 2;
   int64_t rows = 0, ppitch = 0, nb = 0, ncol = 0, units = 0;
-  std::atomic<int> ready{0};  // set by a host callback on the copy stream once the chunk sits in its staging buffer
+  std::atomic<int> issued{0};  // its copy and event are enqueued
+  std::atomic<int> ready{0};   // the chunk sits in its staging buffer (set by the waiter thread)
   std::atomic<int64_t> next{0}, done{0};
 };
 struct TransportSync {
   std::mutex mu;
-  std::condition_variable cv;
+  std::condition_variable cv;       // workers: a chunk has arrived (or abort)
+  std::condition_variable cv_done;  // the dispatcher: a chunk is unpacked, its stage is free
+  std::condition_variable cv_issue; // the waiter thread: the next chunk's copy is enqueued
   std::atomic<int> abort_flag{0};
 };
-struct ChunkReady { TransportSync *sync; PackedChunk *chunk; };
-void CUDART_CB chunk_ready_cb(void *p) {
-  ChunkReady *r = static_cast<ChunkReady *>(p);
-  {
-    std::lock_guard<std::mutex> lk(r->sync->mu);
-    r->chunk->ready.store(1, std::memory_order_release);
-  }
-  r->sync->cv.notify_all();
-}
 constexpr int64_t UNPACK_COLS = 65536;  // sites per work unit of the unpack threads
 }  // namespace
 
-// leaves / internal: base pointers; row r of a matrix starts at base + off[r].  lut4: nullptr = state codes, else the
-// alphabet (FASTA sequence lines).
+// leaves / internal: base pointers; row r of a matrix starts at base + off[r].  lut: nullptr = state codes, else the
+// alphabet (FASTA sequence lines; 4 characters for the 2-bit form, 32 for the 5-bit form).
 static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves,
                                 const int64_t *leaves_off, int32_t *comps, uint8_t *internal, const int64_t *internal_off,
-                                const uint8_t *lut4) {
+                                const uint8_t *lut) {
   CUDA_TRY(h, cudaSetDevice(h->device));
+  const int bits = h->K <= 4 ? 2 : 5;  // a packing group is 32 sites: 8 or 20 bytes
+  auto packed_pitch = [bits](int64_t n) { return (n + 31) / 32 * (bits == 2 ? 8 : 20); };
   const int64_t BATCH = 1 << 20;
   const int NB = 2;
   const int64_t nbatch = (nsites + BATCH - 1) / BATCH;
   const int64_t bmax = nsites < BATCH ? nsites : BATCH;
-  const int64_t bpitch = (bmax + 15) & ~(int64_t)15, ppitch = bpitch / 4;  // ppitch: of a full batch; a ragged last batch packs tighter
+  const int64_t bpitch = (bmax + 31) & ~(int64_t)31, ppitch = packed_pitch(bmax);  // ppitch: of a full batch; a ragged last batch packs tighter
+  size_t stage_mb = 8;
+  if (const char *e = getenv("ELX_STAGE_MB")) stage_mb = (size_t)std::min(128, std::max(1, atoi(e)));
+  const size_t PIN_STAGE_BYTES = std::max<size_t>(stage_mb << 20, (size_t)ppitch);  // a chunk is at least one packed row
+  const int PIN_STAGES = (int)(PIN_BYTES / PIN_STAGE_BYTES);
+  if (PIN_STAGES < 2) return fail(h, ELX_E_INVALID, "packed transport: a packed row does not fit the staging buffers");
   const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)PIN_STAGE_BYTES / ppitch);
   const int nbuf = nbatch > 1 ? NB : 1;
   uint8_t *d_leaves[NB] = {nullptr, nullptr}, *d_internal[NB] = {nullptr, nullptr}, *d_pl[NB] = {nullptr, nullptr},
@@ -1050,15 +1074,20 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
       for (int64_t r0 = 0; r0 < R; r0 += rows_per_chunk) plan.push_back({b, which, r0, std::min(R, r0 + rows_per_chunk)});
     }
   std::vector<PackedChunk> chunks(plan.size());
-  std::vector<ChunkReady> ready_args(plan.size());
+  std::vector<cudaEvent_t> stage_ev;
+  std::thread waiter;
   auto cleanup = [&]() {
     {
       std::lock_guard<std::mutex> lk(sync.mu);
       sync.abort_flag.store(1);
     }
     sync.cv.notify_all();
+    sync.cv_issue.notify_all();
+    if (waiter.joinable()) waiter.join();
     for (auto &t : workers) t.join();
     workers.clear();
+    for (cudaEvent_t e : stage_ev) cudaEventDestroy(e);
+    stage_ev.clear();
     if (copy_stream) cudaStreamSynchronize(copy_stream);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < NB; ++i) {
@@ -1085,9 +1114,42 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
     CT(cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming));
   }
 
-  // all cores but two (this thread feeds the streams, the driver runs the callbacks); waits are blocking: spinning
+  // One waiter thread turns "copy of chunk c finished" (an event per stage) into a wake-up of the workers.  A host
+  // callback on the copy stream did the same at ~0.25 ms per chunk: the stream stalls until the callback has returned.
+  for (int i = 0; i < PIN_STAGES; ++i) {
+    cudaEvent_t e = nullptr;
+    CT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));  // the waiter sleeps, the cores unpack
+    stage_ev.push_back(e);
+  }
+  waiter = std::thread([&chunks, &sync, &stage_ev, dev = h->device]() {
+    cudaSetDevice(dev);
+    for (size_t c = 0; c < chunks.size(); ++c) {
+      PackedChunk &ch = chunks[c];
+      {
+        std::unique_lock<std::mutex> lk(sync.mu);
+        sync.cv_issue.wait(lk, [&]() { return ch.issued.load(std::memory_order_acquire) || sync.abort_flag.load(); });
+      }
+      if (sync.abort_flag.load()) return;
+      if (cudaEventSynchronize(stage_ev[ch.stage]) != cudaSuccess) {
+        {
+          std::lock_guard<std::mutex> lk(sync.mu);
+          sync.abort_flag.store(2);
+        }
+        sync.cv.notify_all();
+        sync.cv_done.notify_all();
+        return;
+      }
+      {
+        std::lock_guard<std::mutex> lk(sync.mu);
+        ch.ready.store(1, std::memory_order_release);
+      }
+      sync.cv.notify_all();
+    }
+  });
+  // all cores but three (this thread feeds the streams, the waiter wakes per chunk, the driver has threads of its own);
+  // waits are blocking: spinning
   // workers were measured to starve the dispatcher (16 spinning threads on 16 cores: 160 ms for cfg2, 8: 122 ms)
-  int nt = (int)std::thread::hardware_concurrency() - 2;
+  int nt = (int)std::thread::hardware_concurrency() - 3;
   if (const char *e = getenv("ELX_HOST_THREADS")) nt = atoi(e);
   nt = std::max(1, std::min(nt, 32));
   const bool debug = getenv("ELX_TRANSPORT_DEBUG") != nullptr;  // prints where the call's time went
@@ -1114,10 +1176,11 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
           if (u >= ch.units) break;
           const int64_t r = u / ch.ncol, k = u - r * ch.ncol;
           const int64_t c0 = k * UNPACK_COLS, c1 = std::min(ch.nb, c0 + UNPACK_COLS);
-          elx::unpack2_rows(ch.src + r * ch.ppitch + c0 / 4, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut4);
+          if (ch.bits == 2) elx::unpack2_rows(ch.src + r * ch.ppitch + c0 / 4, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut);
+          else elx::unpack5_rows(ch.src + r * ch.ppitch + c0 / 8 * 5, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut);
           if (ch.done.fetch_add(1, std::memory_order_acq_rel) + 1 == ch.units) {  // the stage can be refilled
             { std::lock_guard<std::mutex> lk(sync.mu); }
-            sync.cv.notify_all();
+            sync.cv_done.notify_one();
           }
         }
       }
@@ -1129,13 +1192,19 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
     if (b >= nbuf) CT(cudaStreamWaitEvent(h->stream, copy_done[i], 0));  // staging set i has left the device
     int rc = elx_simulate_device(h, seed, site0 + b0, nb, d_leaves[i], bpitch, d_comps[i], d_internal[i], bpitch);
     if (rc) { cleanup(); return rc; }
-    const int64_t n16 = (nb + 15) / 16, pp = n16 * 4;
-    k_pack2<<<(unsigned)std::min<int64_t>((h->T * n16 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(d_leaves[i], bpitch, d_pl[i], pp, n16, h->T * n16);
-    h->launches++;
-    if (internal) {
-      k_pack2<<<(unsigned)std::min<int64_t>((h->N * n16 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(d_internal[i], bpitch, d_pi[i], pp, n16, h->N * n16);
+    const int64_t pp = packed_pitch(nb);
+    auto pack = [&](const uint8_t *src, uint8_t *dst, int64_t rows) {
+      if (bits == 2) {
+        const int64_t n16 = (nb + 31) / 32 * 2;
+        k_pack2<<<(unsigned)std::min<int64_t>((rows * n16 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(src, bpitch, dst, pp, n16, rows * n16);
+      } else {
+        const int64_t n32 = (nb + 31) / 32;
+        k_pack5<<<(unsigned)std::min<int64_t>((rows * n32 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(src, bpitch, dst, pp, n32, rows * n32);
+      }
       h->launches++;
-    }
+    };
+    pack(d_leaves[i], d_pl[i], h->T);
+    if (internal) pack(d_internal[i], d_pi[i], h->N);
     CT(cudaGetLastError());
     CT(cudaEventRecord(sim_done[i], h->stream));
     return 0;
@@ -1150,7 +1219,7 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
     if (b + 1 < nbatch && (rc = issue_batch(b + 1))) return rc;
     CT(cudaStreamWaitEvent(copy_stream, sim_done[i], 0));
     if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps[i], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, copy_stream));
-    const int64_t pp = (nb + 15) / 16 * 4;  // packed pitch of this batch
+    const int64_t pp = packed_pitch(nb);  // of this batch
     for (; c < plan.size() && plan[c].batch == b; ++c) {
       const Plan &pl = plan[c];
       PackedChunk &ch = chunks[c];
@@ -1158,7 +1227,12 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
       if (c >= (size_t)PIN_STAGES) {  // the stage is free once chunk c - PIN_STAGES is unpacked
         PackedChunk &old = chunks[c - PIN_STAGES];
         std::unique_lock<std::mutex> lk(sync.mu);
-        sync.cv.wait(lk, [&]() { return old.done.load(std::memory_order_acquire) >= old.units; });
+        sync.cv_done.wait(lk, [&]() { return old.done.load(std::memory_order_acquire) >= old.units || sync.abort_flag.load(); });
+        if (sync.abort_flag.load()) {
+          lk.unlock();
+          cleanup();
+          return fail(h, ELX_E_CUDA, "packed transport: waiting for a device-to-host copy failed");
+        }
       }
       uint8_t *stage = pin + (size_t)ch.stage * PIN_STAGE_BYTES;
       const size_t bytes = (size_t)(pl.r1 - pl.r0) * pp;
@@ -1167,19 +1241,25 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
       ch.src = stage;
       ch.dst = (pl.which ? internal : leaves) + b0;
       ch.row_off = (pl.which ? internal_off : leaves_off) + pl.r0;
-      ch.lut4 = lut4;
+      ch.lut = lut;
+      ch.bits = bits;
       ch.rows = pl.r1 - pl.r0; ch.ppitch = pp; ch.nb = nb;
       ch.ncol = (nb + UNPACK_COLS - 1) / UNPACK_COLS;
       ch.units = ch.rows * ch.ncol;
-      ready_args[c] = {&sync, &ch};
-      CT(cudaLaunchHostFunc(copy_stream, chunk_ready_cb, &ready_args[c]));
+      CT(cudaEventRecord(stage_ev[ch.stage], copy_stream));
+      {
+        std::lock_guard<std::mutex> lk(sync.mu);
+        ch.issued.store(1, std::memory_order_release);
+      }
+      sync.cv_issue.notify_one();
     }
     CT(cudaEventRecord(copy_done[i], copy_stream));
     if (comps) h->d2h_bytes += (int64_t)sizeof(int32_t) * nb;
   }
   const double t_issued = since(t_start);
-  CT(cudaStreamSynchronize(copy_stream));  // every callback has run (or the stream failed and cleanup() releases the workers)
+  CT(cudaStreamSynchronize(copy_stream));
   const double t_copied = since(t_start);
+  waiter.join();
   for (auto &t : workers) t.join();
   workers.clear();
   if (debug)
@@ -1201,7 +1281,7 @@ static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int
     // 2-bit transport: worth its thread start-up from a few MB of result on
     const char *e = getenv("ELX_PACKED_D2H");
     const bool want = e ? atoi(e) != 0 : (int64_t)(h->T + (internal ? h->N : 0)) * nsites >= ((int64_t)8 << 20);
-    if (!injected && h->K <= 4 && want) {
+    if (!injected && h->K <= 32 && want) {
       std::vector<int64_t> lo(h->T), io(internal ? h->N : 0);
       for (int t = 0; t < h->T; ++t) lo[t] = t * lp;
       for (size_t n = 0; n < io.size(); ++n) io[n] = (int64_t)n * ip;
@@ -1408,7 +1488,7 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
     // `>name` lines are written here (same bytes as K3 writes on the device)
     const char *e = getenv("ELX_PACKED_D2H");
     const bool want = e ? atoi(e) != 0 : (int64_t)h->T * total_sites >= ((int64_t)8 << 20);
-    if (h->K <= 4 && want && total_sites > 0) {
+    if (h->K <= 32 && want && total_sites > 0) {
       if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
       std::vector<int64_t> seq_off(h->T);
       int64_t pos = 0;
@@ -1422,9 +1502,10 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
         pos = seq_off[t] + total_sites + 1;
         out[pos - 1] = '\n';
       }
-      uint8_t lut4[4] = {'?', '?', '?', '?'};
-      memcpy(lut4, alphabet, (size_t)h->K);
-      return simulate_host_packed(h, seed, 0, total_sites, out, seq_off.data(), comps, nullptr, nullptr, lut4);
+      uint8_t lut[32];
+      memset(lut, '?', sizeof lut);
+      memcpy(lut, alphabet, (size_t)h->K);
+      return simulate_host_packed(h, seed, 0, total_sites, out, seq_off.data(), comps, nullptr, nullptr, lut);
     }
   }
   CUDA_TRY(h, cudaSetDevice(h->device));

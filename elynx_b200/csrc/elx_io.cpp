@@ -5,6 +5,7 @@
 // cut into blocks that worker threads deflate independently, each into its own gzip MEMBER; members are written in order.
 // A multi-member file is a valid gzip file: gunzip, Python's gzip module and the reference's reader (`decompress`,
 // InputOutput.hs:73-76; zlib >= 0.6 concatenates members) all return the original bytes.
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -102,6 +103,79 @@ __attribute__((target("avx2"))) void unpack2_avx2(const uint8_t *src, uint8_t *d
 }
 #endif
 
+// ---- 5-bit transport decoding (alphabets of <= 32 states: amino acids) --------------------------------------------
+// site i of a row sits in bits 5i..5i+4 of the row's little-endian bit stream (elx_core.cu:k_pack5): 8 sites = 5 bytes.
+void unpack5_scalar(const uint8_t *src, uint8_t *dst, int64_t i0, int64_t n, const uint8_t *lut) {
+  for (int64_t i = i0; i < n; ++i) {
+    const int64_t bit = 5 * i;
+    const uint32_t lo = src[bit >> 3], hi = (bit & 7) > 3 ? src[(bit >> 3) + 1] : 0u;  // a field spans at most 2 bytes
+    const uint8_t st = (uint8_t)(((lo | (hi << 8)) >> (bit & 7)) & 31);
+    dst[i] = lut ? lut[st] : st;
+  }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2,bmi2"))) void unpack5_bmi2(const uint8_t *src, uint8_t *dst, int64_t n, const uint8_t *lut) {
+  const uint64_t M = 0x1f1f1f1f1f1f1f1fULL;
+  __m256i lut_lo = _mm256_setzero_si256(), lut_hi = _mm256_setzero_si256();
+  if (lut) {
+    lut_lo = _mm256_broadcastsi128_si256(_mm_loadu_si128(reinterpret_cast<const __m128i *>(lut)));
+    lut_hi = _mm256_broadcastsi128_si256(_mm_loadu_si128(reinterpret_cast<const __m128i *>(lut + 16)));
+  }
+  const bool aligned = ((uintptr_t)dst & 31) == 0;
+  int64_t i = 0;
+  // 32 sites = 20 packed bytes per iteration; the 8-byte loads read 3 bytes past each 5-byte group, so the last 32-site
+  // group of the row is left to the exact scalar tail
+  for (; i + 64 <= n; i += 32) {
+    const uint8_t *p = src + (i >> 3) * 5;
+    uint64_t v0, v1, v2, v3;
+    memcpy(&v0, p, 8); memcpy(&v1, p + 5, 8); memcpy(&v2, p + 10, 8); memcpy(&v3, p + 15, 8);
+    __m256i r = _mm256_set_epi64x((long long)_pdep_u64(v3, M), (long long)_pdep_u64(v2, M), (long long)_pdep_u64(v1, M), (long long)_pdep_u64(v0, M));
+    if (lut) {
+      const __m256i lo = _mm256_shuffle_epi8(lut_lo, r), hi = _mm256_shuffle_epi8(lut_hi, r);  // index bits 0..3, bit 7 clear
+      r = _mm256_blendv_epi8(lo, hi, _mm256_cmpgt_epi8(r, _mm256_set1_epi8(15)));
+    }
+    if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), r);
+    else _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i), r);
+  }
+  if (aligned) _mm_sfence();
+  unpack5_scalar(src, dst, i, n, lut);
+}
+
+// AVX-512 VBMI: 64 sites per iteration -- one byte permute brings every 5-byte group into its own 64-bit lane, one
+// multishift extracts the eight 5-bit fields of a lane, one more permute is the 32-entry alphabet look-up.
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) void unpack5_vbmi(const uint8_t *src, uint8_t *dst, int64_t n, const uint8_t *lut) {
+  alignas(64) uint8_t idx_b[64], ctl_b[64], lut_b[64];
+  for (int q = 0; q < 8; ++q)
+    for (int b = 0; b < 8; ++b) {
+      idx_b[8 * q + b] = (uint8_t)std::min(5 * q + b, 63);
+      ctl_b[8 * q + b] = (uint8_t)(5 * b);
+    }
+  memset(lut_b, '?', sizeof lut_b);
+  if (lut) memcpy(lut_b, lut, 32);
+  const __m512i idx = _mm512_load_si512(idx_b), ctl = _mm512_load_si512(ctl_b), lutv = _mm512_load_si512(lut_b);
+  const __m512i m5 = _mm512_set1_epi8(31);
+  const __mmask64 k40 = (__mmask64)((1ULL << 40) - 1);
+  // scalar head (whole 8-site groups) up to a 64-byte boundary of dst, when there is one on a group boundary
+  const bool aligned = ((uintptr_t)dst & 7) == 0;
+  int64_t i = 0;
+  if (aligned && ((uintptr_t)dst & 63)) {
+    const int64_t head = std::min<int64_t>(n, 64 - (int64_t)((uintptr_t)dst & 63));
+    unpack5_scalar(src, dst, 0, head, lut);
+    i = head;
+  }
+  for (; i + 64 <= n; i += 64) {
+    const __m512i v = _mm512_maskz_loadu_epi8(k40, src + (i >> 3) * 5);  // exactly the 40 bytes of these 64 sites
+    __m512i r = _mm512_and_si512(_mm512_multishift_epi64_epi8(ctl, _mm512_permutexvar_epi8(idx, v)), m5);
+    if (lut) r = _mm512_permutexvar_epi8(r, lutv);
+    if (aligned) _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + i), r);
+    else _mm512_storeu_si512(dst + i, r);
+  }
+  if (aligned) _mm_sfence();
+  unpack5_scalar(src, dst, i, n, lut);
+}
+#endif
+
 }  // namespace
 
 namespace elx {
@@ -116,9 +190,48 @@ void unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int
 #endif
   for (int64_t r = row0; r < row1; ++r) unpack2_scalar(packed + r * packed_pitch, dst + r * dst_pitch, nsites, lut4);
 }
+
+void unpack5_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t row0, int64_t row1,
+                  int64_t nsites, const uint8_t *lut32) {
+#if defined(__x86_64__)
+  static const bool vbmi = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+                           !getenv("ELX_NO_AVX512");
+  if (vbmi) {
+    for (int64_t r = row0; r < row1; ++r) unpack5_vbmi(packed + r * packed_pitch, dst + r * dst_pitch, nsites, lut32);
+    return;
+  }
+  static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+  if (fast) {
+    for (int64_t r = row0; r < row1; ++r) unpack5_bmi2(packed + r * packed_pitch, dst + r * dst_pitch, nsites, lut32);
+    return;
+  }
+#endif
+  for (int64_t r = row0; r < row1; ++r) unpack5_scalar(packed + r * packed_pitch, dst + r * dst_pitch, 0, nsites, lut32);
+}
 }  // namespace elx
 
 extern "C" {
+
+int elx_unpack5_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t rows, int64_t nsites,
+                     const char *lut32, int32_t n_threads) {
+  if (rows < 0 || nsites < 0 || ((!packed || !dst) && rows > 0 && nsites > 0)) return elx::fail(nullptr, ELX_E_INVALID, "elx_unpack5_rows: bad argument");
+  if (packed_pitch < (5 * nsites + 7) / 8 || dst_pitch < nsites) return elx::fail(nullptr, ELX_E_INVALID, "elx_unpack5_rows: pitch too small");
+  uint8_t lut[32];
+  if (lut32) {
+    memset(lut, '?', sizeof lut);
+    memcpy(lut, lut32, std::min<size_t>(32, strlen(lut32)));
+  }
+  const uint8_t *lp = lut32 ? lut : nullptr;
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > rows) nt = (int)(rows > 0 ? rows : 1);
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nt; ++w)
+    pool.emplace_back([=]() { elx::unpack5_rows(packed, packed_pitch, dst, dst_pitch, rows * w / nt, rows * (w + 1) / nt, nsites, lp); });
+  elx::unpack5_rows(packed, packed_pitch, dst, dst_pitch, 0, rows / nt, nsites, lp);
+  for (auto &t : pool) t.join();
+  return 0;
+}
 
 int elx_unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t rows, int64_t nsites,
                      const char *lut4, int32_t n_threads) {

@@ -75,6 +75,9 @@ int fail(elx_handle *h, int code, const std::string &msg);
 // elx_io.cpp: expand rows [row0, row1) of a 2-bit packed matrix (4 sites per byte) to one byte per site
 void unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t row0, int64_t row1,
                   int64_t nsites, const uint8_t *lut4);
+// the same for the 5-bit form (8 sites per 5 bytes; lut32: 32 characters or nullptr)
+void unpack5_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t row0, int64_t row1,
+                  int64_t nsites, const uint8_t *lut32);
 
 // elx_fast.cu: tiled shared-memory kernels for the shapes that fit (DNA / protein with few components)
 int fast_tables_build(elx_handle *h);

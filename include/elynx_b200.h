@@ -242,14 +242,19 @@ int elx_examine(const uint8_t *states, int64_t pitch, int32_t n_sequences, int64
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t elx_launch_count(const elx_handle *h);
 /* Bytes the host-buffer calls of this handle (elx_simulate, elx_simulate_injected) have copied device -> host so far.
- * Alignments over <= 4 states cross PCIe packed to 2 bits per site and are expanded into the caller's buffer by host
- * threads (ELX_HOST_THREADS, default: all cores, at most 32; ELX_PACKED_D2H=0 turns the packed transport off). */
+ * Alignments over <= 4 states cross PCIe packed to 2 bits per site, over <= 32 states to 5 bits, and are expanded into the
+ * caller's buffer by host threads (ELX_HOST_THREADS, default: all cores but three, at most 32; ELX_PACKED_D2H=0 turns the
+ * packed transport off). */
 int64_t elx_d2h_bytes(const elx_handle *h);
 /* The host half of that transport, exported for tests and for callers that keep packed alignments: expands a 2-bit packed
  * matrix (site 4i+k of a row in bits 2k..2k+1 of byte i) to one byte per site -- state codes 0..3, or lut4[state] when a
  * 4-character table is given -- with n_threads host threads (<= 0: all cores). */
 int elx_unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t rows, int64_t nsites,
                      const char *lut4, int32_t n_threads);
+/* Alphabets of 5..32 states (amino acids) travel at 5 bits per site: site i of a row in bits 5i..5i+4 of the row's
+ * little-endian bit stream (8 sites = 5 bytes); lut32: up to 32 characters, or NULL for state codes. */
+int elx_unpack5_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t rows, int64_t nsites,
+                     const char *lut32, int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -352,3 +352,34 @@ def test_unpack2_rows_all_alignments():
         assert np.array_equal(raw, want), (rows, n, off, threads)
     with pytest.raises(L.ElxError):
         L.check(L.lib().elx_unpack2_rows(C.c_void_p(packed.ctypes.data), 1, C.c_void_p(raw.ctypes.data), 100, 2, 100, None, 1))
+
+
+def test_unpack5_rows_all_alignments():
+    """elx_unpack5_rows -- the 5-bit transport of amino-acid alignments (8 sites per 5 bytes): ragged lengths, every
+    destination alignment, state codes and characters, bytes around a row untouched, no read past the packed row."""
+    import ctypes as C
+
+    rng = np.random.default_rng(12)
+    aa = b"ACDEFGHIKLMNPQRSTVWY"
+    for rows, n, off, threads, lut in ((1, 0, 0, 1, None), (2, 1, 0, 1, None), (3, 9, 5, 2, aa), (4, 63, 0, 2, None), (4, 64, 32, 1, aa),
+                                       (5, 65, 1, 3, None), (3, 1000, 28, 4, aa), (2, 70001, 13, 8, None), (17, 513, 0, 0, aa)):
+        k = 20 if lut else 32
+        states = rng.integers(0, k, size=(rows, n), dtype=np.uint8)
+        nbytes = (5 * n + 7) // 8
+        bits = np.zeros((rows, nbytes * 8), dtype=np.uint8)
+        for b in range(5):
+            bits[:, b:5 * n:5] = (states >> b) & 1
+        exact = np.packbits(bits, axis=1, bitorder="little")
+        # rows packed back to back in an exactly sized allocation: any read past a row's bytes would leave the buffer
+        packed = np.ascontiguousarray(exact)
+        dpitch = n + off + 9
+        raw = np.full(rows * dpitch + 64, 0xEE, dtype=np.uint8)
+        base = (-raw.ctypes.data) % 32 + off
+        L.check(L.lib().elx_unpack5_rows(C.c_void_p(packed.ctypes.data), nbytes, C.c_void_p(raw.ctypes.data + base), dpitch, rows, n, lut, threads))
+        want = np.full_like(raw, 0xEE)
+        ref = states if lut is None else np.frombuffer(lut, dtype=np.uint8)[states]
+        for r in range(rows):
+            want[base + r * dpitch: base + r * dpitch + n] = ref[r]
+        assert np.array_equal(raw, want), (rows, n, off, threads)
+    with pytest.raises(L.ElxError):
+        L.check(L.lib().elx_unpack5_rows(C.c_void_p(packed.ctypes.data), 1, C.c_void_p(raw.ctypes.data), 100, 2, 100, None, 1))

@@ -424,6 +424,36 @@ def test_host_buffer_call_packed_transport_is_byte_identical(keep_internal, monk
         assert np.array_equal(host.numpy(), plain[0])
 
 
+@pytest.mark.parametrize("keep_internal", [False, True])
+def test_host_buffer_call_5bit_transport_protein(keep_internal, monkeypatch):
+    """Amino-acid alignments cross PCIe at 5 bits per site (k_pack5 / unpack5_rows): byte-identical to the 1-byte transport,
+    for elx_simulate (with components and internal states) and for the FASTA image."""
+    model = model_case("lg_g4")
+    tree = tree_from_file("Newick.tree")
+    nsites = (1 << 20) + 777
+    names = tree.leaf_names()
+    alphabet = om.ALPHABET_CHARS[model[4]]
+    with make_sim(model, tree) as sim:
+        monkeypatch.setenv("ELX_PACKED_D2H", "0")
+        plain = sim.simulate(9, nsites, site0=5, want_comps=True, keep_internal=keep_internal)
+        fasta0 = sim.simulate_fasta(9, nsites, names, alphabet)[0] if not keep_internal else None
+        rows = tree.n_leaves + (tree.n_nodes if keep_internal else 0)
+        for threads in ("1", "6"):
+            monkeypatch.setenv("ELX_PACKED_D2H", "1")
+            monkeypatch.setenv("ELX_HOST_THREADS", threads)
+            b1 = sim.d2h_bytes
+            packed = sim.simulate(9, nsites, site0=5, want_comps=True, keep_internal=keep_internal)
+            moved = sim.d2h_bytes - b1
+            assert np.array_equal(plain[0], packed[0]) and np.array_equal(plain[1], packed[1])
+            if keep_internal:
+                assert np.array_equal(plain[2], packed[2])
+            assert moved < 0.63 * nsites * rows + 4 * nsites + (1 << 16)
+        if not keep_internal:
+            assert plain[0].max() == 19
+            assert sim.simulate_fasta(9, nsites, names, alphabet)[0] == fasta0
+            assert fasta0 == om.sequences_to_fasta(names, sim.simulate(9, nsites)[0], model[4])
+
+
 @pytest.mark.parametrize("name", ["jc", "hky_g4", "mixture_dna"])
 def test_freerun_chi_square_vs_exact_pattern_probabilities(name):
     """Free-running output vs exact Felsenstein-pruning pattern probabilities on a 4-taxon tree (256 patterns)."""
