@@ -424,6 +424,26 @@ def test_host_buffer_call_packed_transport_is_byte_identical(keep_internal, monk
         assert np.array_equal(host.numpy(), plain[0])
 
 
+@pytest.mark.parametrize("name", ["hky_g4", "lg_g4"])
+def test_packed_transport_forced_on_small_and_ragged_calls(name, monkeypatch):
+    """ELX_PACKED_D2H=1 takes the packed path whatever the size: 1 site, sizes around the 32-site packing group and the
+    65 536-site work unit, with components and internal states; FASTA too."""
+    model = model_case(name)
+    tree = tree_from_file("Newick.tree")
+    names = tree.leaf_names()
+    alphabet = om.ALPHABET_CHARS[model[4]]
+    with make_sim(model, tree) as sim:
+        for nsites in (1, 31, 32, 33, 4097, 65536, 65537, 131073):
+            monkeypatch.setenv("ELX_PACKED_D2H", "0")
+            plain = sim.simulate(3, nsites, site0=9, want_comps=True, keep_internal=True)
+            fasta0 = sim.simulate_fasta(3, nsites, names, alphabet)[0]
+            monkeypatch.setenv("ELX_PACKED_D2H", "1")
+            packed = sim.simulate(3, nsites, site0=9, want_comps=True, keep_internal=True)
+            for a, b in zip(plain, packed):
+                assert np.array_equal(a, b), nsites
+            assert sim.simulate_fasta(3, nsites, names, alphabet)[0] == fasta0, nsites
+
+
 @pytest.mark.parametrize("keep_internal", [False, True])
 def test_host_buffer_call_5bit_transport_protein(keep_internal, monkeypatch):
     """Amino-acid alignments cross PCIe at 5 bits per site (k_pack5 / unpack5_rows): byte-identical to the 1-byte transport,
