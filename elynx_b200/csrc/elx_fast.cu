@@ -61,8 +61,11 @@ struct Lay {
   static constexpr int A = AA ? 5 : 2;
 };
 
-template <int ROUNDS, int LAY, int THREADS, int R>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) k2_tiled(FastArgs fa) {
+// PW: a dedicated producer warp (thread THREADS of a THREADS + 32 CTA) keeps the ring full and the consumer warps
+// release a stage buffer one by one (`empty` mbarriers) -- no CTA barrier in the node loop, as in k2_quad_tiled.
+// !PW: thread 0 refills a buffer after a CTA barrier per stage.
+template <int ROUNDS, int LAY, int THREADS, int R, bool PW>
+__global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 1) k2_tiled(FastArgs fa) {
   using L = Lay<LAY>;
   constexpr int NREG = L::NREG;
   constexpr bool AA = L::AA;
@@ -75,17 +78,37 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) k2_tiled(Fast
   const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
   constexpr uint32_t slot_stride = THREADS * R * 16u;  // slot stack [slot][round][thread] x 16 B
 
+  uint64_t *empty_bar = full_bar + MAX_NSTAGE;              // [nstage] (PW): every consumer warp is done with the buffer
   if (tid == 0) {
-    for (int i = 0; i < nstage; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+    for (int i = 0; i < nstage; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      if (PW) mbar_init(smem_u32(&empty_bar[i]), THREADS / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   __syncthreads();
+  // (the warp index through a shuffle: ptxas then knows the branch is warp-uniform and keeps uniform-register
+  // addressing in the consumer loop)
+  if (PW && __shfl_sync(0xffffffffu, tid >> 5, 0) >= THREADS / 32) {
+    if (tid == THREADS) {
+      int pbuf = 0;
+      uint32_t pphase = 1;  // the first pass over the ring finds every buffer free
+      for (int st = 0; st < fa.n_stages; ++st) {
+        if (st >= nstage) mbar_wait_backoff(smem_u32(&empty_bar[pbuf]), pphase, 128);
+        mbar_expect_tx(smem_u32(&full_bar[pbuf]), (uint32_t)fa.stage_bytes);
+        tma_bulk_g2s(stage_smem + (uint32_t)(pbuf * fa.stage_bytes), fa.ftab + (size_t)st * fa.stage_bytes, (uint32_t)fa.stage_bytes,
+                     smem_u32(&full_bar[pbuf]));
+        if (++pbuf == nstage) { pbuf = 0; pphase ^= 1u; }
+      }
+    }
+    return;
+  }
   // Fill the ring: stages 0..nstage-1.  Refills happen at the end of each stage, after the CTA barrier that
   // retires the buffer, in straight-line code.  (Measured: per-warp release with an in-band producer loop was no
   // faster, and any data-dependent loop under `tid == 0` makes ptxas drop uniform-register addressing for the whole
   // node loop, which costs one extra ALU-pipe IADD3 per draw.)
-  if (tid == 0) {
+  if (!PW && tid == 0) {
     for (int i = 0; i < nstage && i < fa.n_stages; ++i) {
       mbar_expect_tx(smem_u32(&full_bar[i]), (uint32_t)fa.stage_bytes);
       tma_bulk_g2s(stage_smem + (uint32_t)(i * fa.stage_bytes), fa.ftab + (size_t)i * fa.stage_bytes, (uint32_t)fa.stage_bytes,
@@ -302,8 +325,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) k2_tiled(Fast
       if (reload) reg_slot = src;
       if (dst >= 0) reg_slot = dst;
     }
-    __syncthreads();  // every warp is done with this stage buffer
-    if (tid == 0 && st + nstage < fa.n_stages) {
+    if (PW) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[buf]));
+    } else {
+      __syncthreads();  // every warp is done with this stage buffer
+    }
+    if (!PW && tid == 0 && st + nstage < fa.n_stages) {
       fence_async_smem();
       mbar_expect_tx(smem_u32(&full_bar[buf]), (uint32_t)fa.stage_bytes);
       tma_bulk_g2s(sbuf, fa.ftab + (size_t)(st + nstage) * fa.stage_bytes, (uint32_t)fa.stage_bytes, smem_u32(&full_bar[buf]));
@@ -408,13 +436,26 @@ void fast_tables_free(elx_handle *h) {
   h->fast = nullptr;
 }
 
-template <int ROUNDS, int LAY, int THREADS, int R>
-static cudaError_t launch_tiled(const FastArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(k2_tiled<ROUNDS, LAY, THREADS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int ROUNDS, int LAY, int THREADS, int R, bool PW>
+static cudaError_t launch_tiled_pw(const FastArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(k2_tiled<ROUNDS, LAY, THREADS, R, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   unsigned blocks = (unsigned)((groups + (int64_t)THREADS * R - 1) / ((int64_t)THREADS * R));
-  k2_tiled<ROUNDS, LAY, THREADS, R><<<blocks, THREADS, smem, stream>>>(fa);
+  k2_tiled<ROUNDS, LAY, THREADS, R, PW><<<blocks, THREADS + (PW ? 32 : 0), smem, stream>>>(fa);
   return cudaGetLastError();
+}
+
+template <int ROUNDS, int LAY, int THREADS, int R>
+static cudaError_t launch_tiled(const FastArgs &fa, int64_t groups, size_t smem, cudaStream_t stream) {
+  // Measured (B200, 10 rounds): the producer warp is +37 % for the big-mixture layout (cfg4, C60: 2.90 -> 3.98e11 cells/s;
+  // one 77 KB branch per stage, the CTA barrier was a third of all stall cycles) and -6 ... -11 % for the small-table
+  // layouts (cfg3 / cfg5 / node-by-node DNA: 5 CTAs of 128 threads per SM, where a fifth warp per CTA costs more than the
+  // barrier), so only LAY 2 uses it.  ELX_FAST_PRODUCER=0 switches it off for A/B runs.
+  if (LAY == 2) {
+    static const bool pw = [] { const char *e = getenv("ELX_FAST_PRODUCER"); return e ? atoi(e) != 0 : true; }();
+    if (pw) return launch_tiled_pw<ROUNDS, LAY, THREADS, R, LAY == 2>(fa, groups, smem, stream);
+  }
+  return launch_tiled_pw<ROUNDS, LAY, THREADS, R, false>(fa, groups, smem, stream);
 }
 
 template <int ROUNDS>

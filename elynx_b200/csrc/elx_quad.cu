@@ -265,21 +265,6 @@ __device__ __forceinline__ uint32_t entry_addr(uint32_t idx, uint32_t entry_byte
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(idx), "r"(entry_bytes), "r"(base));
   return d;
 }
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
-  for (;;) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    if (ok) return;
-    __nanosleep(ns);
-  }
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 // Stage header of the tiled kernel (32 bytes in front of the record's rows), decoded on the host so that the loop
 // spends no instruction on it: out[k] >= 0: leaf row; out[k] = 0x80000000 | byte offset of the slot: internal frontier
 // node; out[k] = 0xffffffff: absent.
@@ -423,7 +408,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) k2_quad_tiled(QuadArgs fa) {
   }
   __syncthreads();
 
-  if (tid >= THREADS) {
+  if (__shfl_sync(0xffffffffu, tid, 0) >= THREADS) {  // (through a shuffle: provably warp-uniform for ptxas)
     // producer warp: one lane keeps the ring full
     if (tid == THREADS) {
       int buf = 0;
