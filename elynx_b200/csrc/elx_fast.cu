@@ -450,7 +450,8 @@ static cudaError_t launch_tiled(const FastArgs &fa, int64_t groups, size_t smem,
   // Measured (B200, 10 rounds): the producer warp is +37 % for the big-mixture layout (cfg4, C60: 2.90 -> 3.98e11 cells/s;
   // one 77 KB branch per stage, the CTA barrier was a third of all stall cycles) and -6 ... -11 % for the small-table
   // layouts (cfg3 / cfg5 / node-by-node DNA: 5 CTAs of 128 threads per SM, where a fifth warp per CTA costs more than the
-  // barrier), so only LAY 2 uses it.  ELX_FAST_PRODUCER=0 switches it off for A/B runs.
+  // barrier; at a register budget that keeps 5 CTAs of 160 threads resident, 72 registers, still -5 % / -2.5 %), so only
+  // LAY 2 uses it.  ELX_FAST_PRODUCER=0 switches it off for A/B runs.
   if (LAY == 2) {
     static const bool pw = [] { const char *e = getenv("ELX_FAST_PRODUCER"); return e ? atoi(e) != 0 : true; }();
     if (pw) return launch_tiled_pw<ROUNDS, LAY, THREADS, R, LAY == 2>(fa, groups, smem, stream);
