@@ -1037,6 +1037,27 @@ struct TransportSync {
 constexpr int64_t UNPACK_COLS = 65536;  // sites per work unit of the unpack threads
 }  // namespace
 
+// Unpack threads of a host-buffer call: all cores but three (the calling thread feeds the streams, the waiter wakes per
+// chunk, the driver has threads of its own); ELX_HOST_THREADS when several processes share a box.
+static int transport_threads() {
+  int nt = (int)std::thread::hardware_concurrency() - 3;
+  if (const char *e = getenv("ELX_HOST_THREADS")) nt = atoi(e);
+  return std::max(1, std::min(nt, 32));
+}
+
+// Packed or plain?  ELX_PACKED_D2H forces either.  Otherwise: from 8 MB of result on (below, the thread start-up is not
+// worth it); the 2-bit form always (ahead even with 3 threads per GPU on an 8-GPU box: 1.00e11 against 8.7e10 cells/s);
+// the 5-bit form only with >= 8 unpack threads -- it moves 5/8 of the bytes over PCIe but the host then reads them and
+// stores the result, 2.25 bytes of host memory traffic per cell against 1 for the DMA alone, and the GPUs of a box share
+// the host's memory system (8 GPUs, 3 threads each, cfg3: 358 ms packed against ~280 ms plain; 1 GPU, 13 threads: 146
+// against 192 ms).
+static bool want_packed_transport(const elx_handle *h, int64_t cells) {
+  if (h->K > 32) return false;
+  if (const char *e = getenv("ELX_PACKED_D2H")) return atoi(e) != 0;
+  if (cells < ((int64_t)8 << 20)) return false;
+  return h->K <= 4 || transport_threads() >= 8;
+}
+
 // leaves / internal: base pointers; row r of a matrix starts at base + off[r].  lut: nullptr = state codes, else the
 // alphabet (FASTA sequence lines; 4 characters for the 2-bit form, 32 for the 5-bit form).
 static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves,
@@ -1149,9 +1170,7 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   // all cores but three (this thread feeds the streams, the waiter wakes per chunk, the driver has threads of its own);
   // waits are blocking: spinning
   // workers were measured to starve the dispatcher (16 spinning threads on 16 cores: 160 ms for cfg2, 8: 122 ms)
-  int nt = (int)std::thread::hardware_concurrency() - 3;
-  if (const char *e = getenv("ELX_HOST_THREADS")) nt = atoi(e);
-  nt = std::max(1, std::min(nt, 32));
+  const int nt = transport_threads();
   const bool debug = getenv("ELX_TRANSPORT_DEBUG") != nullptr;  // prints where the call's time went
   const auto t_start = std::chrono::steady_clock::now();
   auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -1278,10 +1297,7 @@ static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int
   if (rc) return rc;
   if (nsites == 0) return 0;
   {
-    // 2-bit transport: worth its thread start-up from a few MB of result on
-    const char *e = getenv("ELX_PACKED_D2H");
-    const bool want = e ? atoi(e) != 0 : (int64_t)(h->T + (internal ? h->N : 0)) * nsites >= ((int64_t)8 << 20);
-    if (!injected && h->K <= 32 && want) {
+    if (!injected && want_packed_transport(h, (int64_t)(h->T + (internal ? h->N : 0)) * nsites)) {
       std::vector<int64_t> lo(h->T), io(internal ? h->N : 0);
       for (int t = 0; t < h->T; ++t) lo[t] = t * lp;
       for (size_t n = 0; n < io.size(); ++n) io[n] = (int64_t)n * ip;
@@ -1484,11 +1500,9 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
   int64_t need = elx_fasta_size(h, names, total_sites);
   if (need < 0 || out_capacity < need) return fail(h, ELX_E_INVALID, "simulate_fasta: output buffer too small");
   {
-    // <= 4 letters: sequence lines cross PCIe at 2 bits per character and are expanded to characters by host threads, the
+    // sequence lines cross PCIe at 2 / 5 bits per character and are expanded to characters by host threads, the
     // `>name` lines are written here (same bytes as K3 writes on the device)
-    const char *e = getenv("ELX_PACKED_D2H");
-    const bool want = e ? atoi(e) != 0 : (int64_t)h->T * total_sites >= ((int64_t)8 << 20);
-    if (h->K <= 32 && want && total_sites > 0) {
+    if (total_sites > 0 && want_packed_transport(h, (int64_t)h->T * total_sites)) {
       if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
       std::vector<int64_t> seq_off(h->T);
       int64_t pos = 0;
