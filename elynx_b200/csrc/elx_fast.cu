@@ -50,6 +50,7 @@ struct FastArgs {
   SimArgs s;
   const uint8_t *ftab;
   int tb, stage_bytes, n_stages, nps, nstage;
+  uint32_t two;  // = 2, as a launch constant: `w * two` is an IMAD on the FMA pipe, `w << 1` a shift on the busier ALU pipe
 };
 
 template <int LAY>
@@ -239,6 +240,13 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
           // into a 3-input IADD3 per draw instead of using [R + UR] addressing.
           uint32_t aA = ((w[pr] & L::JMASK) << 1) | offA;
           uint32_t aB = (((w[pr] >> 16) & L::JMASK) << 1) | offB;
+          if (LAY == 1) {
+            // both entry addresses in one 3-input logic op on the packed 16-bit lanes: the row offsets are multiples of
+            // 64 (bits 1..5 free), bit 15 of the low draw leaks into bit 0 of the high lane and is masked
+            const uint32_t a2 = ((w[pr] * fa.two) & 0x003e003eu) | par[r][pr];
+            aA = a2 & 0xffffu;
+            aB = a2 >> 16;
+          }
 #ifdef ELX_DEBUG_BOUNDS  // compute-sanitizer is closed on the GPU pool: self-check every shared-memory table access
           if (aA + 2 > (uint32_t)fa.tb || aB + 2 > (uint32_t)fa.tb || (aA & 1) || (aB & 1)) atomicExch(a.error_flag, -7);
 #endif
@@ -479,6 +487,7 @@ int fast_simulate(elx_handle *h, const SimArgs &a, int *used) {
   fa.n_stages = ft->n_stages;
   fa.nps = ft->nps;
   fa.nstage = ft->nstage;
+  fa.two = 2u;
   int64_t g0 = a.site0 >> 4, g1 = (a.site0 + a.nsites + 15) >> 4;
   cudaError_t e = h->rounds == 7 ? launch_kind<7>(ft, fa, g1 - g0, h->stream) : launch_kind<10>(ft, fa, g1 - g0, h->stream);
   if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("k2_tiled launch: ") + cudaGetErrorString(e));
