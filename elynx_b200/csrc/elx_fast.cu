@@ -15,7 +15,9 @@
 // Layouts (template parameter LAY):
 //   0  DNA      K = 4,  KP = 4,  C <= 8: per-site byte = comp*32 + state*8 = byte offset of the table row (4 packed regs)
 //   1  protein  K <= 32, KP = 32, C*K*64 <= 65535: per-site 16-bit lane = (comp*K + state)*64 = row byte offset (8 regs)
-//   2  big mix  K <= 32, KP = 32, C*K <= 65535:   per-site 16-bit lane = comp*K + state (row index); the rows of ONE
+//   2  big mix  K <= 32, KP = 32, C*K*32 <= 65535: per-site 16-bit lane = (comp*K + state)*32 = first entry index of the
+//               row (bits 0..4 free for the column, so both draws of a Philox word get their index in one logic op);
+//               the rows of ONE
 //               branch fill a whole stage (e.g. C60: 76.8 KB), so a CTA is 512 threads (8192 sites) to amortise the
 //               table stream, 2 stages, 1 CTA per SM.
 #include <cstdint>
@@ -141,9 +143,9 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
       const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag,
                                                  (uint64_t)sbase[r] + i, key.x, key.y);
       const int c = (int)(cr & 0xffffu), root = (int)(cr >> 16);
-      if (LAY == 2) {
-        cbase[r][i >> 1] |= (uint32_t)(c * a.K) << (16 * (i & 1));
-        par[r][i >> 1] |= (uint32_t)(c * a.K + root) << (16 * (i & 1));
+      if (LAY == 2) {  // lanes hold the first ENTRY index of the row, row * 32 (< 65536: the table fits shared memory)
+        cbase[r][i >> 1] |= (uint32_t)(c * a.K * 32) << (16 * (i & 1));
+        par[r][i >> 1] |= (uint32_t)((c * a.K + root) * 32) << (16 * (i & 1));
       } else if (LAY == 1) {
         cbase[r][i >> 1] |= (uint32_t)(c * a.K * 64) << (16 * (i & 1));
         par[r][i >> 1] |= (uint32_t)((c * a.K + root) * 64) << (16 * (i & 1));
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
       for (int q = 0; q < 4; ++q) {
         uint32_t lo = par[r][2 * q] - cbase[r][2 * q], hi = par[r][2 * q + 1] - cbase[r][2 * q + 1];  // state lanes
         if (LAY == 1) { lo >>= 6; hi >>= 6; }
+        if (LAY == 2) { lo >>= 5; hi >>= 5; }
         b[q] = __byte_perm(lo, hi, 0x6420u);
       }
       sts_v4(slot_base[r], make_uint4(b[0], b[1], b[2], b[3]));
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
           const uint4 v = lds_v4(slot_base[r] + (uint32_t)src * slot_stride);
           if (AA) {
             const uint32_t b[4] = {v.x, v.y, v.z, v.w};
-            constexpr uint32_t scale = LAY == 1 ? 64u : 1u;
+            constexpr uint32_t scale = LAY == 1 ? 64u : 32u;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // state bytes -> 16-bit lanes -> packed row values
               par[r][2 * q] = __byte_perm(b[q], 0u, 0x4140u) * scale + cbase[r][2 * q];
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
           if (AA) {
             offA = par[r][pr] & 0xffffu;
             offB = par[r][pr] >> 16;
-            if (LAY == 2) { offA <<= 6; offB <<= 6; }  // row index -> row byte offset
+            if (LAY == 2) { offA <<= 1; offB <<= 1; }  // entry index -> byte offset (replaced below)
           } else {
             offA = __byte_perm(par[r][pr >> 1], 0u, 0x4440u | ((pr & 1) * 2));
             offB = __byte_perm(par[r][pr >> 1], 0u, 0x4440u | ((pr & 1) * 2 + 1));
@@ -246,6 +249,13 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
             const uint32_t a2 = ((w[pr] * fa.two) & 0x003e003eu) | par[r][pr];
             aA = a2 & 0xffffu;
             aB = a2 >> 16;
+          }
+          if (LAY == 2) {
+            // the lanes are entry indices with bits 0..4 free: index | j in one logic op for both draws, then two
+            // multiply-adds (FMA pipe) turn them into byte addresses
+            const uint32_t i2 = (w[pr] & 0x001f001fu) | par[r][pr];
+            aA = (i2 & 0xffffu) * fa.two;
+            aB = (i2 >> 16) * fa.two;
           }
 #ifdef ELX_DEBUG_BOUNDS  // compute-sanitizer is closed on the GPU pool: self-check every shared-memory table access
           if (aA + 2 > (uint32_t)fa.tb || aB + 2 > (uint32_t)fa.tb || (aA & 1) || (aB & 1)) atomicExch(a.error_flag, -7);
@@ -287,8 +297,8 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
               if (((tt >> sh) & 0xffffu) < L::TIE) {
                 const uint32_t x16 = (ww >> sh) & 0xffffu, lane = (oo >> sh) & 0xffffu, j = x16 & KPm1;
                 // lane -> row byte offset and row index (= comp*K + state); e16/qlo index = (node*C*K + row)*KP + j
-                const uint32_t off = LAY == 2 ? lane << 6 : lane;
-                const uint32_t row = LAY == 2 ? lane : (LAY == 1 ? lane >> 6 : lane >> 3);
+                const uint32_t off = LAY == 2 ? lane << 1 : lane;
+                const uint32_t row = LAY == 2 ? lane >> 5 : (LAY == 1 ? lane >> 6 : lane >> 3);
                 const uint32_t e = lds_u16(tbl + off + 2u * j);
                 const uint64_t sg = (uint64_t)sbase[r] + 2 * pr + hh;
                 const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node, TAG_REFINE), key);
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(THREADS + (PW ? 32 : 0), THREADS == 128 ? 4 : 
           o.z = __byte_perm(c2[4], c2[5], 0x6420u) & SM;
           o.w = __byte_perm(c2[6], c2[7], 0x6420u) & SM;
           if (dst >= 0) {
-            constexpr uint32_t scale = LAY == 1 ? 64u : 1u;
+            constexpr uint32_t scale = LAY == 1 ? 64u : 32u;
 #pragma unroll
             for (int q = 0; q < 8; ++q) par[r][q] = (c2[q] & 0x001f001fu) * scale + cbase[r][q];
             sts_v4(slot_base[r] + (uint32_t)dst * slot_stride, o);
@@ -379,7 +389,7 @@ int fast_tables_build(elx_handle *h) {
     kind = 1; tb = h->C * 32;
   } else if (h->KP == 32 && (int64_t)h->C * h->K * 64 <= 65535) {
     kind = 2; tb = h->C * h->K * 64;
-  } else if (h->KP == 32 && (int64_t)h->C * h->K <= 65535) {
+  } else if (h->KP == 32 && (int64_t)h->C * h->K * 32 <= 65535) {
     kind = 3; tb = h->C * h->K * 64;
   }
   if (kind) {
