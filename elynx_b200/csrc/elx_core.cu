@@ -1041,7 +1041,12 @@ constexpr int64_t UNPACK_COLS = 65536;  // sites per work unit of the unpack thr
 // chunk, the driver has threads of its own); ELX_HOST_THREADS when several processes share a box.
 static int transport_threads() {
   int nt = (int)std::thread::hardware_concurrency() - 3;
-  if (const char *e = getenv("ELX_HOST_THREADS")) nt = atoi(e);
+  if (const char *e = getenv("ELX_HOST_THREADS")) {
+    nt = atoi(e);
+  } else if (const char *w = getenv("LOCAL_WORLD_SIZE")) {  // torchrun: the ranks of this box share its cores
+    const int ranks = atoi(w);
+    if (ranks > 1) nt /= ranks;
+  }
   return std::max(1, std::min(nt, 32));
 }
 

@@ -243,8 +243,8 @@ int elx_examine(const uint8_t *states, int64_t pitch, int32_t n_sequences, int64
 int64_t elx_launch_count(const elx_handle *h);
 /* Bytes the host-buffer calls of this handle (elx_simulate, elx_simulate_injected) have copied device -> host so far.
  * Alignments over <= 4 states cross PCIe packed to 2 bits per site, over <= 32 states to 5 bits, and are expanded into the
- * caller's buffer by host threads (ELX_HOST_THREADS, default: all cores but three, at most 32; ELX_PACKED_D2H=0 turns the
- * packed transport off). */
+ * caller's buffer by host threads (ELX_HOST_THREADS, default: all cores but three -- divided by LOCAL_WORLD_SIZE under
+ * torchrun --, at most 32; ELX_PACKED_D2H=0 turns the packed transport off). */
 int64_t elx_d2h_bytes(const elx_handle *h);
 /* The host half of that transport, exported for tests and for callers that keep packed alignments: expands a 2-bit packed
  * matrix (site 4i+k of a row in bits 2k..2k+1 of byte i) to one byte per site -- state codes 0..3, or lut4[state] when a
