@@ -43,7 +43,7 @@ class elx_tree(C.Structure):
 
 
 class elx_opts(C.Structure):
-    _fields_ = [("device", C.c_int32), ("philox_rounds", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("device", C.c_int32), ("philox_rounds", C.c_int32), ("flags", C.c_int32), ("n_devices", C.c_int32)]
 
 
 class elx_examine_result(C.Structure):
@@ -66,6 +66,9 @@ SIGNATURES = {
     "elx_destroy": (None, [_VP]),
     "elx_tree_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
     "elx_tree_pair_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
+    "elx_n_devices": (_I32, [_VP]),
+    "elx_shard_range": (C.c_int, [_I64, _I32, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
+    "elx_last_kernel": (C.c_char_p, [_VP]),
     "elx_n_leaves": (_I32, [_VP]),
     "elx_n_nodes": (_I32, [_VP]),
     "elx_n_states": (_I32, [_VP]),

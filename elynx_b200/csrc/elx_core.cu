@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -607,9 +608,10 @@ static int check_error_flag(elx_handle *h) {
   if (flag != 0) {
     int zero = 0;
     cudaMemcpyAsync(h->d_error_flag, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream);
-    char buf[128];
-    snprintf(buf, sizeof buf, "categorical: bad weights! (draw site %d)", flag);
-    return fail(h, ELX_E_BAD_WEIGHTS, buf);
+    std::string what = flag == h->N + 1 ? "the component draw" : flag == h->N + 2 ? "the root-state draw"
+                       : flag >= 1 && flag <= h->N ? "the draw at node " + std::to_string(flag - 1) + " (preorder index)"
+                                                   : "kernel self-check " + std::to_string(flag);
+    return fail(h, ELX_E_BAD_WEIGHTS, "categorical: bad weights! (" + what + ")");
   }
   return 0;
 }
@@ -634,7 +636,9 @@ int elx_version(void) { return 100; }
 
 const char *elx_last_error(const elx_handle *h) { return h ? h->last_error.c_str() : g_last_error.c_str(); }
 
-int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opts, elx_handle **out) {
+// One handle on ONE device: eigensystems, H2D of model + tree, K1, walk programs.  device_override >= 0 replaces
+// opts->device (the peers of a multi-device handle).
+static int create_on_device(const elx_model *model, const elx_tree *tree, const elx_opts *opts, int device_override, elx_handle **out) {
   if (!out) return fail(nullptr, ELX_E_INVALID, "elx_create: out is NULL");
   *out = nullptr;
   if (!model || !tree) return fail(nullptr, ELX_E_INVALID, "elx_create: model/tree is NULL");
@@ -697,7 +701,7 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, ELX_E_CUDA, "no CUDA device available (elynx_b200 has no CPU fallback)");
-  int dev = opts && opts->device >= 0 ? opts->device : -1;
+  int dev = device_override >= 0 ? device_override : (opts && opts->device >= 0 ? opts->device : -1);
   if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, ELX_E_CUDA, "cudaGetDevice failed"); }
   if (dev >= ndev) return fail(nullptr, ELX_E_INVALID, "opts: device ordinal out of range");
 
@@ -767,6 +771,65 @@ int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opt
   return 0;
 }
 
+
+// Multi-device handles (opts->n_devices): the reference's *Par calls parallelise INSIDE the call
+// (MarkovProcessAlongTree.hs:109-125, :221-262: one chunk per capability); here one handle drives n_devices GPUs -- a full
+// copy of the tables per device, one host thread + stream per device in the host-buffer calls.
+int elx_create(const elx_model *model, const elx_tree *tree, const elx_opts *opts, elx_handle **out) {
+  if (!out) return fail(nullptr, ELX_E_INVALID, "elx_create: out is NULL");
+  *out = nullptr;
+  int want = opts ? opts->n_devices : 0;
+  if (want == 0 || want == 1) return create_on_device(model, tree, opts, -1, out);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, ELX_E_CUDA, "no CUDA device available (elynx_b200 has no CPU fallback)");
+  int dev0 = opts->device >= 0 ? opts->device : 0;
+  if (want < 0) want = ndev - dev0;  // all visible devices from `device` on
+  if (want < 1 || dev0 + want > ndev)
+    return fail(nullptr, ELX_E_INVALID, "opts: n_devices = " + std::to_string(opts->n_devices) + " from device " + std::to_string(dev0) +
+                                            " exceeds the " + std::to_string(ndev) + " visible device(s)");
+  std::vector<elx_handle *> hs((size_t)want, nullptr);
+  std::vector<int> rcs((size_t)want, 0);
+  std::vector<std::string> msgs((size_t)want);
+  std::vector<std::thread> th;
+  for (int d = 0; d < want; ++d)
+    th.emplace_back([&, d]() {
+      rcs[d] = create_on_device(model, tree, opts, dev0 + d, &hs[d]);
+      if (rcs[d]) msgs[d] = g_last_error;  // thread-local: carry it over to the caller's thread
+    });
+  for (auto &t : th) t.join();
+  for (int d = 0; d < want; ++d)
+    if (rcs[d]) {
+      const int rc = rcs[d];
+      const std::string m = msgs[d];
+      for (elx_handle *x : hs) elx_destroy(x);
+      return fail(nullptr, rc, m);
+    }
+  for (int d = 1; d < want; ++d) { hs[d]->is_peer = 1; hs[0]->peers.push_back(hs[d]); }
+  *out = hs[0];
+  return 0;
+}
+
+int32_t elx_n_devices(const elx_handle *h) { return h ? 1 + (int32_t)h->peers.size() : 0; }
+
+int elx_shard_range(int64_t nsites, int32_t n_shards, int32_t shard, int32_t align, int64_t *first, int64_t *count) {
+  if (nsites < 0 || n_shards < 1 || shard < 0 || shard >= n_shards || align < 1 || !first || !count)
+    return fail(nullptr, ELX_E_INVALID, "elx_shard_range: bad argument");
+  // getChunks (MarkovProcessAlongTree.hs:210-215): r chunks of q+1 sites, then n_shards - r chunks of q sites; inner
+  // boundaries rounded up to multiples of `align`
+  const int64_t q = nsites / n_shards, r = nsites % n_shards;
+  auto bound = [&](int k) -> int64_t {
+    if (k <= 0) return 0;
+    if (k >= n_shards) return nsites;
+    int64_t b = (int64_t)k * q + std::min<int64_t>(k, r);
+    b = (b + align - 1) / align * align;
+    return std::min(b, nsites);
+  };
+  *first = bound(shard);
+  *count = bound(shard + 1) - bound(shard);
+  return 0;
+}
+
 int elx_tree_walk_info(const elx_tree *tree, int32_t *n_leaves, int32_t *n_slots, int32_t *walk_nodes) {
   if (!tree || tree->n_nodes < 1 || !tree->parent || !tree->leaf_row) return fail(nullptr, ELX_E_INVALID, "tree: empty or NULL arrays");
   WalkProgram walk;
@@ -816,6 +879,8 @@ int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n
 
 void elx_destroy(elx_handle *h) {
   if (!h) return;
+  for (elx_handle *p : h->peers) elx_destroy(p);
+  h->peers.clear();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   fast_tables_free(h);
@@ -835,8 +900,19 @@ int32_t elx_n_states(const elx_handle *h) { return h ? h->K : 0; }
 int32_t elx_n_components(const elx_handle *h) { return h ? h->C : 0; }
 int32_t elx_alias_columns(const elx_handle *h) { return h ? h->KP : 0; }
 void *elx_stream(const elx_handle *h) { return h ? (void *)h->stream : nullptr; }
-int64_t elx_launch_count(const elx_handle *h) { return h ? h->launches : 0; }
-int64_t elx_d2h_bytes(const elx_handle *h) { return h ? h->d2h_bytes : 0; }
+int64_t elx_launch_count(const elx_handle *h) {
+  if (!h) return 0;
+  int64_t n = h->launches;
+  for (const elx_handle *p : h->peers) n += p->launches;
+  return n;
+}
+int64_t elx_d2h_bytes(const elx_handle *h) {
+  if (!h) return 0;
+  int64_t n = h->d2h_bytes;
+  for (const elx_handle *p : h->peers) n += p->d2h_bytes;
+  return n;
+}
+const char *elx_last_kernel(const elx_handle *h) { return h ? h->last_kernel.c_str() : ""; }
 
 int elx_ptables_get(elx_handle *h, double *out, int cumulative) {
   if (!h || !out) return fail(h, ELX_E_INVALID, "elx_ptables_get: NULL argument");
@@ -915,6 +991,7 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   if (h->rounds == 7) k2_freerun_generic<7><<<blocks, threads, 0, h->stream>>>(a);
   else k2_freerun_generic<10><<<blocks, threads, 0, h->stream>>>(a);
   h->launches++;
+  h->last_kernel = "k2_freerun_generic<" + std::to_string(h->rounds) + ">";
   CUDA_TRY(h, cudaGetLastError());
   return 0;
 }
@@ -1007,7 +1084,7 @@ void pin_release(uint8_t *p) {
   if (!p) return;
   {
     std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_free.size() < 2) {
+    if (g_pin_free.size() < 8) {  // one set per device of a multi-device call
       g_pin_free.push_back(p);
       return;
     }
@@ -1039,7 +1116,9 @@ constexpr int64_t UNPACK_COLS = 65536;  // sites per work unit of the unpack thr
 
 // Unpack threads of a host-buffer call: all cores but three (the calling thread feeds the streams, the waiter wakes per
 // chunk, the driver has threads of its own); ELX_HOST_THREADS when several processes share a box.
+static thread_local int g_thread_budget = 0;  // > 0: unpack threads of the host-buffer call running on this thread (multi-device calls divide the cores)
 static int transport_threads() {
+  if (g_thread_budget > 0) return g_thread_budget;
   int nt = (int)std::thread::hardware_concurrency() - 3;
   if (const char *e = getenv("ELX_HOST_THREADS")) {
     nt = atoi(e);
@@ -1286,6 +1365,15 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   waiter.join();
   for (auto &t : workers) t.join();
   workers.clear();
+  if (sync.abort_flag.load()) {  // the waiter gave up on a copy: parts of the caller's buffer were never written
+    cleanup();
+    return fail(h, ELX_E_CUDA, "packed transport: waiting for a device-to-host copy failed");
+  }
+  for (const PackedChunk &ch : chunks)
+    if (ch.done.load(std::memory_order_acquire) < ch.units) {
+      cleanup();
+      return fail(h, ELX_E_CUDA, "packed transport: a chunk was not unpacked completely");
+    }
   if (debug)
     fprintf(stderr, "[elx transport] %zu chunks, %d threads: first chunk ready %.1f ms, all issued %.1f ms, all copied %.1f ms, all unpacked %.1f ms; "
             "workers waited %.1f ms each on average\n", chunks.size(), nt, first_ready_us.load() / 1e3, t_issued, t_copied, since(t_start),
@@ -1370,8 +1458,45 @@ static int simulate_host_common(elx_handle *h, bool injected, uint64_t seed, int
   return check_error_flag(h);
 }
 
+// Multi-device handles: the site range is cut by the getChunks rule (elx_shard_range, boundaries on multiples of 64 sites),
+// one host thread per device runs the single-device path of its peer handle straight into the caller's buffers (column
+// offset = the shard's first site); the unpack threads are divided among the devices.  Sites are independent and every
+// draw is keyed on the global site index, so the bytes equal the single-device result.
+static int run_sharded(elx_handle *h, int64_t nsites, const std::function<int(elx_handle *, int64_t, int64_t)> &shard_call) {
+  const int nd = 1 + (int)h->peers.size();
+  const int budget = std::max(1, transport_threads() / nd);
+  std::vector<int> rcs((size_t)nd, 0);
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; ++d) {
+    int64_t f = 0, n = 0;
+    elx_shard_range(nsites, nd, d, 64, &f, &n);
+    if (n == 0) continue;
+    elx_handle *hd = d == 0 ? h : h->peers[(size_t)d - 1];
+    th.emplace_back([&rcs, &shard_call, d, hd, f, n, budget]() {
+      g_thread_budget = budget;
+      rcs[(size_t)d] = shard_call(hd, f, n);
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int d = 0; d < nd; ++d)
+    if (rcs[(size_t)d]) {
+      elx_handle *hd = d == 0 ? h : h->peers[(size_t)d - 1];
+      if (hd != h) return fail(h, rcs[(size_t)d], "device " + std::to_string(hd->device) + ": " + hd->last_error);
+      return rcs[(size_t)d];
+    }
+  return 0;
+}
+
 int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch,
                  int32_t *comps, uint8_t *internal, int64_t internal_pitch) {
+  if (h && !h->peers.empty() && nsites >= 4096) {
+    int rc = check_sim_args(h, site0, nsites, leaves, leaves_pitch, internal, internal_pitch);
+    if (rc) return rc;
+    return run_sharded(h, nsites, [&](elx_handle *hd, int64_t f, int64_t n) {
+      return simulate_host_common(hd, false, seed, site0 + f, nullptr, 0, n, leaves + f, leaves_pitch, comps ? comps + f : nullptr,
+                                  internal ? internal + f : nullptr, internal_pitch);
+    });
+  }
   return simulate_host_common(h, false, seed, site0, nullptr, 0, nsites, leaves, leaves_pitch, comps, internal, internal_pitch);
 }
 
@@ -1524,6 +1649,10 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
       uint8_t lut[32];
       memset(lut, '?', sizeof lut);
       memcpy(lut, alphabet, (size_t)h->K);
+      if (!h->peers.empty() && total_sites >= 4096)  // every device fills its columns of every sequence line
+        return run_sharded(h, total_sites, [&](elx_handle *hd, int64_t f, int64_t n) {
+          return simulate_host_packed(hd, seed, f, n, out + f, seq_off.data(), comps ? comps + f : nullptr, nullptr, nullptr, lut);
+        });
       return simulate_host_packed(h, seed, 0, total_sites, out, seq_off.data(), comps, nullptr, nullptr, lut);
     }
   }

@@ -502,6 +502,8 @@ int fast_simulate(elx_handle *h, const SimArgs &a, int *used) {
   cudaError_t e = h->rounds == 7 ? launch_kind<7>(ft, fa, g1 - g0, h->stream) : launch_kind<10>(ft, fa, g1 - g0, h->stream);
   if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("k2_tiled launch: ") + cudaGetErrorString(e));
   h->launches++;
+  h->last_kernel = "k2_tiled<" + std::to_string(h->rounds) + "," + std::to_string(ft->kind - 1) + "," + std::to_string(ft->threads) + "," +
+                   std::to_string(ft->rounds) + (ft->kind == 3 ? ",PW>" : ">");
   *used = 1;
   return 0;
 }

@@ -497,6 +497,8 @@ int pair_simulate(elx_handle *h, SimArgs &a, int *used) {
   }
   if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("pair kernel launch: ") + cudaGetErrorString(e));
   h->launches++;
+  h->last_kernel = std::string((pt->tiled && !a.internal && !(h->flags & ELX_FLAG_FORCE_GENERIC)) ? "k2_pair_tiled<" : "k2_pair_generic<") +
+                   std::to_string(h->rounds) + ">";
   *used = 1;
   return 0;
 }

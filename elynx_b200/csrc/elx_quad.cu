@@ -666,6 +666,9 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
   }
   if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("quad kernel launch: ") + cudaGetErrorString(e));
   h->launches++;
+  h->last_kernel = (qt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC))
+                       ? "k2_quad_tiled<" + std::to_string(h->rounds) + "," + std::to_string(qt->threads) + "," + std::to_string(qt->threads == 512 ? 1 : qt->minb) + ">"
+                       : "k2_quad_generic<" + std::to_string(h->rounds) + ">";
   *used = 1;
   return 0;
 }

@@ -29,9 +29,14 @@ struct elx_handle {
   void *pair = nullptr;
   // quad mode (K <= 4): one draw per cap of up to 4 frontier nodes, inner nodes summed out; owned by elx_quad.cu
   void *quad = nullptr;
+  // multi-device handles (elx_opts.n_devices > 1): the handle the caller holds is the primary, peers[] are full handles on
+  // the other devices (own stream, own tables); the host-buffer calls shard the site range over all of them
+  std::vector<elx_handle *> peers;
+  int is_peer = 0;
   int64_t launches = 0;
   int64_t d2h_bytes = 0;  // bytes the host-buffer calls moved device -> host so far
   std::string last_error;
+  std::string last_kernel;  // name of the simulation kernel the last elx_simulate*_device call launched (elx_last_kernel)
 };
 
 namespace elx {

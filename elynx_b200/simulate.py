@@ -33,7 +33,8 @@ class Simulator:
     alias tables and the compiled tree walk."""
 
     def __init__(self, weights, ds, es, tree, is_mixture: bool = True, device: int = -1, philox_rounds: int = 0,
-                 force_generic: bool = False, pade: bool = False, single_draws: bool = False, pair_draws: bool = False):
+                 force_generic: bool = False, pade: bool = False, single_draws: bool = False, pair_draws: bool = False,
+                 n_devices: int = 1):
         ds = np.ascontiguousarray(ds, dtype=np.float64)
         es = np.ascontiguousarray(es, dtype=np.float64)
         if ds.ndim == 1:
@@ -55,12 +56,13 @@ class Simulator:
         t = L.elx_tree(len(parent), parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
                        leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
         o = L.elx_opts(device, philox_rounds, (L.ELX_FLAG_FORCE_GENERIC if force_generic else 0) | (L.ELX_FLAG_PADE if pade else 0) |
-                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0) | (L.ELX_FLAG_PAIR_DRAWS if pair_draws else 0), 0)
+                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0) | (L.ELX_FLAG_PAIR_DRAWS if pair_draws else 0), n_devices)
         h = C.c_void_p()
         self._h = None
         L.check(L.lib().elx_create(C.byref(m), C.byref(t), C.byref(o), C.byref(h)))
         self._h = h
         self.n_states, self.n_components, self.is_mixture = k, c, bool(is_mixture)
+        self.n_devices = int(L.lib().elx_n_devices(h))  # host-buffer calls shard the site range over this many GPUs
         self.n_nodes = int(L.lib().elx_n_nodes(h))
         self.n_leaves = int(L.lib().elx_n_leaves(h))
         self.alias_columns = int(L.lib().elx_alias_columns(h))
@@ -98,6 +100,11 @@ class Simulator:
     @property
     def launch_count(self) -> int:
         return int(L.lib().elx_launch_count(self._h))
+
+    @property
+    def last_kernel(self) -> str:
+        """name of the simulation kernel the last device call launched (elx_last_kernel)"""
+        return (L.lib().elx_last_kernel(self._h) or b"").decode()
 
     @property
     def d2h_bytes(self) -> int:

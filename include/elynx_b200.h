@@ -75,7 +75,12 @@ typedef struct {
   int32_t device;        /* CUDA device ordinal; -1 = current device */
   int32_t philox_rounds; /* 0 = default (10) */
   int32_t flags;         /* ELX_FLAG_* */
-  int32_t reserved;
+  int32_t n_devices;     /* 0 or 1: one device.  N > 1: the handle drives devices device .. device+N-1 (device = -1: from 0);
+                            -1: every visible device from `device` on.  The reference's *Par calls parallelise inside the call
+                            (MarkovProcessAlongTree.hs:109-125, :221-262); so do elx_simulate / elx_simulate_fasta /
+                            elx_simulate_packed of such a handle: contiguous site ranges by the getChunks rule (:210-215), one
+                            host thread + stream per device, every device writing its columns of the caller's buffers.  The
+                            *_device entry points and the parity hooks address the first device only. */
 } elx_opts;
 
 #define ELX_FLAG_FORCE_GENERIC 1 /* always use the generic global-table kernel (cross-check of the tiled one) */
@@ -106,6 +111,12 @@ int elx_tree_walk_info(const elx_tree *tree, int32_t *n_leaves, int32_t *n_slots
  * leaf row of a / of b (-1: internal).  recs (optional) must hold 7 * n_nodes values (there are at most n_nodes records). */
 int elx_tree_pair_walk_info(const elx_tree *tree, int32_t *n_groups, int32_t *n_slots, int32_t *recs);
 
+/* number of devices the handle drives (elx_opts.n_devices resolved) */
+int32_t elx_n_devices(const elx_handle *h);
+/* Host-only: the site range of shard `shard` of `n_shards` over [0, nsites) -- getChunks c n (MarkovProcessAlongTree.hs:210-215:
+ * r = n mod c chunks of n div c + 1 sites, then chunks of n div c) with the inner boundaries rounded up to multiples of `align`
+ * (the multi-device calls use 64).  The shards tile [0, nsites) exactly for every alignment. */
+int elx_shard_range(int64_t nsites, int32_t n_shards, int32_t shard, int32_t align, int64_t *first, int64_t *count);
 int32_t elx_n_leaves(const elx_handle *h);
 int32_t elx_n_nodes(const elx_handle *h);
 int32_t elx_n_states(const elx_handle *h);
@@ -241,6 +252,9 @@ int elx_examine(const uint8_t *states, int64_t pitch, int32_t n_sequences, int64
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t elx_launch_count(const elx_handle *h);
+/* Name (with its template arguments) of the simulation kernel the last elx_simulate*_device call of this handle launched,
+ * e.g. "k2_quad_tiled<10,256,2>"; "" before the first call.  bench.py reports it next to every roofline figure. */
+const char *elx_last_kernel(const elx_handle *h);
 /* Bytes the host-buffer calls of this handle (elx_simulate, elx_simulate_injected) have copied device -> host so far.
  * Alignments over <= 4 states cross PCIe packed to 2 bits per site, over <= 32 states to 5 bits, and are expanded into the
  * caller's buffer by host threads (ELX_HOST_THREADS, default: all cores but three -- divided by LOCAL_WORLD_SIZE under

@@ -383,3 +383,36 @@ def test_unpack5_rows_all_alignments():
         assert np.array_equal(raw, want), (rows, n, off, threads)
     with pytest.raises(L.ElxError):
         L.check(L.lib().elx_unpack5_rows(C.c_void_p(packed.ctypes.data), 1, C.c_void_p(raw.ctypes.data), 100, 2, 100, None, 1))
+
+
+def test_shard_range_follows_get_chunks():
+    """elx_shard_range = getChunks (MarkovProcessAlongTree.hs:210-215) with aligned inner boundaries: tiles [0, n) exactly and
+    agrees with the Python restatement used by the torchrun path (elynx_b200.distributed.site_range) and with the oracle."""
+    import ctypes as C
+
+    import oracle.model as om
+    from elynx_b200 import _lib as L
+    from elynx_b200.distributed import site_range
+
+    lib = L.lib()
+    for n in (0, 1, 63, 64, 65, 1000, 4096, 10_000_000, 10_000_019, (1 << 40) + 5):
+        for shards in (1, 2, 3, 4, 7, 8):
+            for align in (1, 16, 64):
+                pos = 0
+                for k in range(shards):
+                    f, c = C.c_int64(), C.c_int64()
+                    assert lib.elx_shard_range(n, shards, k, align, C.byref(f), C.byref(c)) == 0
+                    assert (f.value, c.value) == site_range(k, shards, n, align=align)
+                    assert f.value == pos and c.value >= 0
+                    pos += c.value
+                assert pos == n
+            if n <= 10_000_019:
+                sizes = []
+                for k in range(shards):
+                    f, c = C.c_int64(), C.c_int64()
+                    lib.elx_shard_range(n, shards, k, 1, C.byref(f), C.byref(c))
+                    sizes.append(c.value)
+                assert sizes == om.get_chunks(shards, n)
+    f, c = C.c_int64(), C.c_int64()
+    assert lib.elx_shard_range(10, 0, 0, 1, C.byref(f), C.byref(c)) == L.ELX_E_INVALID
+    assert lib.elx_shard_range(10, 2, 2, 1, C.byref(f), C.byref(c)) == L.ELX_E_INVALID
