@@ -83,6 +83,7 @@ SIGNATURES = {
     "elx_quad_groups": (_I32, [_VP]),
     "elx_quad_get": (C.c_int, [_VP, _VP, _VP, _VP]),
     "elx_tree_quad_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
+    "elx_tree_duo_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
     "elx_simulate": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_synchronize": (C.c_int, [_VP]),

@@ -877,6 +877,21 @@ int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n
   return 0;
 }
 
+int elx_tree_duo_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs) {
+  if (!tree || tree->n_nodes < 1 || !tree->parent || !tree->leaf_row) return fail(nullptr, ELX_E_INVALID, "tree: empty or NULL arrays");
+  WalkProgram walk;
+  int T = 0;
+  std::string msg;
+  if (!compile_walk(tree->n_nodes, tree->parent, tree->leaf_row, walk, T, msg)) return fail(nullptr, ELX_E_INVALID, msg);
+  QuadProgram qp;
+  compile_quad_walk(tree->n_nodes, tree->parent, tree->leaf_row, qp, 2);
+  if (n_records) *n_records = (int32_t)qp.recs.size();
+  if (n_slots) *n_slots = qp.n_slots;
+  if (recs)
+    for (size_t g = 0; g < qp.recs.size(); ++g) quad_rec_to_ints(qp.recs[g], recs + g * ELX_QUAD_REC_INTS);
+  return 0;
+}
+
 void elx_destroy(elx_handle *h) {
   if (!h) return;
   for (elx_handle *p : h->peers) elx_destroy(p);

@@ -171,9 +171,10 @@ void compile_pair_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
   out.n_slots = high;
 }
 
-void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, QuadProgram &out) {
+void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, QuadProgram &out, int max_frontier) {
   const int N = n_nodes;
-  constexpr int W = 4, INF = 1 << 29;
+  constexpr int WMAX = 4, INF = 1 << 29;
+  const int W = max_frontier < 1 ? 1 : (max_frontier > WMAX ? WMAX : max_frontier);  // frontier nodes per cap (4: quad mode, 2: duo mode)
   std::vector<std::vector<int>> kids(N);
   for (int n = 1; n < N; ++n) kids[parent[n]].push_back(n);
   std::vector<int64_t> size(N, 1);
@@ -185,7 +186,7 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
   // when the open cap has w frontier nodes at or below v; nn[v][w]: how many nodes of the open cap lie at or below v.
   // w == 1 is either "v is a frontier node" (closed: v's own caps are counted) or, for a unary v, "v is summed out".
   struct Choice {
-    std::vector<int8_t> kw[W + 1];       // v summed out: frontier share of every kid (kids[] order)
+    std::vector<int8_t> kw[WMAX + 1];    // v summed out: frontier share of every kid (kids[] order)
     std::vector<int8_t> ckw;             // v closed: share and cap number of every kid (caps = runs of kids)
     std::vector<int32_t> cgrp;
     bool closed1 = true;                 // the w == 1 entry is the closed one
@@ -200,10 +201,10 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
     if (k.empty()) { C_(v, 1) = 0; N_(v, 1) = 1; continue; }
     // v summed out: all kids share the open cap
     if ((int)k.size() <= W) {
-      Part comb[W + 1];
+      Part comb[WMAX + 1];
       comb[0].cost = 0;
       for (size_t i = 0; i < k.size(); ++i) {
-        Part nx[W + 1];
+        Part nx[WMAX + 1];
         for (int w0 = 0; w0 <= W; ++w0) {
           if (comb[w0].cost >= INF) continue;
           for (int w = 1; w0 + w <= W; ++w) {
@@ -225,11 +226,11 @@ void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_r
     // star with 10^5 leaves.
     struct Step { int8_t prev, w; bool fresh; };  // how state s after kid i was reached
     std::vector<Step> steps((k.size() + 1) * (W + 1), Step{-1, 0, false});
-    int dcost[W + 1], dnodes[W + 1];
+    int dcost[WMAX + 1], dnodes[WMAX + 1];
     for (int s = 0; s <= W; ++s) { dcost[s] = INF; dnodes[s] = 0; }
     dcost[0] = 0;
     for (size_t i = 0; i < k.size(); ++i) {
-      int ncost[W + 1], nnodes[W + 1];
+      int ncost[WMAX + 1], nnodes[WMAX + 1];
       for (int s = 0; s <= W; ++s) { ncost[s] = INF; nnodes[s] = 0; }
       Step *st_i = &steps[(i + 1) * (W + 1)];
       for (int s0 = 0; s0 <= W; ++s0) {

@@ -78,7 +78,8 @@ struct QuadProgram {
 // Cuts the tree into the minimum number of caps (tree DP over the open cap's frontier size), orders the records depth
 // first with the heaviest frontier node last and assigns slots (slot 0 = the root states; a record reads src before it
 // writes dst, so a slot freed by a node's last cap is reused at once).  Expects arrays compile_walk accepted.
-void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, QuadProgram &out);
+// max_frontier = 2 gives the caps of duo mode (protein: 20 x 20 outcomes per draw, elx_duo.cu).
+void compile_quad_walk(int n_nodes, const int32_t *parent, const int32_t *leaf_row, QuadProgram &out, int max_frontier = 4);
 
 // Symmetric eigen-decomposition (cyclic Jacobi) of S = D^{1/2} Q D^{-1/2}, Q = setDiagonal(E diag(pi)).
 // Produces lambda[K], A = D^{-1/2} V and B = V^T D^{1/2} so that exp(Qt) = I + A diag(expm1(lambda t)) B.

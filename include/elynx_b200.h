@@ -161,6 +161,8 @@ int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16
 int32_t elx_quad_groups(const elx_handle *h);
 int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
 int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
+/* the same cut with at most TWO frontier nodes per cap: the records of duo mode (below) */
+int elx_tree_duo_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
 
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
  * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed); the result is a
