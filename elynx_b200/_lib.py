@@ -20,6 +20,7 @@ ELX_FLAG_FORCE_GENERIC = 1
 ELX_FLAG_PADE = 2
 ELX_FLAG_SINGLE_DRAWS = 4
 ELX_FLAG_PAIR_DRAWS = 8
+ELX_FLAG_EIGEN = 16
 ELX_QUAD_REC_INTS = 52
 
 

@@ -463,11 +463,15 @@ __global__ void k3_fasta_body(const uint8_t *__restrict__ leaves, int64_t pitch,
   }
 }
 
-// slice mode: [T][out_pitch] characters, no frame
-__global__ void k3_fasta_slice(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, const uint8_t *__restrict__ lut,
+// slice mode: [T][out_pitch] characters, no frame.  The alphabet travels in the kernel's parameter block: the call only
+// enqueues (no table upload, no host synchronisation), so a caller's batches overlap.
+struct FastaLut {
+  uint8_t c[64];
+};
+__global__ void k3_fasta_slice(const uint8_t *__restrict__ leaves, int64_t pitch, int64_t nsites, const FastaLut lut,
                                int K, uint8_t *__restrict__ out, int64_t out_pitch) {
   __shared__ __align__(8) uint8_t slut[64];
-  if (threadIdx.x < 64) slut[threadIdx.x] = threadIdx.x < K ? lut[threadIdx.x] : (uint8_t)'?';
+  if (threadIdx.x < 64) slut[threadIdx.x] = threadIdx.x < K ? lut.c[threadIdx.x] : (uint8_t)'?';
   __syncthreads();
   const bool small = K <= 8;
   const uint32_t lut_lo = reinterpret_cast<const uint32_t *>(slut)[0], lut_hi = reinterpret_cast<const uint32_t *>(slut)[1];
@@ -557,6 +561,20 @@ __global__ void k_pattern_counts(const uint8_t *__restrict__ leaves, int64_t pit
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+int ensure_pair_tables(elx_handle *h) {
+  if (!h->pair || h->pair_ready) return 0;
+  const int rc = pair_tables_build(h);
+  if (!rc) h->pair_ready = 1;
+  return rc;
+}
+
+int ensure_fast_tables(elx_handle *h) {
+  if (h->fast_ready) return 0;
+  const int rc = fast_tables_build(h);
+  if (!rc) h->fast_ready = 1;
+  return rc;
+}
+
 static int build_tables_from_p(elx_handle *h, bool have_p) {
   const int64_t rows = (int64_t)h->N * h->C * h->K;
   const int threads = 128;
@@ -576,11 +594,15 @@ static int build_tables_from_p(elx_handle *h, bool have_p) {
   k1_alias<<<blocks, threads, 0, h->stream>>>(rows, h->K, h->A, h->d_P, h->d_e16, h->d_qlo);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  int rc = fast_tables_build(h);
-  if (rc) return rc;
-  rc = pair_tables_build(h);
-  if (rc) return rc;
-  rc = quad_tables_build(h);
+  // Only the table family the handle's default call shape needs is built now: quad rows (K <= 4, leaves-only calls), else
+  // pair rows, else the node-by-node stage images.  The others follow on the first call that needs them (a K <= 4 call
+  // that keeps the internal states -> pair rows; elx_pair_get), see ensure_pair_tables / ensure_fast_tables.
+  h->pair_ready = 0;
+  h->fast_ready = 0;
+  int rc = 0;
+  if (h->quad) rc = quad_tables_build(h);
+  else if (h->pair) rc = ensure_pair_tables(h);
+  else rc = ensure_fast_tables(h);
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return 0;
@@ -676,7 +698,10 @@ static int create_on_device(const elx_model *model, const elx_tree *tree, const 
   // exchangeabilities, a zero stationary frequency) or ELX_FLAG_PADE is set, the general Pade path on
   // Q = setDiagonal(E diag pi) (RateMatrix.hs:87-103).
   std::vector<double> lambda((size_t)C * K), A((size_t)C * K * K), B((size_t)C * K * K), Qh;
-  bool use_pade = opts && (opts->flags & ELX_FLAG_PADE);
+  // Default: the Pade kernel (hmatrix expm's own algorithm: element-wise parity <= 1e-12 with the reference's tables on
+  // every branch length); ELX_FLAG_EIGEN selects the eigen form, which models with more than 32 states always take.
+  const int oflags = opts ? opts->flags : 0;
+  bool use_pade = (K <= 32 && !(oflags & ELX_FLAG_EIGEN)) || (oflags & ELX_FLAG_PADE);
   for (int c = 0; c < C && !use_pade; ++c)
     if (!eigen_reversible(K, model->pi + (size_t)c * K, model->exch + (size_t)c * K * K, &lambda[(size_t)c * K],
                           &A[(size_t)c * K * K], &B[(size_t)c * K * K], msg))
@@ -961,6 +986,8 @@ int32_t elx_pair_groups(const elx_handle *h) { return h ? pair_groups(h) : 0; }
 int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16, uint32_t *pqlo) {
   if (!h) return fail(nullptr, ELX_E_INVALID, "elx_pair_get: null handle");
   CUDA_TRY(h, cudaSetDevice(h->device));
+  const int rc = ensure_pair_tables(h);
+  if (rc) return rc;
   return pair_get(h, node_a, node_b, pe16, pqlo);
 }
 
@@ -989,12 +1016,16 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   }
   if (h->pair) {
     int used = 0;
+    rc = ensure_pair_tables(h);
+    if (rc) return rc;
     rc = pair_simulate(h, a, &used);
     if (rc) return rc;
     if (used) return 0;
   }
   if (!(h->flags & ELX_FLAG_FORCE_GENERIC)) {
     int used = 0;
+    rc = ensure_fast_tables(h);
+    if (rc) return rc;
     rc = fast_simulate(h, a, &used);
     if (rc) return rc;
     if (used) return 0;
@@ -1625,15 +1656,11 @@ int elx_fasta_pack_slice_device(elx_handle *h, const uint8_t *d_leaves, int64_t 
   if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
   if (nsites == 0) return 0;
   CUDA_TRY(h, cudaSetDevice(h->device));
-  if (!h->d_lut) CUDA_TRY(h, cudaMalloc((void **)&h->d_lut, 64));
-  uint8_t lut[64];
-  memset(lut, '?', sizeof lut);
-  memcpy(lut, alphabet, (size_t)h->K);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_lut, lut, 64, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // `lut` is a stack buffer
-  h->fasta_names_key.clear();                     // the frame cache shares d_lut
+  FastaLut lut;
+  memset(lut.c, '?', sizeof lut.c);
+  memcpy(lut.c, alphabet, (size_t)h->K);
   dim3 grid((unsigned)((nsites + 16 * 256 - 1) / (16 * 256)), (unsigned)h->T);
-  k3_fasta_slice<<<grid, 256, 0, h->stream>>>(d_leaves, leaves_pitch, nsites, h->d_lut, h->K, d_out, out_pitch);
+  k3_fasta_slice<<<grid, 256, 0, h->stream>>>(d_leaves, leaves_pitch, nsites, lut, h->K, d_out, out_pitch);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return 0;

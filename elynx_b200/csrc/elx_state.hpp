@@ -29,6 +29,7 @@ struct elx_handle {
   void *pair = nullptr;
   // quad mode (K <= 4): one draw per cap of up to 4 frontier nodes, inner nodes summed out; owned by elx_quad.cu
   void *quad = nullptr;
+  int pair_ready = 0, fast_ready = 0;  // pair rows / node-by-node stage images built from the current P tables (lazy)
   // multi-device handles (elx_opts.n_devices > 1): the handle the caller holds is the primary, peers[] are full handles on
   // the other devices (own stream, own tables); the host-buffer calls shard the site range over all of them
   std::vector<elx_handle *> peers;
@@ -108,6 +109,8 @@ int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
 int quad_simulate(elx_handle *h, SimArgs &a, int *used);
 
 // elx_core.cu
+int ensure_pair_tables(elx_handle *h);  // build the pair rows / the node-by-node stage images on first use
+int ensure_fast_tables(elx_handle *h);
 void launch_k1_alias(elx_handle *h, int64_t rows, int K, int A, const double *P, uint16_t *e16, uint32_t *qlo);
 
 }  // namespace elx

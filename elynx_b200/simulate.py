@@ -34,7 +34,7 @@ class Simulator:
 
     def __init__(self, weights, ds, es, tree, is_mixture: bool = True, device: int = -1, philox_rounds: int = 0,
                  force_generic: bool = False, pade: bool = False, single_draws: bool = False, pair_draws: bool = False,
-                 n_devices: int = 1):
+                 n_devices: int = 1, eigen: bool = False, flags: int = 0):
         ds = np.ascontiguousarray(ds, dtype=np.float64)
         es = np.ascontiguousarray(es, dtype=np.float64)
         if ds.ndim == 1:
@@ -56,7 +56,7 @@ class Simulator:
         t = L.elx_tree(len(parent), parent.ctypes.data_as(C.POINTER(C.c_int32)), brlen.ctypes.data_as(C.POINTER(C.c_double)),
                        leaf_row.ctypes.data_as(C.POINTER(C.c_int32)))
         o = L.elx_opts(device, philox_rounds, (L.ELX_FLAG_FORCE_GENERIC if force_generic else 0) | (L.ELX_FLAG_PADE if pade else 0) |
-                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0) | (L.ELX_FLAG_PAIR_DRAWS if pair_draws else 0), n_devices)
+                       (L.ELX_FLAG_SINGLE_DRAWS if single_draws else 0) | (L.ELX_FLAG_PAIR_DRAWS if pair_draws else 0) | (L.ELX_FLAG_EIGEN if eigen else 0) | int(flags), n_devices)
         h = C.c_void_p()
         self._h = None
         L.check(L.lib().elx_create(C.byref(m), C.byref(t), C.byref(o), C.byref(h)))

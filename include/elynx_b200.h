@@ -88,8 +88,12 @@ typedef struct {
                                     draw of sibling pairs; a different (equally exact) free-running stream */
 #define ELX_FLAG_PAIR_DRAWS 8    /* models with K <= 4: draw sibling pairs (pair mode) instead of the default quad mode (one draw per cap
                                     of up to 4 frontier nodes, inner nodes summed out); a different, equally exact stream */
-#define ELX_FLAG_PADE 2          /* build P(t) by the scaled Pade-7 + squaring kernel (hmatrix `expm`'s algorithm) instead of
-                                    the eigen form; taken automatically for non-reversible components */
+#define ELX_FLAG_PADE 2          /* build P(t) by the scaled Pade-7 + squaring kernel (hmatrix `expm`'s own algorithm).  This is
+                                    the DEFAULT for models with at most 32 states (element-wise parity <= 1e-12 with the
+                                    reference's probMatrix on every branch length); the flag forces it */
+#define ELX_FLAG_EIGEN 16        /* build P(t) in the eigen form I + A diag(expm1(lambda t)) B instead (reversible components
+                                    only; max-norm parity <= 1e-12, element-wise ~1e-10 on vanishing entries); models with more
+                                    than 32 states always take it */
 
 int elx_version(void);
 const char *elx_last_error(const elx_handle *h);

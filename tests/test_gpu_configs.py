@@ -75,8 +75,23 @@ def test_cfg5_shape_tiled_generic_and_spec_agree():
                 idx = np.linspace(0, tree.n_nodes - 1, 64).astype(int)
                 ref = om.prob_tables(model.pi, model.exch, tree.brlen[idx])
                 assert np.max(np.abs(p[idx] - ref)) < 5e-14
+                assert np.max(np.abs(p[idx] - ref) / np.maximum(ref, 1e-300)) < 1e-12
     for site0 in (0, (1 << 32) + 5):
         assert np.array_equal(outs[(False, site0)], outs[(True, site0)])
+
+
+@pytest.mark.parametrize("taxa,seed,mstr,gamma", [(1000, 1, "HKY[6.0]{0.2,0.3,0.3,0.2}", (4, 0.5)), (1000, 1, "LG", (4, 0.5)),
+                                                  (500, 2, "C60", None)])
+def test_ptables_elementwise_on_baseline_trees(taxa, seed, mstr, gamma):
+    """probMatrix parity (MarkovProcess.hs:33-41) ELEMENT-WISE <= 1e-12 on the trees of BASELINE configs 2, 3 and 4 (sampled
+    branches, every component) -- the default K1 path."""
+    tree = pm.birth_death_tree(taxa, 1.0, 0.5, seed=seed)
+    model = pm.get_phylo_model(mstr, gamma=gamma) if mstr != "C60" else pm.get_phylo_model(mixture_model="C60", global_normalization=True)
+    with _sim(model, tree) as sim:
+        p = sim.ptables()
+    idx = np.unique(np.concatenate([np.linspace(0, tree.n_nodes - 1, 48).astype(int), np.argsort(tree.brlen)[:9], np.argsort(tree.brlen)[-8:]]))
+    ref = om.prob_tables(model.pi, model.exch, tree.brlen[idx])
+    assert np.max(np.abs(p[idx] - ref) / np.maximum(ref, 1e-300)) < 1e-12
 
 
 def test_cfg5_shape_stationarity_from_device_histograms():
