@@ -84,9 +84,12 @@ SIGNATURES = {
     "elx_quad_groups": (_I32, [_VP]),
     "elx_quad_get": (C.c_int, [_VP, _VP, _VP, _VP]),
     "elx_tree_quad_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
+    "elx_duo_groups": (_I32, [_VP]),
+    "elx_duo_get": (C.c_int, [_VP, _VP, _VP, _VP]),
     "elx_tree_duo_walk_info": (C.c_int, [C.POINTER(elx_tree), C.POINTER(_I32), C.POINTER(_I32), _VP]),
     "elx_simulate": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
+    "elx_simulate_fasta_gz": (C.c_int, [_VP, _U64, _I64, _CSTRS, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "elx_synchronize": (C.c_int, [_VP]),
     "elx_simulate_injected": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_injected_device": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libelynx_b200.so")
-SOURCES = ["elx_core.cu", "elx_fast.cu", "elx_pair.cu", "elx_quad.cu", "elx_examine.cu", "elx_host.cpp", "elx_model.cpp", "elx_io.cpp"]
+SOURCES = ["elx_core.cu", "elx_fast.cu", "elx_pair.cu", "elx_quad.cu", "elx_duo.cu", "elx_examine.cu", "elx_host.cpp", "elx_model.cpp", "elx_io.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2",
               "-shared", "-cudart", "static", "-lz"]
 

@@ -601,6 +601,7 @@ static int build_tables_from_p(elx_handle *h, bool have_p) {
   h->fast_ready = 0;
   int rc = 0;
   if (h->quad) rc = quad_tables_build(h);
+  else if (h->duo) rc = duo_tables_build(h);
   else if (h->pair) rc = ensure_pair_tables(h);
   else rc = ensure_fast_tables(h);
   if (rc) return rc;
@@ -790,6 +791,12 @@ static int create_on_device(const elx_model *model, const elx_tree *tree, const 
     int qrc = quad_create(h, tree->parent, tree->leaf_row);
     if (qrc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, qrc, m); }
   }
+  // Duo mode (amino acids, leaves-only calls): one draw per cap of up to 2 frontier nodes on component-bucketed sites
+  // (elx_duo.cu); calls that keep the internal states draw node by node.
+  if (K > 4 && !(h->flags & ELX_FLAG_SINGLE_DRAWS)) {
+    int drc = duo_create(h, tree->parent, tree->leaf_row);
+    if (drc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, drc, m); }
+  }
   int rc = build_tables_from_p(h, false);
   if (rc) { std::string m = h->last_error; elx_destroy(h); return fail(nullptr, rc, m); }
   *out = h;
@@ -926,6 +933,7 @@ void elx_destroy(elx_handle *h) {
   fast_tables_free(h);
   pair_free(h);
   quad_free(h);
+  duo_free(h);
   cudaFree(h->d_Q); cudaFree(h->d_brlen); cudaFree(h->d_lambda); cudaFree(h->d_A); cudaFree(h->d_B); cudaFree(h->d_P); cudaFree(h->d_cum);
   cudaFree(h->d_e16); cudaFree(h->d_qlo); cudaFree(h->d_cumw); cudaFree(h->d_cumpi); cudaFree(h->d_walk);
   cudaFree(h->d_error_flag); cudaFree(h->d_names); cudaFree(h->d_name_off); cudaFree(h->d_seq_off);
@@ -999,6 +1007,14 @@ int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24) 
   return quad_get(h, recs, qe32, qlo24);
 }
 
+int32_t elx_duo_groups(const elx_handle *h) { return h ? duo_groups(h) : 0; }
+
+int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "elx_duo_get: null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return duo_get(h, recs, de32, dlo24);
+}
+
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves, int64_t leaves_pitch,
                         int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch) {
   int rc = check_sim_args(h, site0, nsites, d_leaves, leaves_pitch, d_internal, internal_pitch);
@@ -1011,6 +1027,12 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   if (h->quad) {
     int used = 0;
     rc = quad_simulate(h, a, &used);
+    if (rc) return rc;
+    if (used) return 0;
+  }
+  if (h->duo) {
+    int used = 0;
+    rc = duo_simulate(h, a, &used);
     if (rc) return rc;
     if (used) return 0;
   }
@@ -1722,6 +1744,93 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
   CT(cudaStreamSynchronize(h->stream));
 #undef CT
   cleanup();
+  return check_error_flag(h);
+}
+
+// writeGZFile for the alignment (elynx-tools InputOutput.hs:80-83 after Export/Fasta.hs:24-36), streamed: the alignment is
+// simulated into device memory, then blocks of whole sequence lines (or column chunks of one very long line) are mapped to
+// characters by K3 straight into one of two pinned host buffers; while the GPU fills the next buffer the host appends the
+// finished block to an ordered multi-member gzip stream whose members are deflated by worker threads and written in file
+// order.  D2H, deflate and the file write overlap; host memory stays bounded (2 x 64 MB + the members in flight).
+int elx_simulate_fasta_gz(elx_handle *h, uint64_t seed, int64_t total_sites, const char *const *names, const char *alphabet,
+                          const char *path, int32_t level, int32_t n_threads, int32_t *comps) {
+  if (!h || !alphabet || !path) return fail(h, ELX_E_INVALID, "simulate_fasta_gz: NULL argument");
+  if (total_sites < 0) return fail(h, ELX_E_INVALID, "simulate_fasta_gz: negative site count");
+  if (strlen(alphabet) < (size_t)h->K) return fail(h, ELX_E_INVALID, "fasta: alphabet shorter than the number of states");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int T = h->T;
+  const int64_t S = total_sites, pitch = ((S > 0 ? S : 1) + 127) & ~(int64_t)127;
+  uint8_t *d_leaves = nullptr, *pin = nullptr;
+  int32_t *d_comps = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  GzStream *gz = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_leaves); cudaFree(d_comps);
+    if (pin) pin_release(pin);
+    for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+  };
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); if (gz) { std::string x; gz_close(gz, x); } return fail(h, _e == cudaErrorMemoryAllocation ? ELX_E_NOMEM : ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  CT(cudaMalloc((void **)&d_leaves, (size_t)T * pitch));
+  if (comps) CT(cudaMalloc((void **)&d_comps, sizeof(int32_t) * (size_t)(S > 0 ? S : 1)));
+  const int64_t BATCH = 1 << 22;
+  for (int64_t b0 = 0; b0 < S; b0 += BATCH) {
+    const int64_t nb = S - b0 < BATCH ? S - b0 : BATCH;
+    const int rc = elx_simulate_device(h, seed, b0, nb, d_leaves + b0, pitch, d_comps ? d_comps + b0 : nullptr, nullptr, 0);
+    if (rc) { cleanup(); return rc; }
+  }
+  if (comps && S > 0) CT(cudaMemcpyAsync(comps, d_comps, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, h->stream));
+  pin = pin_acquire();
+  if (!pin) { cleanup(); return fail(h, ELX_E_NOMEM, "simulate_fasta_gz: cannot pin host staging memory"); }
+  for (cudaEvent_t &e : ev) CT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+  std::string gerr;
+  gz = gz_open(path, n_threads, level, 0, gerr);
+  if (!gz) { cleanup(); return fail(h, ELX_E_INVALID, "simulate_fasta_gz: " + gerr); }
+  const int64_t half = (int64_t)(PIN_BYTES / 2);
+  // blocks in file order: (first row, number of rows, first column, number of columns)
+  struct Blk { int r0, nr; int64_t c0, nc; };
+  std::vector<Blk> blks;
+  if (S <= half) {
+    const int rows = (int)std::max<int64_t>(1, std::min<int64_t>(T, half / std::max<int64_t>(S, 1)));
+    for (int r = 0; r < T; r += rows) blks.push_back({r, std::min(rows, T - r), 0, S});
+  } else {
+    for (int r = 0; r < T; ++r)
+      for (int64_t c = 0; c < S; c += half) blks.push_back({r, 1, c, std::min(half, S - c)});
+  }
+  FastaLut lut;
+  memset(lut.c, '?', sizeof lut.c);
+  memcpy(lut.c, alphabet, (size_t)h->K);
+  auto issue = [&](size_t i) -> cudaError_t {
+    const Blk &b = blks[i];
+    if (b.nc > 0) {
+      dim3 grid((unsigned)((b.nc + 16 * 256 - 1) / (16 * 256)), (unsigned)b.nr);
+      k3_fasta_slice<<<grid, 256, 0, h->stream>>>(d_leaves + (size_t)b.r0 * pitch + b.c0, pitch, b.nc, lut, h->K, pin + (i & 1) * half, b.nc);
+      h->launches++;
+      h->d2h_bytes += (int64_t)b.nr * b.nc;
+    }
+    return cudaEventRecord(ev[i & 1], h->stream);
+  };
+  bool ok = true;
+  if (!blks.empty()) CT(issue(0));
+  for (size_t i = 0; i < blks.size() && ok; ++i) {
+    if (i + 1 < blks.size()) CT(issue(i + 1));  // the GPU fills the other buffer while this one is compressed
+    CT(cudaEventSynchronize(ev[i & 1]));
+    const Blk &b = blks[i];
+    const uint8_t *src = pin + (i & 1) * half;
+    for (int r = 0; r < b.nr && ok; ++r) {
+      if (b.c0 == 0) {
+        const char *nm = names && names[b.r0 + r] ? names[b.r0 + r] : "";
+        ok = gz_append(gz, (const uint8_t *)">", 1) && gz_append(gz, (const uint8_t *)nm, strlen(nm)) && gz_append(gz, (const uint8_t *)"\n", 1);
+      }
+      ok = ok && gz_append(gz, src + (size_t)r * b.nc, (size_t)b.nc);
+      if (b.c0 + b.nc == S) ok = ok && gz_append(gz, (const uint8_t *)"\n", 1);
+    }
+  }
+#undef CT
+  const bool closed = gz_close(gz, gerr);
+  gz = nullptr;
+  cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (!ok || !closed) return fail(h, ELX_E_INVALID, "simulate_fasta_gz: " + (gerr.empty() ? std::string("write failed") : gerr));
   return check_error_flag(h);
 }
 

@@ -10,6 +10,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -207,6 +210,120 @@ void unpack5_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int
   }
 #endif
   for (int64_t r = row0; r < row1; ++r) unpack5_scalar(packed + r * packed_pitch, dst + r * dst_pitch, 0, nsites, lut32);
+}
+
+// ---- ordered multi-member gzip stream ------------------------------------------------------------------------------
+// append() cuts the byte stream into members of block_bytes; worker threads deflate them; the appending thread writes the
+// finished members in order whenever more than `max_inflight` are pending (back-pressure) and at close.  The file is the
+// same sequence of members elx_gzip_write produces for the same bytes and block size.
+struct GzJob {
+  std::string in, out, err;
+  std::atomic<int> done{0};
+  bool ok = true;
+};
+struct GzStream {
+  FILE *f = nullptr;
+  int level = 6;
+  size_t block = (size_t)4 << 20;
+  std::vector<std::thread> pool;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<GzJob *> queue;     // submitted, not yet taken by a worker
+  std::deque<GzJob *> inflight;  // submitted, not yet written (file order)
+  std::string cur;
+  bool closing = false, failed = false, any = false;
+  std::string error;
+  size_t max_inflight = 8;
+};
+
+static void gz_worker(GzStream *g) {
+  for (;;) {
+    GzJob *j = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(g->mu);
+      g->cv_work.wait(lk, [&]() { return !g->queue.empty() || g->closing; });
+      if (g->queue.empty()) return;
+      j = g->queue.front();
+      g->queue.pop_front();
+    }
+    j->ok = deflate_member(reinterpret_cast<const uint8_t *>(j->in.data()), j->in.size(), g->level, j->out, j->err);
+    std::string().swap(j->in);
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      j->done.store(1, std::memory_order_release);
+    }
+    g->cv_done.notify_all();
+  }
+}
+
+static void gz_drain(GzStream *g, size_t keep) {  // write the oldest members until at most `keep` are pending
+  for (;;) {
+    GzJob *j = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(g->mu);
+      if (g->inflight.size() <= keep) return;
+      j = g->inflight.front();
+      g->cv_done.wait(lk, [&]() { return j->done.load(std::memory_order_acquire) != 0; });
+      g->inflight.pop_front();
+    }
+    if (!j->ok) { g->failed = true; if (g->error.empty()) g->error = j->err; }
+    else if (!g->failed && fwrite(j->out.data(), 1, j->out.size(), g->f) != j->out.size()) { g->failed = true; g->error = "short write"; }
+    delete j;
+  }
+}
+
+static void gz_submit(GzStream *g) {
+  GzJob *j = new GzJob();
+  j->in.swap(g->cur);
+  g->any = true;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->queue.push_back(j);
+    g->inflight.push_back(j);
+  }
+  g->cv_work.notify_one();
+  gz_drain(g, g->max_inflight);
+}
+
+GzStream *gz_open(const char *path, int n_threads, int level, int64_t block_bytes, std::string &err) {
+  FILE *f = fopen(path, "wb");
+  if (!f) { err = std::string("cannot open ") + path; return nullptr; }
+  GzStream *g = new GzStream();
+  g->f = f;
+  g->level = (level < 0 || level > 9) ? 6 : level;
+  if (block_bytes > 0) g->block = (size_t)std::min<int64_t>(block_bytes, (int64_t)1 << 30);
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  g->max_inflight = (size_t)nt * 4;
+  for (int t = 0; t < nt; ++t) g->pool.emplace_back(gz_worker, g);
+  return g;
+}
+
+bool gz_append(GzStream *g, const uint8_t *data, size_t n) {
+  while (n > 0 && !g->failed) {
+    const size_t room = g->block - g->cur.size(), take = n < room ? n : room;
+    g->cur.append(reinterpret_cast<const char *>(data), take);
+    data += take;
+    n -= take;
+    if (g->cur.size() == g->block) gz_submit(g);
+  }
+  return !g->failed;
+}
+
+bool gz_close(GzStream *g, std::string &err) {
+  if (!g->cur.empty() || !g->any) gz_submit(g);  // an empty stream is one empty member
+  gz_drain(g, 0);
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->closing = true;
+  }
+  g->cv_work.notify_all();
+  for (auto &t : g->pool) t.join();
+  if (fclose(g->f) != 0 && !g->failed) { g->failed = true; g->error = "close failed"; }
+  const bool ok = !g->failed;
+  err = g->error;
+  delete g;
+  return ok;
 }
 }  // namespace elx
 

@@ -29,6 +29,8 @@ struct elx_handle {
   void *pair = nullptr;
   // quad mode (K <= 4): one draw per cap of up to 4 frontier nodes, inner nodes summed out; owned by elx_quad.cu
   void *quad = nullptr;
+  // duo mode (5 <= K <= 22): one draw per cap of up to 2 frontier nodes on component-bucketed sites; owned by elx_duo.cu
+  void *duo = nullptr;
   int pair_ready = 0, fast_ready = 0;  // pair rows / node-by-node stage images built from the current P tables (lazy)
   // multi-device handles (elx_opts.n_devices > 1): the handle the caller holds is the primary, peers[] are full handles on
   // the other devices (own stream, own tables); the host-buffer calls shard the site range over all of them
@@ -85,6 +87,12 @@ void unpack2_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int
 void unpack5_rows(const uint8_t *packed, int64_t packed_pitch, uint8_t *dst, int64_t dst_pitch, int64_t row0, int64_t row1,
                   int64_t nsites, const uint8_t *lut32);
 
+// elx_io.cpp: ordered multi-member gzip stream (worker threads deflate members of block_bytes, written in order)
+struct GzStream;
+GzStream *gz_open(const char *path, int n_threads, int level, int64_t block_bytes, std::string &err);
+bool gz_append(GzStream *g, const uint8_t *data, size_t n);
+bool gz_close(GzStream *g, std::string &err);  // flushes, joins the workers, closes the file and frees g
+
 // elx_fast.cu: tiled shared-memory kernels for the shapes that fit (DNA / protein with few components)
 int fast_tables_build(elx_handle *h);
 void fast_tables_free(elx_handle *h);
@@ -107,6 +115,15 @@ int quad_groups(const elx_handle *h);
 void quad_rec_to_ints(const QuadRec &r, int32_t *o);  // ELX_QUAD_REC_INTS values, the layout include/elynx_b200.h documents
 int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
 int quad_simulate(elx_handle *h, SimArgs &a, int *used);
+
+// elx_duo.cu: duo mode (models with 5..22 states unless ELX_FLAG_SINGLE_DRAWS; leaves-only calls); leaves h->duo null when
+// the tree or model does not fit (the handle then draws node by node)
+int duo_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row);
+int duo_tables_build(elx_handle *h);
+void duo_free(elx_handle *h);
+int duo_groups(const elx_handle *h);
+int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24);
+int duo_simulate(elx_handle *h, SimArgs &a, int *used);
 
 // elx_core.cu
 int ensure_pair_tables(elx_handle *h);  // build the pair rows / the node-by-node stage images on first use

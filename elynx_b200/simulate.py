@@ -69,6 +69,8 @@ class Simulator:
         self.pair_groups = int(L.lib().elx_pair_groups(h))  # > 0: K <= 4, sibling pairs are drawn jointly (elx_pair.cu)
         # > 0: K <= 4, leaves-only calls draw one cap of <= 4 frontier nodes at a time, inner nodes summed out (elx_quad.cu)
         self.quad_groups = int(L.lib().elx_quad_groups(h))
+        # > 0: 5 <= K <= 22, leaves-only calls draw one cap of <= 2 frontier nodes at a time on component-bucketed sites (elx_duo.cu)
+        self.duo_groups = int(L.lib().elx_duo_groups(h))
 
     # -- lifetime --------------------------------------------------------------------------
     def close(self):
@@ -157,6 +159,17 @@ class Simulator:
         return recs, qe32, qlo24
 
     # -- simulation ----------------------------------------------------------------------------
+    def duo_tables(self):
+        """(recs[G][ELX_QUAD_REC_INTS], de32[G][C][K][512], dlo24[G][C][K][512]) of the duo-mode records, or None."""
+        g = self.duo_groups
+        if g == 0:
+            return None
+        recs = np.empty((g, L.ELX_QUAD_REC_INTS), dtype=np.int32)
+        de32 = np.empty((g, self.n_components, self.n_states, 512), dtype=np.uint32)
+        dlo24 = np.empty_like(de32)
+        L.check(L.lib().elx_duo_get(self._h, _ptr(recs), _ptr(de32), _ptr(dlo24)), self._h)
+        return recs, de32, dlo24
+
     def simulate(self, seed: int, nsites: int, site0: int = 0, want_comps: bool = False, keep_internal: bool = False):
         """(leaves[T][nsites] uint8, comps[nsites] int32 | None, internal[N][nsites] uint8 | None) in host memory."""
         nsites = int(nsites)
@@ -211,6 +224,16 @@ class Simulator:
         L.check(L.lib().elx_simulate_fasta(self._h, C.c_uint64(seed & (2 ** 64 - 1)), total_sites, self._names(names),
                                            alphabet.encode(), _ptr(out), size, _ptr(comps)), self._h)
         return out.tobytes(), comps
+
+    def simulate_fasta_gz(self, seed: int, total_sites: int, names: Sequence[str], alphabet: str, path: str, level: int = 6,
+                          threads: int = 0, want_comps: bool = False):
+        """`<base>.fasta.gz` streamed from the device (writeGZFile, InputOutput.hs:80-83): D2H, deflate and the file write overlap."""
+        if len(names) != self.n_leaves:
+            raise L.ElxError(L.ELX_E_INVALID, "fasta: need one name per leaf")
+        comps = np.empty(total_sites, dtype=np.int32) if want_comps else None
+        L.check(L.lib().elx_simulate_fasta_gz(self._h, C.c_uint64(seed & (2 ** 64 - 1)), total_sites, self._names(names),
+                                              alphabet.encode(), path.encode(), level, threads, _ptr(comps)), self._h)
+        return comps
 
     def fasta_pack_device(self, d_leaves: int, leaves_pitch: int, site0: int, nsites: int, total_sites: int,
                           names: Sequence[str], alphabet: str, d_out: int):

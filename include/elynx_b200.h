@@ -168,6 +168,17 @@ int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n
 /* the same cut with at most TWO frontier nodes per cap: the records of duo mode (below) */
 int elx_tree_duo_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
 
+/* Duo mode (the default for models with 5..22 states -- amino acids -- when only the leaves are requested; ELX_FLAG_SINGLE_DRAWS
+ * turns it off): the same summing-out with caps of at most TWO frontier nodes, one draw from the K*K-outcome joint row
+ * P(frontier states | state of r) in 512 alias columns, o = state(out[0]) + K * state(out[1]).  A record's rows are 40 KB per
+ * component, so every call first buckets its sites by component (stable inside superblocks of 2^22 sites); the rank of a site
+ * among the sites of its component and superblock selects its 16-site Philox group (see elx_duo.cu for the specification).
+ * elx_duo_groups: number of records (0: the handle draws node by node); elx_duo_get: the records (ELX_QUAD_REC_INTS layout,
+ * frontier positions 0..1) and their alias rows de32 / dlo24 [G][C][K][512] (uint32: [threshold bits 38..24 : 15][alias : 9][0 : 8]
+ * / threshold bits 23..0).  A draw is 24 bits ([t : 15][column : 9]); t == threshold high bits (2^-15) is settled with 24 more. */
+int32_t elx_duo_groups(const elx_handle *h);
+int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24);
+
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
  * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed); the result is a
  * pure function of (seed, global site index, node), so any partition of the site range over calls,
@@ -207,6 +218,13 @@ int elx_fasta_pack_device(elx_handle *h, const uint8_t *d_leaves, int64_t leaves
                           int64_t total_sites, const char *const *names, const char *alphabet, uint8_t *d_out);
 int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const char *const *names, const char *alphabet,
                        uint8_t *out, int64_t out_capacity, int32_t *comps);
+/* The same alignment written as a gzip file (what writeGZFile, elynx-tools InputOutput.hs:80-83, does for a path ending in
+ * .gz): simulated into device memory, then streamed in blocks of sequence lines -- K3 writes the characters of a block into
+ * pinned host memory while host threads deflate the previous block into gzip members (4 MiB of text each) that are written
+ * in file order.  gunzip / the reference's `decompress` return exactly the bytes elx_simulate_fasta produces.
+ * level: zlib 0..9 (else 6); n_threads <= 0: all host cores.  Fails with ELX_E_NOMEM when the alignment does not fit the device. */
+int elx_simulate_fasta_gz(elx_handle *h, uint64_t seed, int64_t total_sites, const char *const *names, const char *alphabet,
+                          const char *path, int32_t level, int32_t n_threads, int32_t *comps);
 /* K3 in slice mode: the characters of columns [0, nsites) of every sequence as a plain [T][out_pitch] matrix (no header
  * lines, no newlines).  d_out may be any device-accessible pointer, in particular pinned host memory: with several GPUs
  * every rank packs its site range straight into its own pinned buffer and the host writes each row segment into the

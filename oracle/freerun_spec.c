@@ -29,6 +29,14 @@
  *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < qlo24[g][c][state of r][j] ? j : alias
  * Records come in walk order (r is the root or a frontier node of an earlier record); recs = 52 int32 per record in the
  * layout include/elynx_b200.h documents.
+ *
+ * Duo mode (models with 5..22 states, leaves only; elynx_b200/csrc/elx_duo.cu): record g = (out[0..1] | r) draws up to two frontier
+ * nodes at once from a K*K-outcome joint row in 512 alias columns, o = state(out[0]) + K * state(out[1]).  Sites are bucketed by
+ * component inside superblocks of 2^22 sites: B = s >> 22, rank = number of earlier sites of B with the same component,
+ * q = rank >> 4, d = rank & 15; the 16 sites of a group share three Philox calls:
+ *   Z[0..47] = little-endian bytes of philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
+ *   x24 = Z[3d] | Z[3d+1] << 8 | Z[3d+2] << 16;  j = x24 & 511; t = x24 >> 9; e = de32[g][c][state of r][j] = [q_hi : 15][alias : 9][0 : 8]
+ *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < dlo24[g][c][state of r][j] ? j : alias
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -232,5 +240,86 @@ int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int
       }
   }
   free(st); free(done);
+  return rc;
+}
+
+#define DUO_SB 22
+static int64_t duo_ties = 0;
+int64_t spec_duo_ties(void) { return duo_ties; } /* ties seen by the last spec_freerun_duo call */
+int spec_freerun_duo(int N, int K, int C, int is_mixture, int rounds, const int32_t *leaf_row, const double *cumw,
+                     const double *cumpi, int G, const int32_t *recs, const uint32_t *de32, const uint32_t *dlo24, uint64_t seed,
+                     int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch, int32_t *comps) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint8_t *st = (uint8_t *)malloc((size_t)N);
+  uint8_t *done = (uint8_t *)malloc((size_t)N);
+  uint32_t *count = (uint32_t *)calloc((size_t)C, sizeof(uint32_t));
+  int rc = 0;
+  duo_ties = 0;
+  const uint64_t first = ((uint64_t)site0 >> DUO_SB) << DUO_SB;
+  uint64_t cur_sb = (uint64_t)-1;
+  for (uint64_t s = first; s < (uint64_t)(site0 + nsites) && !rc; ++s) {
+    const uint64_t sb = s >> DUO_SB;
+    if (sb != cur_sb) { for (int c = 0; c < C; ++c) count[c] = 0; cur_sb = sb; }
+    int c = 0;
+    if (is_mixture) {
+      uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 2};
+      philox(rounds, x, k0, k1);
+      uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+      c = cat_cum(cumw, C, (double)((w >> 11) + 1) * 0x1p-53);
+      if (c < 0) { rc = -(N + 1); break; }
+    }
+    const uint32_t rank = count[c]++;
+    if (s < (uint64_t)site0) continue;
+    const int64_t col = (int64_t)(s - (uint64_t)site0);
+    if (comps) comps[col] = c;
+    uint32_t x[4] = {(uint32_t)s, (uint32_t)(s >> 32), 0, 3};
+    philox(rounds, x, k0, k1);
+    uint64_t w = ((uint64_t)x[1] << 32) | x[0];
+    int root = cat_cum(cumpi + (int64_t)c * K, K, (double)((w >> 11) + 1) * 0x1p-53);
+    if (root < 0) { rc = -(N + 2); break; }
+    for (int n = 0; n < N; ++n) done[n] = 0;
+    st[0] = (uint8_t)root; done[0] = 1;
+    const uint32_t q = rank >> 4;
+    const int d = (int)(rank & 15);
+    for (int g = 0; g < G; ++g) {
+      const int32_t *r = recs + (size_t)g * QUAD_REC_INTS;
+      const int rt = r[0], n0 = r[1];
+      if (rt < 0 || rt >= N || !done[rt] || n0 < 0 || n0 >= N) { rc = -2; break; }  /* not in walk order */
+      uint8_t B[48];
+      for (int call = 0; call < 3; ++call) {
+        uint32_t y[4] = {q | ((uint32_t)c << 20), (uint32_t)sb, (uint32_t)n0, ((uint32_t)(sb >> 32) << 8) | (4u * (uint32_t)call)};
+        philox(rounds, y, k0, k1);
+        for (int b = 0; b < 16; ++b) B[16 * call + b] = (uint8_t)(y[b >> 2] >> (8 * (b & 3)));
+      }
+      uint32_t x24 = (uint32_t)B[3 * d] | ((uint32_t)B[3 * d + 1] << 8) | ((uint32_t)B[3 * d + 2] << 16);
+      uint32_t j = x24 & 511u, t = x24 >> 9;
+      int64_t idx = (((int64_t)g * C + c) * K + st[rt]) * 512 + j;
+      uint32_t e = de32[idx], qh = e >> 17, al = (e >> 8) & 511u, o;
+      if (t < qh) o = j;
+      else if (t > qh) o = al;
+      else {
+        uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)n0, 1};
+        philox(rounds, z, k0, k1);
+        o = (z[0] >> 8) < dlo24[idx] ? j : al;
+        ++duo_ties;
+      }
+      const uint32_t sv[2] = {o % (uint32_t)K, o / (uint32_t)K};
+      if (sv[1] >= (uint32_t)K) { rc = -4; break; }
+      for (int k = 0; k < 2; ++k) {
+        const int n = r[1 + k];
+        if (n < 0) continue;
+        if (n >= N || done[n]) { rc = -1; break; }
+        st[n] = (uint8_t)sv[k]; done[n] = 1;
+      }
+      if (rc) break;
+    }
+    if (rc) break;
+    for (int n = 0; n < N; ++n)
+      if (leaf_row[n] >= 0) {
+        if (!done[n]) { rc = -3; break; }
+        leaves[(int64_t)leaf_row[n] * leaves_pitch + col] = st[n];
+      }
+  }
+  free(st); free(done); free(count);
   return rc;
 }

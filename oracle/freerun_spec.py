@@ -29,6 +29,8 @@ def lib():
         _lib.spec_freerun_pair.restype = C.c_int
         _lib.spec_freerun_quad.restype = C.c_int
         _lib.spec_quad_ties.restype = C.c_int64
+        _lib.spec_freerun_duo.restype = C.c_int
+        _lib.spec_duo_ties.restype = C.c_int64
     return _lib
 
 
@@ -129,3 +131,33 @@ def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites
 def quad_ties():
     """Number of tied draws the last freerun_quad call had to refine."""
     return int(lib().spec_quad_ties())
+
+
+def freerun_duo(is_mixture, parent, leaf_row, ws, ds, duo, seed, site0, nsites, rounds=10):
+    """Duo mode (5 <= K <= 22, leaves only): duo = (recs[G][52], de32[G][C][K][512], dlo24[G][C][K][512]) in walk order."""
+    leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
+    recs = np.ascontiguousarray(duo[0], dtype=np.int32)
+    de32 = np.ascontiguousarray(duo[1], dtype=np.uint32)
+    dlo24 = np.ascontiguousarray(duo[2], dtype=np.uint32)
+    g, c, k, cols = de32.shape
+    assert cols == 512 and dlo24.shape == de32.shape and recs.shape == (g, QUAD_REC_INTS)
+    n = len(leaf_row)
+    assert np.asarray(ds).reshape(c, -1).shape[1] == k
+    cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
+    cumpi = np.ascontiguousarray(np.cumsum(np.asarray(ds, dtype=np.float64).reshape(c, k), axis=1))
+    t = int((leaf_row >= 0).sum())
+    leaves = np.zeros((t, max(nsites, 1)), dtype=np.uint8)
+    comps = np.zeros(max(nsites, 1), dtype=np.int32)
+    vp = C.c_void_p
+    rc = lib().spec_freerun_duo(n, k, c, int(bool(is_mixture)), rounds, vp(leaf_row.ctypes.data), vp(cumw.ctypes.data),
+                                vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(de32.ctypes.data), vp(dlo24.ctypes.data),
+                                C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0), C.c_int64(nsites), vp(leaves.ctypes.data),
+                                C.c_int64(max(nsites, 1)), vp(comps.ctypes.data))
+    if rc:
+        raise RuntimeError("spec_freerun_duo rc=%d" % rc)
+    return leaves[:, :nsites], comps[:nsites], None
+
+
+def duo_ties():
+    """Number of tied draws the last freerun_duo call had to refine."""
+    return int(lib().spec_duo_ties())

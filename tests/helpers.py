@@ -67,7 +67,7 @@ def uniforms(rng, rows, s):
 
 def spec_freerun(sim, model, tree, seed, site0, s, **kw):
     """The executable spec of the product's free-running draw for this handle, run on the handle's own tables:
-    quad mode (K <= 4, leaves only: one draw per cap), pair mode (K <= 4: sibling pairs drawn jointly) or node by node."""
+    quad mode (K <= 4, leaves only: one draw per cap), duo mode (5 <= K <= 22, leaves only: caps of <= 2 frontier nodes), pair mode (K <= 4: sibling pairs drawn jointly) or node by node."""
     import oracle.freerun_spec as spec
 
     is_mix, ws, ds = model[0], model[1], model[2]
@@ -75,6 +75,10 @@ def spec_freerun(sim, model, tree, seed, site0, s, **kw):
     if quad is not None and not kw.get("keep_internal"):
         kw.pop("keep_internal", None)
         return spec.freerun_quad(is_mix, tree.parent, tree.leaf_row, ws, ds, quad, seed, site0, s, **kw)
+    duo = sim.duo_tables()
+    if duo is not None and not kw.get("keep_internal"):
+        kw.pop("keep_internal", None)
+        return spec.freerun_duo(is_mix, tree.parent, tree.leaf_row, ws, ds, duo, seed, site0, s, **kw)
     pair = sim.pair_tables()
     if pair is not None:
         return spec.freerun_pair(is_mix, tree.parent, tree.leaf_row, ws, ds, pair, seed, site0, s, **kw)
@@ -237,4 +241,67 @@ def check_quad_tables(p, quad, parent, leaf_row, max_records=40):
         ref = quad_joint_reference(pn, recs[g], k)
         ref = ref / ref.sum(-1, keepdims=True)
         got = mass[g, :, :k] / float(1 << 48)
+        assert np.max(np.abs(got - ref)) < 2.0 ** -40, (g, np.max(np.abs(got - ref)))
+
+
+def duo_masses(de32, dlo24):
+    """Integer outcome masses (sum 2^48 per row) encoded by duo alias rows de32 = [q bits 38..24 : 15][alias : 9][0 : 8], dlo24."""
+    cap = 1 << 39
+    e = de32.astype(np.int64)
+    assert np.all((e & 255) == 0)
+    al = (e >> 8) & 511
+    q = ((e >> 17) << 24) | dlo24.astype(np.int64)
+    assert np.all(dlo24 < (1 << 24))
+    q = np.where(al == np.arange(512), cap, q)
+    flat_q = q.reshape(-1, 512)
+    flat_al = al.reshape(-1, 512)
+    mass = flat_q.copy()
+    rows = np.arange(flat_q.shape[0])
+    for j in range(512):
+        np.add.at(mass, (rows, flat_al[:, j]), cap - flat_q[:, j])
+    return mass.reshape(q.shape)
+
+
+def duo_joint_reference(p, rec):
+    """P(frontier states | root state) [C][K][512] of one duo record (o = s0 + K s1) by matrix products over the cap:
+    inner nodes are summed out children first."""
+    n, c, k, _ = p.shape
+    ncap = int(rec[14])
+    cap = [(int(rec[16 + 3 * i]), int(rec[17 + 3 * i]), int(rec[18 + 3 * i])) for i in range(ncap)]
+    nfr = sum(1 for x in cap if x[2] >= 0)
+    out = np.zeros((c, k, 512))
+    for s1 in range(k if nfr > 1 else 1):
+        for s0 in range(k):
+            fs = (s0, s1)
+            like = [np.ones((c, k)) for _ in range(ncap)]  # L[i][comp][state of cap node i]
+            top = np.ones((c, k))
+            for i in range(ncap - 1, -1, -1):
+                node, par, fr = cap[i]
+                if fr >= 0:
+                    msg = p[node][:, :, fs[fr]]  # [c][parent state]
+                else:
+                    msg = np.einsum("cst,ct->cs", p[node], like[i])
+                if par >= 0:
+                    like[par] = like[par] * msg
+                else:
+                    top = top * msg
+            out[:, :, s0 + k * s1] = top
+    return out
+
+
+def check_duo_tables(p, duo, parent, leaf_row, max_records=12):
+    """The walk is valid (caps of at most two frontier nodes) and the alias rows carry integer masses (sum 2^48) equal to the
+    caps' joint probabilities."""
+    recs, de32, dlo24 = duo
+    check_quad_walk(recs, parent, leaf_row)
+    assert np.all(recs[:, 3:5] == -1), "a duo cap has at most two frontier nodes"
+    k = p.shape[2]
+    pn = p / p.sum(-1, keepdims=True)
+    step = max(1, len(recs) // max_records)
+    for g in range(0, len(recs), step):
+        mass = duo_masses(de32[g], dlo24[g])
+        assert np.all(mass.sum(-1) == 1 << 48)
+        ref = duo_joint_reference(pn, recs[g])
+        ref = ref / ref.sum(-1, keepdims=True)
+        got = mass / float(1 << 48)
         assert np.max(np.abs(got - ref)) < 2.0 ** -40, (g, np.max(np.abs(got - ref)))

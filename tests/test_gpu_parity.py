@@ -7,7 +7,7 @@ import oracle.freerun_spec as spec
 import oracle.model as om
 import oracle.pruning as pruning
 import oracle.sim as osim
-from helpers import alias_masses, check_pair_tables, check_quad_tables, model_case, random_tree, spec_freerun, tree_from_file, uniforms
+from helpers import alias_masses, check_duo_tables, check_pair_tables, check_quad_tables, model_case, random_tree, spec_freerun, tree_from_file, uniforms
 
 pytestmark = pytest.mark.gpu
 
@@ -178,14 +178,17 @@ def test_freerun_matches_spec(name, tree_file, s, force_generic, draws):
     model = model_case(name)
     is_mix, ws, ds, es, _ = model
     k = ds.shape[1]
-    if draws != "default" and k > 4:
-        pytest.skip("pair_draws / single_draws only change models with K <= 4")
+    if draws == "pair" and k > 4:
+        pytest.skip("pair_draws only changes models with K <= 4")
     tree = tree_from_file(tree_file)
     with make_sim(model, tree, force_generic=force_generic, single_draws=draws == "single", pair_draws=draws == "pair") as sim:
         e16, qlo = sim.alias_tables()
         check_alias_tables(sim.ptables(), e16, qlo, k)
         assert (sim.pair_groups > 0) == (k <= 4 and draws != "single")
         assert (sim.quad_groups > 0) == (k <= 4 and draws == "default")
+        assert (sim.duo_groups > 0) == (5 <= k <= 22 and draws == "default")
+        if sim.duo_groups:
+            check_duo_tables(sim.ptables(), sim.duo_tables(), tree.parent, tree.leaf_row)
         if sim.pair_groups:
             check_pair_tables(sim.ptables(), sim.pair_tables(), tree.parent)
         if sim.quad_groups:
@@ -200,7 +203,7 @@ def test_freerun_matches_spec(name, tree_file, s, force_generic, draws):
             leaves2, comps2, _ = sim.simulate(seed, s, site0=site0, want_comps=True)
             l1, c1, _ = spec_freerun(sim, model, tree, seed, site0, s)
             assert np.array_equal(leaves2, l1) and np.array_equal(comps2, c1)
-            if not sim.quad_groups:
+            if not sim.quad_groups and not sim.duo_groups:
                 assert np.array_equal(l1, l0)
 
 
