@@ -25,6 +25,7 @@
 #include "../../include/elynx_b200.h"
 #include "elx_device.cuh"
 #include "elx_internal.hpp"
+#include "elx_ptx.cuh"
 #include "elx_state.hpp"
 
 namespace elx {
@@ -561,6 +562,16 @@ __global__ void k_pattern_counts(const uint8_t *__restrict__ leaves, int64_t pit
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// the component draw of every site alone (getComponentsAndRootStates, MarkovProcessAlongTree.hs:163-173, first half)
+template <int ROUNDS>
+__global__ void k_site_components(SimArgs a) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.nsites) return;
+  const uint32_t cr = draw_comp_root<ROUNDS>(a.cumw, a.cumpi, a.C, a.K, a.N, a.is_mixture, a.error_flag, (uint64_t)(a.site0 + col),
+                                             (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  a.comps[col] = (int32_t)(cr & 0xffffu);
+}
+
 int ensure_pair_tables(elx_handle *h) {
   if (!h->pair || h->pair_ready) return 0;
   const int rc = pair_tables_build(h);
@@ -737,6 +748,7 @@ static int create_on_device(const elx_model *model, const elx_tree *tree, const 
   h->rounds = (opts && opts->philox_rounds == 7) ? 7 : 10;
   h->flags = opts ? opts->flags : 0;
   h->use_pade = use_pade ? 1 : 0;
+  h->weights = w;
   if (opts && opts->philox_rounds != 0 && opts->philox_rounds != 7 && opts->philox_rounds != 10) {
     delete h;
     return fail(nullptr, ELX_E_INVALID, "opts: philox_rounds must be 0, 7 or 10");
@@ -1062,6 +1074,26 @@ int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsi
   h->last_kernel = "k2_freerun_generic<" + std::to_string(h->rounds) + ">";
   CUDA_TRY(h, cudaGetLastError());
   return 0;
+}
+
+int elx_site_components(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, int32_t *comps) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "null handle");
+  if (nsites < 0 || site0 < 0 || (!comps && nsites > 0)) return fail(h, ELX_E_INVALID, "site_components: bad argument");
+  if (nsites == 0) return 0;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int32_t *d = nullptr;
+  CUDA_TRY(h, cudaMalloc((void **)&d, sizeof(int32_t) * (size_t)nsites));
+  SimArgs a = base_args(h);
+  a.comps = d; a.site0 = site0; a.nsites = nsites; a.seed = seed;
+  const unsigned blocks = (unsigned)((nsites + 127) / 128);
+  if (h->rounds == 7) k_site_components<7><<<blocks, 128, 0, h->stream>>>(a);
+  else k_site_components<10><<<blocks, 128, 0, h->stream>>>(a);
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(comps, d, sizeof(int32_t) * (size_t)nsites, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("site_components: ") + cudaGetErrorString(e));
+  return check_error_flag(h);
 }
 
 int elx_synchronize(elx_handle *h) {

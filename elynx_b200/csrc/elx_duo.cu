@@ -28,6 +28,8 @@
 // (ranks of the tiles) -> k_duo_layout (segments = (superblock, component) runs of 16-site groups, CTA tiles) ->
 // k_duo_scatter (site -> bucket slot) -> k2_duo_tiled / k2_duo_generic (states in bucket order, [T][slots]) ->
 // k_duo_unpermute (back to site order, [T][S]).
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -270,20 +272,29 @@ __global__ void __launch_bounds__(256) k_duo_comps(DuoBucketArgs b) {
   }
 }
 
-// base[tile][c] = sites of component c in the earlier tiles of the same superblock; total[j][c] = all of superblock j
+// base[tile][c] = sites of component c in the earlier tiles of the same superblock; total[j][c] = all of superblock j.
+// One warp per (superblock, component): 32 tiles per step, a shuffle scan inside the step.
 __global__ void k_duo_scan(DuoBucketArgs b) {
-  const int C = b.s.C, j = blockIdx.x;
+  const int C = b.s.C, lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (int64_t)b.NSB * C) return;
+  const int j = (int)(wid / C), c = (int)(wid % C);
   const int64_t tiles_per_sb = ((int64_t)1 << DUO_SB) / DUO_TILE;
   const int64_t ntile = (b.M + DUO_TILE - 1) / DUO_TILE;
   const int64_t t_first = (int64_t)j * tiles_per_sb, t_last = min(t_first + tiles_per_sb, ntile);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    uint32_t acc = 0;
-    for (int64_t t = t_first; t < t_last; ++t) {
-      b.base[t * C + c] = acc;
-      acc += b.hist[t * C + c];
+  uint32_t carry = 0;
+  for (int64_t t = t_first; t < t_last; t += 32) {
+    const int64_t tt = t + lane;
+    const uint32_t n = tt < t_last ? b.hist[tt * C + c] : 0u;
+    uint32_t x = n;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    b.total[(int64_t)j * C + c] = acc;
+    if (tt < t_last) b.base[tt * C + c] = carry + x - n;
+    carry += __shfl_sync(0xffffffffu, x, 31);
   }
+  if (lane == 0) b.total[(int64_t)j * C + c] = carry;
 }
 
 // Segments in component-major order (concurrent CTAs then stream the same component's rows) and the CTA tiles.
@@ -381,11 +392,12 @@ __global__ void __launch_bounds__(256) k_duo_unpermute(const uint8_t *__restrict
 // thread picks the bytes of its 16 sites and writes them with one 128-bit store: 1 byte read + 1 byte written per cell.
 constexpr int UNP_TS = 4096;
 constexpr int UNP_WORDS = UNP_TS / 4 + 2 * DUO_MAX_C;  // every run wastes at most two words (its unaligned ends)
-__global__ void __launch_bounds__(256) k_duo_unpermute_smem(const uint8_t *__restrict__ tmp, int64_t tmp_pitch, const uint32_t *__restrict__ pos32,
+constexpr int UNP_R = 4;                               // rows per step
+__global__ void __launch_bounds__(256, 3) k_duo_unpermute_smem(const uint8_t *__restrict__ tmp, int64_t tmp_pitch, const uint32_t *__restrict__ pos32,
                                                            const uint8_t *__restrict__ comp8, int64_t u0, int64_t ua, int64_t ub, int C, int T,
                                                            int rows_per_block, uint8_t *__restrict__ out, int64_t out_pitch) {
   __shared__ uint32_t s_min[DUO_MAX_C], s_cnt[DUO_MAX_C], s_woff[DUO_MAX_C + 1];
-  __shared__ __align__(16) uint32_t s_buf[2][UNP_WORDS];
+  __shared__ __align__(16) uint32_t s_buf[UNP_R][UNP_WORDS];
   const int tid = threadIdx.x;
   const int64_t tile0 = (ua / UNP_TS + blockIdx.x) * (int64_t)UNP_TS;
   s_min[tid] = 0xffffffffu;
@@ -449,29 +461,51 @@ __global__ void __launch_bounds__(256) k_duo_unpermute_smem(const uint8_t *__res
   const int t0 = blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
   const uint8_t *src = tmp + (int64_t)t0 * tmp_pitch;
   uint8_t *dst = out + (int64_t)t0 * out_pitch + col;
-  for (int t = t0; t < t1; ++t) {
-    uint32_t *buf = s_buf[t & 1];
+  // UNP_R rows per step; the loads of the next step are in flight (in registers) while this one is gathered and stored:
+  // a row-at-a-time loop is bound by the latency of its loads (2.4 TB/s measured), not by HBM
+  uint32_t pre[UNP_R][NW];
+  auto prefetch = [&](int t) {
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const uint32_t w = (uint32_t)tid + 256u * k;
-      if (w < W) buf[w] = __ldcs(reinterpret_cast<const uint32_t *>(src + srcoff[k]));
+    for (int r = 0; r < UNP_R; ++r)
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t w = (uint32_t)tid + 256u * k;
+        pre[r][k] = 0;
+        if (w < W && t + r < t1) pre[r][k] = __ldcs(reinterpret_cast<const uint32_t *>(src + (int64_t)r * tmp_pitch + srcoff[k]));
+      }
+  };
+  prefetch(t0);
+  for (int t = t0; t < t1; t += UNP_R) {
+#pragma unroll
+    for (int r = 0; r < UNP_R; ++r)
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t w = (uint32_t)tid + 256u * k;
+        if (w < W) s_buf[r][w] = pre[r][k];
+      }
+    __syncthreads();
+    src += (int64_t)UNP_R * tmp_pitch;
+    if (t + UNP_R < t1) prefetch(t + UNP_R);
+#pragma unroll
+    for (int r = 0; r < UNP_R; ++r) {
+      if (t + r < t1) {
+        const uint8_t *bb = reinterpret_cast<const uint8_t *>(s_buf[r]);
+        if (vec) {
+          uint32_t v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            v[q] = (uint32_t)bb[sidx[4 * q]] | ((uint32_t)bb[sidx[4 * q + 1]] << 8) | ((uint32_t)bb[sidx[4 * q + 2]] << 16) |
+                   ((uint32_t)bb[sidx[4 * q + 3]] << 24);
+          stg_cs_v4(dst, make_uint4(v[0], v[1], v[2], v[3]));
+        } else if (any) {
+#pragma unroll 1
+          for (int i = 0; i < 16; ++i)
+            if (ubase + i >= ua && ubase + i < ub) dst[i] = bb[sidx[i]];
+        }
+      }
+      dst += out_pitch;
     }
     __syncthreads();
-    const uint8_t *bb = reinterpret_cast<const uint8_t *>(buf);
-    if (vec) {
-      uint32_t v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        v[q] = (uint32_t)bb[sidx[4 * q]] | ((uint32_t)bb[sidx[4 * q + 1]] << 8) | ((uint32_t)bb[sidx[4 * q + 2]] << 16) |
-               ((uint32_t)bb[sidx[4 * q + 3]] << 24);
-      stg_cs_v4(dst, make_uint4(v[0], v[1], v[2], v[3]));
-    } else if (any) {
-#pragma unroll 1
-      for (int i = 0; i < 16; ++i)
-        if (ubase + i >= ua && ubase + i < ub) dst[i] = bb[sidx[i]];
-    }
-    src += tmp_pitch;
-    dst += out_pitch;
   }
 }
 
@@ -738,14 +772,14 @@ static bool duo_geometry(int K, int n_slots, DuoTables *dt) {
   if (const char *e = getenv("ELX_DUO_THREADS")) want_threads = atoi(e);  // tuning knobs
   if (const char *e = getenv("ELX_DUO_NSTAGE")) want_stages = atoi(e);
   if (const char *e = getenv("ELX_DUO_MINB")) want_minb = atoi(e);
-  const int cand[3][2] = {{512, 1}, {256, 2}, {256, 1}};
-  for (int ci = 0; ci < 3; ++ci) {
+  const int cand[4][2] = {{640, 1}, {512, 1}, {256, 2}, {256, 1}};
+  for (int ci = 0; ci < 4; ++ci) {
     const int th = cand[ci][0], minb = cand[ci][1];
     if (want_threads && th != want_threads) continue;
     if (want_minb && minb != want_minb) continue;
     const size_t per_cta = (size_t)226 * 1024 / minb;
     const size_t slots = (size_t)(n_slots > 0 ? n_slots : 1) * th * 16;
-    if (128 + 2 * stage + slots > per_cta) continue;
+    if (128 + (th == 640 ? 3 : 2) * stage + slots > per_cta) continue;  // (the 640 class only with a full ring)
     int nstage = (int)((per_cta - 128 - slots) / stage);
     const int cap = want_stages ? want_stages : 3;
     if (nstage > cap) nstage = cap;
@@ -869,10 +903,45 @@ static cudaError_t launch_duo_tiled(int threads, const DuoArgs &fa, int max_tile
 }
 
 template <int ROUNDS>
-static cudaError_t launch_duo_tiled_t(int maxt, int minb, const DuoArgs &fa, int max_tiles, size_t smem, cudaStream_t stream) {
-  if (maxt == 512) return launch_duo_tiled<ROUNDS, 512, 1>(512, fa, max_tiles, smem, stream);
-  if (minb == 2) return launch_duo_tiled<ROUNDS, 256, 2>(256, fa, max_tiles, smem, stream);
-  return launch_duo_tiled<ROUNDS, 256, 1>(256, fa, max_tiles, smem, stream);
+static cudaError_t launch_duo_tiled_t(int maxt, int minb, int threads, const DuoArgs &fa, int max_tiles, size_t smem, cudaStream_t stream) {
+  if (maxt == 640) return launch_duo_tiled<ROUNDS, 640, 1>(threads, fa, max_tiles, smem, stream);
+  if (maxt == 512) return launch_duo_tiled<ROUNDS, 512, 1>(threads, fa, max_tiles, smem, stream);
+  if (minb == 2) return launch_duo_tiled<ROUNDS, 256, 2>(threads, fa, max_tiles, smem, stream);
+  return launch_duo_tiled<ROUNDS, 256, 1>(threads, fa, max_tiles, smem, stream);
+}
+
+// Groups (threads) per CTA tile of this call: any multiple of 32 up to the kernel's class works (the slot stride and the
+// shared-memory budget are those of the class).  A tile count just above a multiple of the SM count costs a whole extra
+// wave (cfg5: 1.25 M sites in tiles of 512 groups = 156 tiles on 148 SMs), so the tile is sized from the EXPECTED segment
+// lengths -- sites of the superblock x component weight -- to minimise  waves x max(tile, 448 threads).
+static int duo_tile_groups(const elx_handle *h, const DuoTables *dt, int64_t u0, int64_t M) {
+  if (const char *e = getenv("ELX_DUO_TILE")) {  // tuning knob
+    const int t = atoi(e);
+    if (t >= 32 && t <= dt->threads && t % 32 == 0) return t;
+  }
+  int ndev_sms = 148;
+  cudaDeviceGetAttribute(&ndev_sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int conc = ndev_sms * (dt->threads == 256 ? dt->minb : 1);
+  double wsum = 0;
+  for (double w : h->weights) wsum += w;
+  const int NSB = (int)((M + ((int64_t)1 << DUO_SB) - 1) >> DUO_SB);
+  int best = dt->threads;
+  double best_cost = 1e300;
+  for (int tg = dt->threads; tg >= (dt->threads >= 512 ? 320 : 128); tg -= 32) {
+    int64_t nt = 0;
+    for (int j = 0; j < NSB; ++j) {
+      const int64_t lo = std::max<int64_t>((int64_t)j << DUO_SB, u0), hi = std::min<int64_t>(((int64_t)j + 1) << DUO_SB, M);
+      for (int c = 0; c < h->C; ++c) {
+        const double n = (double)(hi - lo) * (wsum > 0 ? h->weights[(size_t)c] / wsum : 1.0 / h->C);
+        if (n <= 0) continue;
+        const double groups = (n + 4.0 * std::sqrt(n)) / 16.0 + 1.0;
+        nt += (int64_t)std::ceil(groups / tg);
+      }
+    }
+    const double cost = (double)((nt + conc - 1) / conc) * std::max(tg, dt->threads >= 512 ? 448 : 224);
+    if (cost < best_cost) { best_cost = cost; best = tg; }
+  }
+  return best;
 }
 
 int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
@@ -888,7 +957,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   if (slots_bound >= ((size_t)1 << 32) || M >= ((int64_t)1 << 32))
     return fail(h, ELX_E_UNSUPPORTED, "duo mode: more than 2^32 sites in one device call; split the site range");
   const bool tiled = dt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC);
-  const int tile_groups = dt->threads;
+  const int tile_groups = duo_tile_groups(h, dt, u0, M);
   const int max_tiles = (int)((slots_bound / 16 + tile_groups - 1) / tile_groups) + NSB * C + 1;
   const int64_t tmp_pitch = (int64_t)((slots_bound + 16 + 127) / 128 * 128);  // + 16: the un-permute pass reads whole words
   size_t cs = dt->cap_sites;
@@ -920,7 +989,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   DUO_CUDA(h, cudaMemsetAsync(dt->d_site32, 0, slots_bound * sizeof(uint32_t), h->stream));
   if (h->rounds == 7) k_duo_comps<7><<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
   else k_duo_comps<10><<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
-  k_duo_scan<<<(unsigned)NSB, 256, 0, h->stream>>>(b);
+  k_duo_scan<<<(unsigned)(((int64_t)NSB * C * 32 + 255) / 256), 256, 0, h->stream>>>(b);
   k_duo_layout<<<1, 32, 0, h->stream>>>(b);
   k_duo_scatter<<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
   h->launches += 4;
@@ -939,8 +1008,8 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   fa.rk = philox_round_keys(a.seed);
   cudaError_t e;
   if (tiled) {
-    e = h->rounds == 7 ? launch_duo_tiled_t<7>(dt->threads, dt->minb, fa, max_tiles, dt->smem, h->stream)
-                       : launch_duo_tiled_t<10>(dt->threads, dt->minb, fa, max_tiles, dt->smem, h->stream);
+    e = h->rounds == 7 ? launch_duo_tiled_t<7>(dt->threads, dt->minb, tile_groups, fa, max_tiles, dt->smem, h->stream)
+                       : launch_duo_tiled_t<10>(dt->threads, dt->minb, tile_groups, fa, max_tiles, dt->smem, h->stream);
   } else {
     const dim3 grid((unsigned)max_tiles, (unsigned)(tile_groups * 16 / 256));
     if (h->rounds == 7) k2_duo_generic<7><<<grid, 256, 0, h->stream>>>(fa);
@@ -965,7 +1034,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   }
   h->launches++;
   DUO_CUDA(h, cudaGetLastError());
-  h->last_kernel = tiled ? "k2_duo_tiled<" + std::to_string(h->rounds) + "," + std::to_string(dt->threads) + "," + std::to_string(dt->minb) + ">"
+  h->last_kernel = tiled ? "k2_duo_tiled<" + std::to_string(h->rounds) + "," + std::to_string(dt->threads) + "," + std::to_string(dt->threads == 256 ? dt->minb : 1) + ">"
                          : "k2_duo_generic<" + std::to_string(h->rounds) + ">";
   *used = 1;
   return 0;

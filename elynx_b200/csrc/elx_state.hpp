@@ -34,6 +34,7 @@ struct elx_handle {
   int pair_ready = 0, fast_ready = 0;  // pair rows / node-by-node stage images built from the current P tables (lazy)
   // multi-device handles (elx_opts.n_devices > 1): the handle the caller holds is the primary, peers[] are full handles on
   // the other devices (own stream, own tables); the host-buffer calls shard the site range over all of them
+  std::vector<double> weights;  // host copy of the component weights (all 1 for the single-model API)
   std::vector<elx_handle *> peers;
   int is_peer = 0;
   int64_t launches = 0;

@@ -182,6 +182,12 @@ class Simulator:
                                      _ptr(comps), _ptr(internal), max(nsites, 1)), self._h)
         return leaves, comps, internal
 
+    def site_components(self, seed: int, nsites: int, site0: int = 0) -> np.ndarray:
+        """Component index of every site (the `cs` of simulateAndFlattenMixtureModelPar) without simulating the alignment."""
+        comps = np.empty(nsites, dtype=np.int32)
+        L.check(L.lib().elx_site_components(self._h, C.c_uint64(seed & (2 ** 64 - 1)), site0, nsites, _ptr(comps)), self._h)
+        return comps
+
     def simulate_injected(self, u, want_comps: bool = False, keep_internal: bool = False):
         u = np.ascontiguousarray(u, dtype=np.float64)
         rows = self.n_nodes + (2 if self.is_mixture else 1)

@@ -193,6 +193,10 @@ int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, ui
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves,
                         int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch);
 
+/* The component index of every site of [site0, site0 + nsites) alone -- the `cs` of simulateAndFlattenMixtureModelPar (:257)
+ * without the alignment (writeSiteDists of a sharded run, slynx Simulate.hs:79-89).  Same values as `comps` above. */
+int elx_site_components(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, int32_t *comps);
+
 /* Waits for the work enqueued by the *_device entry points on elx_stream(h) and reports what the kernels flagged
  * ("categorical: bad weights!", ELX_E_BAD_WEIGHTS); the host variants do this themselves. */
 int elx_synchronize(elx_handle *h);
