@@ -1250,10 +1250,16 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int bits = h->K <= 4 ? 2 : 5;  // a packing group is 32 sites: 8 or 20 bytes
   auto packed_pitch = [bits](int64_t n) { return (n + 31) / 32 * (bits == 2 ? 8 : 20); };
-  const int64_t BATCH = 1 << 20;
+  // Duo handles bucket every device call by component inside superblocks (elx_duo.cu): their batches are whole superblocks
+  // (a batch that starts inside one has to draw the components of the sites in front of it again), the first one shorter
+  // when site0 is not aligned.
+  const int64_t BATCH = duo_batch_sites(h) > 0 ? duo_batch_sites(h) : (int64_t)1 << 20;
+  const int64_t boff = duo_batch_sites(h) > 0 ? site0 % BATCH : 0;
   const int NB = 2;
-  const int64_t nbatch = (nsites + BATCH - 1) / BATCH;
+  const int64_t nbatch = (nsites + boff + BATCH - 1) / BATCH;
   const int64_t bmax = nsites < BATCH ? nsites : BATCH;
+  auto batch_begin = [&](int64_t b) { return std::max<int64_t>(0, b * BATCH - boff); };
+  auto batch_len = [&](int64_t b) { return std::min<int64_t>(nsites, (b + 1) * BATCH - boff) - batch_begin(b); };
   const int64_t bpitch = (bmax + 31) & ~(int64_t)31, ppitch = packed_pitch(bmax);  // ppitch: of a full batch; a ragged last batch packs tighter
   size_t stage_mb = 8;
   if (const char *e = getenv("ELX_STAGE_MB")) stage_mb = (size_t)std::min(128, std::max(1, atoi(e)));
@@ -1391,7 +1397,7 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
 
   auto issue_batch = [&](int64_t b) -> int {
     const int i = (int)(b % nbuf);
-    const int64_t b0 = b * BATCH, nb = std::min(BATCH, nsites - b0);
+    const int64_t b0 = batch_begin(b), nb = batch_len(b);
     if (b >= nbuf) CT(cudaStreamWaitEvent(h->stream, copy_done[i], 0));  // staging set i has left the device
     int rc = elx_simulate_device(h, seed, site0 + b0, nb, d_leaves[i], bpitch, d_comps[i], d_internal[i], bpitch);
     if (rc) { cleanup(); return rc; }
@@ -1418,7 +1424,7 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   size_t c = 0;
   for (int64_t b = 0; b < nbatch; ++b) {
     const int i = (int)(b % nbuf);
-    const int64_t b0 = b * BATCH, nb = std::min(BATCH, nsites - b0);
+    const int64_t b0 = batch_begin(b), nb = batch_len(b);
     if (b + 1 < nbatch && (rc = issue_batch(b + 1))) return rc;
     CT(cudaStreamWaitEvent(copy_stream, sim_done[i], 0));
     if (comps) CT(cudaMemcpyAsync(comps + b0, d_comps[i], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, copy_stream));

@@ -7,14 +7,15 @@
 // the 0.5 of the node-by-node walk.
 //
 // A record's alias rows are K x 512 x 4 B = 40 KB PER COMPONENT, so one CTA must work on sites of ONE component
-// (SURVEY hard part 2): every call buckets its sites by component first.  Sites are cut into superblocks of 2^22; inside
+// (SURVEY hard part 2): every call buckets its sites by component first.  Sites are cut into superblocks of 2^SB sites (SB = 20
+// for up to 16 components, 22 for up to 64, else 24); inside
 // a superblock the sites of a component keep their order (a stable counting sort); the rank of a site among the sites
 // of its component and superblock decides which 16-site group it shares its Philox calls with.  Everything is a pure
 // function of (seed, global site), so any partition of a site range over calls and GPUs gives the same alignment.
 //
 // Draw specification (oracle/freerun_spec.c spec_freerun_duo executes it on the CPU; kernels must agree bit for bit):
 //   site s: component c and root state from the shared component / root draws (elx_ptx.cuh draw_comp_root);
-//   B = s >> 22;  rank = #{s' in [B << 22, s) : c(s') = c};  q = rank >> 4;  d = rank & 15
+//   B = s >> SB;  rank = #{s' in [B << SB, s) : c(s') = c};  q = rank >> 4;  d = rank & 15
 //   record g = (out[0..1] | r), state i of r:  48 bytes Z[0..47] = little-endian words of
 //     philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
 //     x24 = Z[3d] | Z[3d+1] << 8 | Z[3d+2] << 16 = [t : 15][j : 9]
@@ -49,7 +50,10 @@ namespace elx {
 constexpr int DUO_COLS = 512;
 constexpr int DUO_MAX_K = 22;       // K * K <= 512
 constexpr int DUO_MAX_C = 256;      // components travel as bytes through the bucketing passes
-constexpr int DUO_SB = 22;          // log2 sites per superblock
+constexpr int DUO_MAX_BATCH = 8;    // main / un-permute kernel pairs of one call
+// log2 sites per superblock: the sites of ONE component inside a superblock should fill several CTA tiles (8192 slots), and a
+// call is pipelined superblock-wise (the un-permute pass of one batch of superblocks runs under the simulation of the next)
+__host__ __device__ inline int duo_sb_log2(int C) { return C <= 16 ? 20 : C <= 64 ? 22 : 24; }
 constexpr int DUO_TILE = 2048;      // sites per block of the bucketing passes (divides a superblock)
 constexpr int DUO_MAX_SLOTS = 24;
 constexpr int DUO_MAX_NSTAGE = 4;
@@ -96,7 +100,12 @@ struct DuoTables {
   uint32_t *d_pos32 = nullptr, *d_site32 = nullptr, *d_hist = nullptr, *d_base = nullptr, *d_total = nullptr, *d_r0 = nullptr;
   DuoSeg *d_seg = nullptr;
   DuoTile *d_tiles = nullptr;
-  int *d_ntiles = nullptr;
+  int *d_ntiles = nullptr, *d_tile_begin = nullptr;
+  int sb = 22;
+  // pipelined calls: the simulation kernels of the batches run on sm[] (concurrently: the next batch's CTAs fill the SMs the
+  // last wave of the previous one leaves idle), the un-permute passes on s2 under the next batch's simulation
+  cudaStream_t s2 = nullptr, sm[DUO_MAX_BATCH] = {};
+  cudaEvent_t ev_main[DUO_MAX_BATCH] = {}, ev_done = nullptr, ev_bucket = nullptr;
   size_t cap_sites = 0, cap_slots = 0, cap_tmp = 0, cap_tiles = 0, cap_hist = 0, cap_seg = 0;
 };
 
@@ -108,7 +117,8 @@ struct DuoArgs {
   const uint32_t *dlo24;
   int stage_bytes, nstage, slot_stride;
   const DuoTile *tiles;
-  const int *ntiles;
+  const int *tile_begin;  // [nbatch + 1]
+  int batch;
   const uint8_t *rootb;
   const uint32_t *site32;
   uint8_t *tmp;
@@ -234,6 +244,10 @@ struct DuoBucketArgs {
   int64_t M;   // sites from base0 to the end of the range
   int64_t u0;  // first site of the range (site0 - base0)
   int NSB;     // superblocks touched
+  int sb;      // log2 sites per superblock
+  int nbatch;  // batches of consecutive superblocks
+  int batch_sb[DUO_MAX_BATCH + 1];  // first superblock (0-based in the call) of every batch
+  int *tile_begin;                  // [nbatch + 1] first tile of every batch (device)
   uint8_t *comp8, *root8, *rootb;
   uint32_t *pos32, *site32, *hist, *base, *total, *r0;
   DuoSeg *seg;
@@ -279,7 +293,7 @@ __global__ void k_duo_scan(DuoBucketArgs b) {
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= (int64_t)b.NSB * C) return;
   const int j = (int)(wid / C), c = (int)(wid % C);
-  const int64_t tiles_per_sb = ((int64_t)1 << DUO_SB) / DUO_TILE;
+  const int64_t tiles_per_sb = ((int64_t)1 << b.sb) / DUO_TILE;
   const int64_t ntile = (b.M + DUO_TILE - 1) / DUO_TILE;
   const int64_t t_first = (int64_t)j * tiles_per_sb, t_last = min(t_first + tiles_per_sb, ntile);
   uint32_t carry = 0;
@@ -297,33 +311,38 @@ __global__ void k_duo_scan(DuoBucketArgs b) {
   if (lane == 0) b.total[(int64_t)j * C + c] = carry;
 }
 
-// Segments in component-major order (concurrent CTAs then stream the same component's rows) and the CTA tiles.
+// Segments batch by batch, component-major inside a batch (concurrent CTAs then stream the same component's rows), and the
+// CTA tiles; tile_begin[b] = first tile of batch b.
 __global__ void k_duo_layout(DuoBucketArgs b) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const int C = b.s.C;
   uint64_t slot = 0;
   int nt = 0;
-  const uint64_t sb0 = b.base0 >> DUO_SB;
-  for (int c = 0; c < C; ++c)
-    for (int j = 0; j < b.NSB; ++j) {
-      const uint32_t r0 = j == 0 ? b.r0[c] : 0u, r1 = b.total[(int64_t)j * C + c];
-      DuoSeg sg;
-      sg.q0 = r0 >> 4;
-      sg.ngroups = r1 > r0 ? ((r1 + 15u) >> 4) - sg.q0 : 0u;
-      sg.slot_off = slot;
-      b.seg[(int64_t)j * C + c] = sg;
-      for (uint32_t g = 0; g < sg.ngroups; g += (uint32_t)b.tile_groups) {
-        if (nt < b.max_tiles) {
-          DuoTile t;
-          t.comp = (uint32_t)c; t.q_first = sg.q0 + g; t.ngroups = min((uint32_t)b.tile_groups, sg.ngroups - g);
-          t.sb_lo = (uint32_t)(sb0 + j); t.sb_hi = (uint32_t)((sb0 + j) >> 32); t.pad = 0;
-          t.slot_off = slot + (uint64_t)g * 16u;
-          b.tiles[nt] = t;
+  const uint64_t sb0 = b.base0 >> b.sb;
+  for (int bt = 0; bt < b.nbatch; ++bt) {
+    b.tile_begin[bt] = nt < b.max_tiles ? nt : b.max_tiles;
+    for (int c = 0; c < C; ++c)
+      for (int j = b.batch_sb[bt]; j < b.batch_sb[bt + 1]; ++j) {
+        const uint32_t r0 = j == 0 ? b.r0[c] : 0u, r1 = b.total[(int64_t)j * C + c];
+        DuoSeg sg;
+        sg.q0 = r0 >> 4;
+        sg.ngroups = r1 > r0 ? ((r1 + 15u) >> 4) - sg.q0 : 0u;
+        sg.slot_off = slot;
+        b.seg[(int64_t)j * C + c] = sg;
+        for (uint32_t g = 0; g < sg.ngroups; g += (uint32_t)b.tile_groups) {
+          if (nt < b.max_tiles) {
+            DuoTile t;
+            t.comp = (uint32_t)c; t.q_first = sg.q0 + g; t.ngroups = min((uint32_t)b.tile_groups, sg.ngroups - g);
+            t.sb_lo = (uint32_t)(sb0 + j); t.sb_hi = (uint32_t)((sb0 + j) >> 32); t.pad = 0;
+            t.slot_off = slot + (uint64_t)g * 16u;
+            b.tiles[nt] = t;
+          }
+          ++nt;
         }
-        ++nt;
+        slot += (uint64_t)sg.ngroups * 16u;
       }
-      slot += (uint64_t)sg.ngroups * 16u;
-    }
+  }
+  b.tile_begin[b.nbatch] = nt < b.max_tiles ? nt : b.max_tiles;
   *b.ntiles = nt < b.max_tiles ? nt : b.max_tiles;
   if (nt > b.max_tiles) atomicExch(b.s.error_flag, -21);
 }
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(256) k_duo_scatter(DuoBucketArgs b) {
   __shared__ uint16_t wcnt[8][DUO_MAX_C];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t t0 = (int64_t)blockIdx.x * DUO_TILE;
-  const int j = (int)(t0 >> DUO_SB);
+  const int j = (int)(t0 >> b.sb);
   run[tid] = tid < C ? b.base[(int64_t)blockIdx.x * C + tid] : 0u;
   for (int k = 0; k < DUO_TILE / 256; ++k) {
     for (int x = 0; x < 8; ++x) wcnt[x][tid] = 0;
@@ -509,6 +528,171 @@ __global__ void __launch_bounds__(256, 3) k_duo_unpermute_smem(const uint8_t *__
   }
 }
 
+// The hot version: asynchronous copies, no load passes through a register, so enough bytes are in flight to cover the HBM
+// latency (the register version above stops at 3.1 TB/s).  The runs of a row are brought into shared memory as 16-byte aligned
+// supersets, UNP_R rows per stage, two stages in flight:
+//   few components (TMA = true): one cp.async.bulk per run and row, issued by one warp, behind full mbarriers;
+//   many components (runs of a few dozen bytes, where the TMA's per-copy cost dominates): 16-byte cp.async.cg per thread
+//   with commit groups.
+// The gather maps lane l to 4 consecutive sites of each quarter of the block, so that the byte reads of a warp fall into
+// neighbouring words (few bank conflicts) and its 32-bit stores are contiguous.  THREADS = 128 (2048 sites per block, 17 KB of
+// shared memory, 8 K registers) fits onto an SM NEXT TO a CTA of the simulation kernel: that is how the pass hides under the
+// next batch's simulation.  Row buffer = TS + 32 C bytes: C <= UNP_ASYNC_MAX_C.
+constexpr int UNP_ASYNC_MAX_C = 128;
+constexpr int UNP_MAX_CHUNKS = 3;  // 16-byte chunks per thread and row of the cp.async form: (TS + 32 C) / 16 / THREADS
+template <int THREADS, bool TMA>
+__global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *__restrict__ tmp, int64_t tmp_pitch, const uint32_t *__restrict__ pos32,
+                                                                const uint8_t *__restrict__ comp8, int64_t u0, int64_t ua, int64_t ub, int C, int T,
+                                                                int rows_per_block, int rowb, uint8_t *__restrict__ out, int64_t out_pitch) {
+  constexpr int TS = THREADS * 16, QS = THREADS * 4;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ uint32_t s_min[UNP_ASYNC_MAX_C], s_cnt[UNP_ASYNC_MAX_C], s_off[UNP_ASYNC_MAX_C + 1];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t tile0 = (ua / TS + blockIdx.x) * (int64_t)TS;
+  for (int c = tid; c < UNP_ASYNC_MAX_C; c += THREADS) { s_min[c] = 0xffffffffu; s_cnt[c] = 0; }
+  if (TMA && tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  __syncthreads();
+  // site of (quarter k, byte i): tile0 + QS k + 4 tid + i
+  uint32_t cc[16], pp[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) {
+    const int64_t u = tile0 + QS * (x >> 2) + 4 * tid + (x & 3);
+    cc[x] = 0xffffffffu;
+    pp[x] = 0;
+    if (u >= ua && u < ub) {
+      cc[x] = comp8[u];
+      pp[x] = pos32[u - u0];
+      atomicMin(&s_min[cc[x]], pp[x]);
+      atomicAdd(&s_cnt[cc[x]], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {  // byte offsets of the runs' aligned supersets in a row buffer
+    uint32_t carry = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + tid;
+      uint32_t n = 0;
+      if (c < C && s_cnt[c]) n = ((s_min[c] & 15u) + s_cnt[c] + 15u) & ~15u;
+      uint32_t x = n;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (tid >= o) x += y;
+      }
+      if (c < C) s_off[c] = carry + x - n;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (tid == 0) s_off[C] = carry;
+  }
+  __syncthreads();
+  const uint32_t row_bytes = s_off[C];
+  uint16_t sidx[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) sidx[x] = cc[x] == 0xffffffffu ? (uint16_t)0 : (uint16_t)(s_off[cc[x]] + (pp[x] - (s_min[cc[x]] & ~15u)));
+  const int t0 = blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+  const int ngroups = (t1 - t0 + UNP_R - 1) / UNP_R;
+  const uint32_t stage_bytes = (uint32_t)(UNP_R * rowb);
+  const uint32_t dsm_u32 = smem_u32(dsm);
+  // cp.async form: this thread's 16-byte chunks of a row (chunk x of the row buffer <- tmp row + csrc[x])
+  uint32_t csrc[UNP_MAX_CHUNKS];
+  if (!TMA) {
+#pragma unroll
+    for (int k = 0; k < UNP_MAX_CHUNKS; ++k) {
+      const uint32_t x = (uint32_t)tid + (uint32_t)THREADS * k;
+      csrc[k] = 0xffffffffu;
+      if (x * 16u < row_bytes) {
+        int lo = 0, hi = C - 1;  // last component whose run starts at or before chunk x (empty runs share their successor's offset)
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_off[mid] <= x * 16u) lo = mid; else hi = mid - 1;
+        }
+        csrc[k] = (s_min[lo] & ~15u) + (x * 16u - s_off[lo]);
+      }
+    }
+  }
+  auto issue = [&](int g) {  // the rows of group g into stage g & 1
+    const int s = g & 1, ta = t0 + g * UNP_R, nr = min(UNP_R, t1 - ta);
+    if (TMA) {  // (warp 0 only)
+      const uint32_t bar = smem_u32(&s_bar[s]);
+      if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)nr);
+      __syncwarp();
+      for (int c = lane; c < C; c += 32) {
+        if (!s_cnt[c]) continue;
+        const uint32_t a16 = s_min[c] & ~15u, nb = ((s_min[c] & 15u) + s_cnt[c] + 15u) & ~15u;
+        for (int r = 0; r < nr; ++r)
+          tma_bulk_g2s(dsm_u32 + (uint32_t)s * stage_bytes + (uint32_t)r * (uint32_t)rowb + s_off[c], tmp + (int64_t)(ta + r) * tmp_pitch + a16, nb, bar);
+      }
+    } else {  // (every thread)
+#pragma unroll
+      for (int k = 0; k < UNP_MAX_CHUNKS; ++k) {
+        if (csrc[k] == 0xffffffffu) continue;
+        const uint32_t dst = dsm_u32 + (uint32_t)s * stage_bytes + ((uint32_t)tid + (uint32_t)THREADS * k) * 16u;
+        for (int r = 0; r < nr; ++r)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)r * (uint32_t)rowb),
+                       "l"(tmp + (int64_t)(ta + r) * tmp_pitch + csrc[k]) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  if (row_bytes && (!TMA || tid < 32)) {
+    issue(0);
+    if (ngroups > 1) issue(1);
+    else if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");  // (keeps the group count uniform)
+  }
+  const int64_t colq = tile0 + 4 * tid - u0;  // column of this thread's first site of quarter 0
+  bool vec[4], anyq[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t ub0 = tile0 + QS * k + 4 * tid;
+    anyq[k] = ub0 + 4 > ua && ub0 < ub;
+    vec[k] = ub0 >= ua && ub0 + 4 <= ub && ((out_pitch & 3) == 0) && (((reinterpret_cast<uintptr_t>(out) + (uintptr_t)(colq + QS * k)) & 3) == 0);
+  }
+  uint8_t *dst = out + (int64_t)t0 * out_pitch + colq;
+  for (int g = 0; g < ngroups; ++g) {
+    const int s = g & 1, ta = t0 + g * UNP_R, nr = min(UNP_R, t1 - ta);
+    if (row_bytes) {
+      if (TMA) {
+        mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((g >> 1) & 1));
+      } else {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // all but the newest group (the next stage) have landed
+        __syncthreads();
+      }
+    }
+    const uint8_t *sb = dsm + (size_t)s * stage_bytes;
+#pragma unroll
+    for (int r = 0; r < UNP_R; ++r) {
+      if (r < nr) {
+        const uint8_t *bb = sb + (size_t)r * rowb;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (vec[k]) {
+            const uint32_t v = (uint32_t)bb[sidx[4 * k]] | ((uint32_t)bb[sidx[4 * k + 1]] << 8) | ((uint32_t)bb[sidx[4 * k + 2]] << 16) |
+                               ((uint32_t)bb[sidx[4 * k + 3]] << 24);
+            __stcs(reinterpret_cast<uint32_t *>(dst + QS * k), v);
+          } else if (anyq[k]) {
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int64_t u = tile0 + QS * k + 4 * tid + i;
+              if (u >= ua && u < ub) dst[QS * k + i] = bb[sidx[4 * k + i]];
+            }
+          }
+        }
+      }
+      dst += out_pitch;
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (row_bytes && (!TMA || tid < 32)) {
+      if (g + 2 < ngroups) issue(g + 2);
+      else if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2 duo mode, generic: tables through L1/L2, one thread per bucket slot (the cross-check of the tiled kernel).
 // ---------------------------------------------------------------------------------------------
@@ -532,8 +716,9 @@ __device__ __forceinline__ uint32_t duo_draw24(uint32_t q, uint32_t comp, uint32
 template <int ROUNDS>
 __global__ void __launch_bounds__(256) k2_duo_generic(DuoArgs fa) {
   const SimArgs &a = fa.s;
-  if ((int)blockIdx.x >= *fa.ntiles) return;
-  const DuoTile tile = fa.tiles[blockIdx.x];
+  const int tile_first = fa.tile_begin[fa.batch];
+  if ((int)blockIdx.x >= fa.tile_begin[fa.batch + 1] - tile_first) return;
+  const DuoTile tile = fa.tiles[tile_first + blockIdx.x];
   const uint32_t idx = blockIdx.y * 256u + threadIdx.x;  // slot of the tile
   if ((idx >> 4) >= tile.ngroups) return;
   const uint32_t q = tile.q_first + (idx >> 4);
@@ -698,14 +883,15 @@ template <int ROUNDS, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT + 32, MINB) k2_duo_tiled(DuoArgs fa) {
   const int THREADS = (int)blockDim.x - 32;
   extern __shared__ __align__(128) uint8_t smem[];
-  if ((int)blockIdx.x >= *fa.ntiles) return;
+  const int tile_first = fa.tile_begin[fa.batch];
+  if ((int)blockIdx.x >= fa.tile_begin[fa.batch + 1] - tile_first) return;
   const int tid = threadIdx.x;
   const int nstage = fa.nstage;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty_bar = full_bar + DUO_MAX_NSTAGE;
   const uint32_t stage_smem = smem_u32(smem + 128);
   const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
-  const DuoTile tile = fa.tiles[blockIdx.x];
+  const DuoTile tile = fa.tiles[tile_first + blockIdx.x];
 
   if (tid == 0) {
     for (int i = 0; i < nstage; ++i) {
@@ -758,6 +944,12 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) k2_duo_tiled(DuoArgs fa) {
     cudaError_t _e = (expr);                                                                                    \
     if (_e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
   } while (0)
+
+int64_t duo_batch_sites(const elx_handle *h) {
+  const DuoTables *dt = static_cast<const DuoTables *>(h->duo);
+  if (!dt) return 0;
+  return (int64_t)1 << std::min(dt->sb, 22);  // (2^24-site superblocks are walked in quarters: device buffers stay bounded)
+}
 
 int duo_groups(const elx_handle *h) {
   const DuoTables *dt = static_cast<const DuoTables *>(h->duo);
@@ -821,6 +1013,19 @@ int duo_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_ftab, (size_t)G * h->C * dt->stage_bytes));
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_dlo24, sizeof(uint32_t) * rows * DUO_COLS));
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_ntiles, sizeof(int)));
+  DUO_CUDA(h, cudaMalloc((void **)&dt->d_tile_begin, sizeof(int) * (DUO_MAX_BATCH + 1)));
+  dt->sb = duo_sb_log2(h->C);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    DUO_CUDA(h, cudaStreamCreateWithPriority(&dt->s2, cudaStreamNonBlocking, hi));
+    for (cudaEvent_t &e : dt->ev_main) DUO_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    DUO_CUDA(h, cudaEventCreateWithFlags(&dt->ev_done, cudaEventDisableTiming));
+    DUO_CUDA(h, cudaEventCreateWithFlags(&dt->ev_bucket, cudaEventDisableTiming));
+    // earlier batches get the higher priority: the block scheduler then finishes them in order (measured without: four
+    // concurrent grids share the SMs evenly and all finish at the end), yet the next batch fills the SMs a tail leaves idle
+    for (int i = 0; i < DUO_MAX_BATCH; ++i) DUO_CUDA(h, cudaStreamCreateWithPriority(&dt->sm[i], cudaStreamNonBlocking, std::min(lo, hi + 1 + i)));
+  }
   DUO_CUDA(h, cudaMemcpy(dt->d_recs, dev.data(), sizeof(DuoRecDev) * (size_t)G, cudaMemcpyHostToDevice));
   DUO_CUDA(h, cudaMemcpy(dt->d_caps, caps.data(), sizeof(DuoCapDev) * (size_t)G, cudaMemcpyHostToDevice));
   return 0;
@@ -862,7 +1067,12 @@ void duo_free(elx_handle *h) {
   cudaFree(dt->d_recs); cudaFree(dt->d_caps); cudaFree(dt->d_ftab); cudaFree(dt->d_dlo24); cudaFree(dt->d_ntiles);
   cudaFree(dt->d_comp8); cudaFree(dt->d_root8); cudaFree(dt->d_rootb); cudaFree(dt->d_tmp); cudaFree(dt->d_pos32);
   cudaFree(dt->d_site32); cudaFree(dt->d_hist); cudaFree(dt->d_base); cudaFree(dt->d_total); cudaFree(dt->d_r0);
-  cudaFree(dt->d_seg); cudaFree(dt->d_tiles);
+  cudaFree(dt->d_seg); cudaFree(dt->d_tiles); cudaFree(dt->d_tile_begin);
+  if (dt->s2) { cudaStreamSynchronize(dt->s2); cudaStreamDestroy(dt->s2); }
+  for (cudaEvent_t e : dt->ev_main) if (e) cudaEventDestroy(e);
+  if (dt->ev_done) cudaEventDestroy(dt->ev_done);
+  if (dt->ev_bucket) cudaEventDestroy(dt->ev_bucket);
+  for (cudaStream_t st : dt->sm) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   delete dt;
   h->duo = nullptr;
 }
@@ -898,6 +1108,8 @@ template <int ROUNDS, int MAXT, int MINB>
 static cudaError_t launch_duo_tiled(int threads, const DuoArgs &fa, int max_tiles, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(k2_duo_tiled<ROUNDS, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k2_duo_tiled<ROUNDS, MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   k2_duo_tiled<ROUNDS, MAXT, MINB><<<(unsigned)max_tiles, threads + 32, smem, stream>>>(fa);
   return cudaGetLastError();
 }
@@ -924,13 +1136,13 @@ static int duo_tile_groups(const elx_handle *h, const DuoTables *dt, int64_t u0,
   const int conc = ndev_sms * (dt->threads == 256 ? dt->minb : 1);
   double wsum = 0;
   for (double w : h->weights) wsum += w;
-  const int NSB = (int)((M + ((int64_t)1 << DUO_SB) - 1) >> DUO_SB);
+  const int NSB = (int)((M + ((int64_t)1 << dt->sb) - 1) >> dt->sb);
   int best = dt->threads;
   double best_cost = 1e300;
   for (int tg = dt->threads; tg >= (dt->threads >= 512 ? 320 : 128); tg -= 32) {
     int64_t nt = 0;
     for (int j = 0; j < NSB; ++j) {
-      const int64_t lo = std::max<int64_t>((int64_t)j << DUO_SB, u0), hi = std::min<int64_t>(((int64_t)j + 1) << DUO_SB, M);
+      const int64_t lo = std::max<int64_t>((int64_t)j << dt->sb, u0), hi = std::min<int64_t>(((int64_t)j + 1) << dt->sb, M);
       for (int c = 0; c < h->C; ++c) {
         const double n = (double)(hi - lo) * (wsum > 0 ? h->weights[(size_t)c] / wsum : 1.0 / h->C);
         if (n <= 0) continue;
@@ -938,7 +1150,10 @@ static int duo_tile_groups(const elx_handle *h, const DuoTables *dt, int64_t u0,
         nt += (int64_t)std::ceil(groups / tg);
       }
     }
-    const double cost = (double)((nt + conc - 1) / conc) * std::max(tg, dt->threads >= 512 ? 448 : 224);
+    // a CTA's time goes with the busiest sub-partition: ceil(warps / 4); fewer than 4 warps per sub-partition do not saturate it
+    const int wps = (tg / 32 + 3) / 4;
+    const double eff = dt->threads == 256 ? 1.0 : (wps >= 4 ? 1.0 : wps == 3 ? 0.87 : 0.65);
+    const double cost = (double)((nt + conc - 1) / conc) * wps / eff;
     if (cost < best_cost) { best_cost = cost; best = tg; }
   }
   return best;
@@ -949,16 +1164,16 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   DuoTables *dt = static_cast<DuoTables *>(h->duo);
   if (!dt || a.internal) return 0;  // summed-out nodes have no states: `simulate` (keep internal states) draws node by node
   const int C = h->C;
-  const uint64_t base0 = ((uint64_t)a.site0 >> DUO_SB) << DUO_SB;
+  const uint64_t base0 = ((uint64_t)a.site0 >> dt->sb) << dt->sb;
   const int64_t u0 = (int64_t)((uint64_t)a.site0 - base0), M = u0 + a.nsites;
-  const int NSB = (int)((M + ((int64_t)1 << DUO_SB) - 1) >> DUO_SB);
+  const int NSB = (int)((M + ((int64_t)1 << dt->sb) - 1) >> dt->sb);
   const int64_t ntile_b = (M + DUO_TILE - 1) / DUO_TILE;
   const size_t slots_bound = (size_t)a.nsites + 32u * (size_t)NSB * C + 16;
   if (slots_bound >= ((size_t)1 << 32) || M >= ((int64_t)1 << 32))
     return fail(h, ELX_E_UNSUPPORTED, "duo mode: more than 2^32 sites in one device call; split the site range");
   const bool tiled = dt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC);
-  const int tile_groups = duo_tile_groups(h, dt, u0, M);
-  const int max_tiles = (int)((slots_bound / 16 + tile_groups - 1) / tile_groups) + NSB * C + 1;
+  int tile_groups = duo_tile_groups(h, dt, u0, M);
+  const int max_tiles = (int)((slots_bound / 16 + 511) / 512) * 2 + NSB * C + 1;  // (tiles are never smaller than 320 groups unless ELX_DUO_TILE says so)
   const int64_t tmp_pitch = (int64_t)((slots_bound + 16 + 127) / 128 * 128);  // + 16: the un-permute pass reads whole words
   size_t cs = dt->cap_sites;
   DUO_CUDA(h, duo_grow(&dt->d_comp8, &cs, (size_t)M));
@@ -978,9 +1193,35 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   DUO_CUDA(h, duo_grow(&dt->d_tiles, &dt->cap_tiles, (size_t)max_tiles));
   DUO_CUDA(h, duo_grow(&dt->d_tmp, &dt->cap_tmp, (size_t)tmp_pitch * h->T));
 
+  // Optional pipeline (ELX_DUO_PIPELINE=1): batches of consecutive superblocks, the un-permute pass of a batch (HBM-bound) on
+  // a second stream under the simulation of the next one (integer-bound).  Measured on cfg3 / cfg4 (B200): the two kernels do
+  // run side by side (128-thread un-permute blocks next to a 544-thread simulation CTA), but the simulation slows down by
+  // half while they do -- both hammer shared memory with random byte / word reads -- and the call ends 5 % sooner (cfg3,
+  // 15.7 against 16.5 ms) or 5 % later (cfg4): off by default.
+  int conc = 148;
+  cudaDeviceGetAttribute(&conc, cudaDevAttrMultiProcessorCount, h->device);
+  conc *= dt->threads == 256 ? dt->minb : 1;
+  static const int want_batches = getenv("ELX_DUO_PIPELINE") && atoi(getenv("ELX_DUO_PIPELINE")) > 0 ? 0 : 1;
+  if (NSB >= 2 && want_batches != 1 && tile_groups > 544) tile_groups = 512;  // (registers for a co-resident un-permute block)
+  const double sb_tiles = (double)((int64_t)1 << dt->sb) / 16.0 / tile_groups;  // CTA tiles of one full superblock
+  const int L = std::max(1, (int)std::ceil(0.75 * conc / sb_tiles));
+  std::vector<int> batch_sb{0};
+  if (want_batches != 1) {
+    int rem = NSB;
+    while ((int)batch_sb.size() < DUO_MAX_BATCH - 1 && rem >= 2 * L && rem >= 2) {
+      const int take = std::max(L, (rem + 1) / 2);
+      batch_sb.push_back(batch_sb.back() + take);
+      rem -= take;
+    }
+  }
+  if (batch_sb.back() != NSB) batch_sb.push_back(NSB);
+  const int nbatch = (int)batch_sb.size() - 1;
+
   DuoBucketArgs b;
   memset(&b, 0, sizeof b);
-  b.s = a; b.base0 = base0; b.M = M; b.u0 = u0; b.NSB = NSB;
+  b.s = a; b.base0 = base0; b.M = M; b.u0 = u0; b.NSB = NSB; b.sb = dt->sb; b.nbatch = nbatch;
+  for (int i = 0; i <= nbatch; ++i) b.batch_sb[i] = batch_sb[(size_t)i];
+  b.tile_begin = dt->d_tile_begin;
   b.comp8 = dt->d_comp8; b.root8 = dt->d_root8; b.rootb = dt->d_rootb; b.pos32 = dt->d_pos32; b.site32 = dt->d_site32;
   b.hist = dt->d_hist; b.base = dt->d_base; b.total = dt->d_total; b.r0 = dt->d_r0; b.seg = dt->d_seg; b.tiles = dt->d_tiles;
   b.ntiles = dt->d_ntiles; b.tile_groups = tile_groups; b.max_tiles = max_tiles;
@@ -994,6 +1235,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   k_duo_scatter<<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
   h->launches += 4;
   DUO_CUDA(h, cudaGetLastError());
+  if (nbatch > 1) DUO_CUDA(h, cudaEventRecord(dt->ev_bucket, h->stream));
 
   DuoArgs fa;
   memset(&fa, 0, sizeof fa);
@@ -1001,39 +1243,104 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   fa.s.n_slots = dt->prog.n_slots;
   fa.G = dt->G; fa.recs = dt->d_recs; fa.ftab = dt->d_ftab; fa.dlo24 = dt->d_dlo24;
   fa.stage_bytes = dt->stage_bytes; fa.nstage = dt->nstage; fa.slot_stride = dt->threads * 16;
-  fa.tiles = dt->d_tiles; fa.ntiles = dt->d_ntiles; fa.rootb = dt->d_rootb; fa.site32 = dt->d_site32;
+  fa.tiles = dt->d_tiles; fa.tile_begin = dt->d_tile_begin; fa.rootb = dt->d_rootb; fa.site32 = dt->d_site32;
   fa.tmp = dt->d_tmp; fa.tmp_pitch = tmp_pitch; fa.base0 = base0;
   fa.mhi = (uint32_t)((65536 / h->K + 1) << 8);
   fa.negk256 = (uint32_t)(-(h->K << 8));
   fa.rk = philox_round_keys(a.seed);
-  cudaError_t e;
-  if (tiled) {
-    e = h->rounds == 7 ? launch_duo_tiled_t<7>(dt->threads, dt->minb, tile_groups, fa, max_tiles, dt->smem, h->stream)
-                       : launch_duo_tiled_t<10>(dt->threads, dt->minb, tile_groups, fa, max_tiles, dt->smem, h->stream);
-  } else {
-    const dim3 grid((unsigned)max_tiles, (unsigned)(tile_groups * 16 / 256));
-    if (h->rounds == 7) k2_duo_generic<7><<<grid, 256, 0, h->stream>>>(fa);
-    else k2_duo_generic<10><<<grid, 256, 0, h->stream>>>(fa);
-    e = cudaGetLastError();
-  }
-  if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("duo kernel launch: ") + cudaGetErrorString(e));
-  h->launches++;
-  static const int unperm_mode = getenv("ELX_DUO_UNPERM") ? atoi(getenv("ELX_DUO_UNPERM")) : 2;  // tuning knob: 1 = plain gather
-  if (unperm_mode == 1) {
-    const int rpb = 64;
-    const dim3 ugrid((unsigned)((a.nsites + 255) / 256), (unsigned)((h->T + rpb - 1) / rpb));
-    k_duo_unpermute<<<ugrid, 256, 0, h->stream>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, a.nsites, h->T, rpb, a.leaves, a.leaves_pitch);
-  } else {
-    const int64_t nt = (M + UNP_TS - 1) / UNP_TS - u0 / UNP_TS;
+  static const int unperm_mode = getenv("ELX_DUO_UNPERM") ? atoi(getenv("ELX_DUO_UNPERM")) : 3;  // tuning knob: 1 = plain gather, 2 = word copies, 3 = TMA
+  static const bool timeline = getenv("ELX_DUO_TIMELINE") != nullptr;  // debug: per-kernel start / end times of a call on stderr
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (timeline) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  mark(h->stream);
+  for (int bt = 0; bt < nbatch; ++bt) {
+    // sites of this batch in bucketing index space, and an upper bound of its CTA tiles
+    const int64_t ua = std::max<int64_t>(u0, (int64_t)batch_sb[(size_t)bt] << dt->sb), ub = std::min<int64_t>(M, (int64_t)batch_sb[(size_t)bt + 1] << dt->sb);
+    int grid_tiles = 0;
+    for (int j = batch_sb[(size_t)bt]; j < batch_sb[(size_t)bt + 1]; ++j) {
+      const int64_t nj = std::min<int64_t>(M, ((int64_t)j + 1) << dt->sb) - std::max<int64_t>(u0, (int64_t)j << dt->sb);
+      grid_tiles += (int)((nj / 16 + 2 * C) / tile_groups) + C + 1;
+    }
+    if (grid_tiles > max_tiles) grid_tiles = max_tiles;
+    fa.batch = bt;
+    cudaStream_t ms = nbatch > 1 ? dt->sm[bt] : h->stream;
+    if (nbatch > 1) DUO_CUDA(h, cudaStreamWaitEvent(ms, dt->ev_bucket, 0));
+    mark(ms);
+    cudaError_t e;
+    if (tiled) {
+      e = h->rounds == 7 ? launch_duo_tiled_t<7>(dt->threads, dt->minb, tile_groups, fa, grid_tiles, dt->smem, ms)
+                         : launch_duo_tiled_t<10>(dt->threads, dt->minb, tile_groups, fa, grid_tiles, dt->smem, ms);
+    } else {
+      const dim3 grid((unsigned)grid_tiles, (unsigned)(tile_groups * 16 / 256));
+      if (h->rounds == 7) k2_duo_generic<7><<<grid, 256, 0, ms>>>(fa);
+      else k2_duo_generic<10><<<grid, 256, 0, ms>>>(fa);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return fail(h, ELX_E_CUDA, std::string("duo kernel launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    mark(ms);
+    cudaStream_t us = h->stream;
+    if (nbatch > 1) {
+      us = dt->s2;
+      DUO_CUDA(h, cudaEventRecord(dt->ev_main[bt], ms));
+      DUO_CUDA(h, cudaStreamWaitEvent(us, dt->ev_main[bt], 0));
+    }
+    mark(us);
     // enough blocks to fill the machine a few times over, rows split only when there are few site tiles
-    int rpb = h->T;
-    while (rpb > 64 && nt * ((h->T + rpb - 1) / rpb) < 148 * 16) rpb = (rpb + 1) / 2;
-    const dim3 ugrid((unsigned)nt, (unsigned)((h->T + rpb - 1) / rpb));
-    k_duo_unpermute_smem<<<ugrid, 256, 0, h->stream>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, dt->d_comp8, u0, u0, M, C, h->T, rpb, a.leaves,
-                                                       a.leaves_pitch);
+    auto rows_per_block = [&](int64_t nt) {
+      int rpb = h->T;
+      while (rpb > 64 && nt * ((h->T + rpb - 1) / rpb) < 148 * 16) rpb = (rpb + 1) / 2;
+      return (rpb + UNP_R - 1) / UNP_R * UNP_R;
+    };
+    if (unperm_mode == 1) {
+      const int rpb = 64;
+      const dim3 ugrid((unsigned)((ub - ua + 255) / 256), (unsigned)((h->T + rpb - 1) / rpb));
+      k_duo_unpermute<<<ugrid, 256, 0, us>>>(dt->d_tmp, tmp_pitch, dt->d_pos32 + (ua - u0), ub - ua, h->T, rpb, a.leaves + (ua - u0), a.leaves_pitch);
+    } else if (unperm_mode == 3 && C <= 16) {
+      constexpr int TS = 128 * 16;
+      const int64_t nt = (ub + TS - 1) / TS - ua / TS;
+      const int rpb = rows_per_block(nt), rowb = (TS + 32 * C + 127) / 128 * 128;
+      const size_t dsmem = (size_t)2 * UNP_R * rowb;
+      DUO_CUDA(h, cudaFuncSetAttribute(k_duo_unpermute_async<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+      // the same shared-memory carve-out as the simulation kernel: an SM does not run two carve-outs side by side
+      DUO_CUDA(h, cudaFuncSetAttribute(k_duo_unpermute_async<128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      const dim3 ugrid((unsigned)nt, (unsigned)((h->T + rpb - 1) / rpb));
+      k_duo_unpermute_async<128, true><<<ugrid, 128, dsmem, us>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, dt->d_comp8, u0, ua, ub, C, h->T, rpb, rowb,
+                                                                a.leaves, a.leaves_pitch);
+    } else if (unperm_mode == 3 && C <= UNP_ASYNC_MAX_C) {
+      constexpr int TS = 256 * 16;
+      const int64_t nt = (ub + TS - 1) / TS - ua / TS;
+      const int rpb = rows_per_block(nt), rowb = (TS + 32 * C + 127) / 128 * 128;
+      const size_t dsmem = (size_t)2 * UNP_R * rowb;
+      DUO_CUDA(h, cudaFuncSetAttribute(k_duo_unpermute_async<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+      const dim3 ugrid((unsigned)nt, (unsigned)((h->T + rpb - 1) / rpb));
+      k_duo_unpermute_async<256, false><<<ugrid, 256, dsmem, us>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, dt->d_comp8, u0, ua, ub, C, h->T, rpb, rowb,
+                                                                 a.leaves, a.leaves_pitch);
+    } else {
+      const int64_t nt = (ub + UNP_TS - 1) / UNP_TS - ua / UNP_TS;
+      const int rpb = rows_per_block(nt);
+      const dim3 ugrid((unsigned)nt, (unsigned)((h->T + rpb - 1) / rpb));
+      k_duo_unpermute_smem<<<ugrid, 256, 0, us>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, dt->d_comp8, u0, ua, ub, C, h->T, rpb, a.leaves, a.leaves_pitch);
+    }
+    h->launches++;
+    mark(us);
+    DUO_CUDA(h, cudaGetLastError());
   }
-  h->launches++;
-  DUO_CUDA(h, cudaGetLastError());
+  if (timeline) {
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[elx duo] %d batch(es), tile %d groups:", nbatch, tile_groups);
+    for (size_t i = 1; i < tev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[0], tev[i]);
+      fprintf(stderr, "%s%.2f", (i - 1) % 4 == 0 ? " | sim " : (i - 1) % 4 == 2 ? " unp " : "-", ms);
+    }
+    fprintf(stderr, " ms\n");
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
+  if (nbatch > 1) {  // the caller's stream sees the whole alignment
+    DUO_CUDA(h, cudaEventRecord(dt->ev_done, dt->s2));
+    DUO_CUDA(h, cudaStreamWaitEvent(h->stream, dt->ev_done, 0));
+  }
   h->last_kernel = tiled ? "k2_duo_tiled<" + std::to_string(h->rounds) + "," + std::to_string(dt->threads) + "," + std::to_string(dt->threads == 256 ? dt->minb : 1) + ">"
                          : "k2_duo_generic<" + std::to_string(h->rounds) + ">";
   *used = 1;

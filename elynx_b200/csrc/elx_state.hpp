@@ -125,6 +125,7 @@ void duo_free(elx_handle *h);
 int duo_groups(const elx_handle *h);
 int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24);
 int duo_simulate(elx_handle *h, SimArgs &a, int *used);
+int64_t duo_batch_sites(const elx_handle *h);  // sites per batch of a host-buffer call (whole superblocks), 0: no duo tables
 
 // elx_core.cu
 int ensure_pair_tables(elx_handle *h);  // build the pair rows / the node-by-node stage images on first use

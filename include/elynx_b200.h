@@ -171,7 +171,7 @@ int elx_tree_duo_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_
 /* Duo mode (the default for models with 5..22 states -- amino acids -- when only the leaves are requested; ELX_FLAG_SINGLE_DRAWS
  * turns it off): the same summing-out with caps of at most TWO frontier nodes, one draw from the K*K-outcome joint row
  * P(frontier states | state of r) in 512 alias columns, o = state(out[0]) + K * state(out[1]).  A record's rows are 40 KB per
- * component, so every call first buckets its sites by component (stable inside superblocks of 2^22 sites); the rank of a site
+ * component, so every call first buckets its sites by component (stable inside superblocks of 2^20 .. 2^24 sites); the rank of a site
  * among the sites of its component and superblock selects its 16-site Philox group (see elx_duo.cu for the specification).
  * elx_duo_groups: number of records (0: the handle draws node by node); elx_duo_get: the records (ELX_QUAD_REC_INTS layout,
  * frontier positions 0..1) and their alias rows de32 / dlo24 [G][C][K][512] (uint32: [threshold bits 38..24 : 15][alias : 9][0 : 8]

@@ -32,7 +32,7 @@
  *
  * Duo mode (models with 5..22 states, leaves only; elynx_b200/csrc/elx_duo.cu): record g = (out[0..1] | r) draws up to two frontier
  * nodes at once from a K*K-outcome joint row in 512 alias columns, o = state(out[0]) + K * state(out[1]).  Sites are bucketed by
- * component inside superblocks of 2^22 sites: B = s >> 22, rank = number of earlier sites of B with the same component,
+ * component inside superblocks of 2^SB sites (SB = 20 for C <= 16, 22 for C <= 64, else 24): B = s >> SB, rank = number of earlier sites of B with the same component,
  * q = rank >> 4, d = rank & 15; the 16 sites of a group share three Philox calls:
  *   Z[0..47] = little-endian bytes of philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
  *   x24 = Z[3d] | Z[3d+1] << 8 | Z[3d+2] << 16;  j = x24 & 511; t = x24 >> 9; e = de32[g][c][state of r][j] = [q_hi : 15][alias : 9][0 : 8]
@@ -243,7 +243,7 @@ int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int
   return rc;
 }
 
-#define DUO_SB 22
+static int duo_sb(int C) { return C <= 16 ? 20 : C <= 64 ? 22 : 24; }
 static int64_t duo_ties = 0;
 int64_t spec_duo_ties(void) { return duo_ties; } /* ties seen by the last spec_freerun_duo call */
 int spec_freerun_duo(int N, int K, int C, int is_mixture, int rounds, const int32_t *leaf_row, const double *cumw,
@@ -255,6 +255,7 @@ int spec_freerun_duo(int N, int K, int C, int is_mixture, int rounds, const int3
   uint32_t *count = (uint32_t *)calloc((size_t)C, sizeof(uint32_t));
   int rc = 0;
   duo_ties = 0;
+  const int DUO_SB = duo_sb(C);
   const uint64_t first = ((uint64_t)site0 >> DUO_SB) << DUO_SB;
   uint64_t cur_sb = (uint64_t)-1;
   for (uint64_t s = first; s < (uint64_t)(site0 + nsites) && !rc; ++s) {

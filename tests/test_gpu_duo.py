@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 import elynx_b200 as eb  # noqa: E402
 
-SB = 1 << 22  # sites per superblock of the component bucketing
+SB = 1 << 20  # sites per superblock of the component bucketing (models with up to 16 components)
 
 
 def make_sim(model, tree, **kw):
@@ -120,3 +120,18 @@ def test_duo_chi_square_vs_exact_pattern_probabilities():
     e = np.concatenate([exp[big], [exp[~big].sum()]])
     pv = stats.chisquare(o, e).pvalue
     assert pv > 1e-4, pv
+
+
+def test_duo_pipelined_call_equals_superblock_calls():
+    """A call spanning many superblocks is cut into batches whose un-permute passes run on a second stream under the next
+    batch's simulation; it must equal the concatenation of one-superblock calls (which are never pipelined)."""
+    model = model_case("lg_g4")
+    tree = om.parse_newick("((a:0.3,b:0.1):0.2,((c:0.4,d:0.15):0.1,e:0.2):0.05,(f:0.1,g:0.2):0.3);")
+    site0, s = SB - 4097, 7 * SB + 5000
+    with make_sim(model, tree) as sim:
+        whole, cw, _ = sim.simulate(21, s, site0=site0, want_comps=True)
+        cuts = [site0] + [k * SB for k in range(1, 9)] + [site0 + s]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part, cp, _ = sim.simulate(21, b - a, site0=a, want_comps=True)
+            assert np.array_equal(whole[:, a - site0:b - site0], part), (a, b)
+            assert np.array_equal(cw[a - site0:b - site0], cp)
