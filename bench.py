@@ -402,17 +402,21 @@ def run_product(args):
             if world > 1:
                 dist.barrier(group=host_group)
 
-        def e2e_variant(alloc, label):
+        def e2e_variant(alloc, label, packed=False):
             """rank 0 drives all `world` GPUs from inside elx_simulate; the other ranks idle at the barriers"""
             step_ms, d2h = [], 0
+            ppitch = (total_sites + 31) // 32 * (8 if model.n_states <= 4 else 20)
             for it in range(k_e2e + 1):  # first iteration untimed
                 host_barrier()
                 if rank == 0:
                     t1 = time.perf_counter()
-                    host = alloc((T, total_sites))
+                    host = alloc((T, ppitch if packed else total_sites))
                     s2 = make_sim(model, tree, device=0, n_devices=world)
-                    L.check(L.lib().elx_simulate(s2.handle, C.c_uint64(seed), 0, total_sites, C.c_void_p(host.ctypes.data), total_sites, None, None, 0),
-                            s2.handle)
+                    if packed:
+                        L.check(L.lib().elx_simulate_packed(s2.handle, C.c_uint64(seed), 0, total_sites, C.c_void_p(host.ctypes.data), ppitch, None), s2.handle)
+                    else:
+                        L.check(L.lib().elx_simulate(s2.handle, C.c_uint64(seed), 0, total_sites, C.c_void_p(host.ctypes.data), total_sites, None, None, 0),
+                                s2.handle)
                     d2h = s2.d2h_bytes
                     s2.close()
                     dt = (time.perf_counter() - t1) * 1e3
@@ -433,9 +437,19 @@ def run_product(args):
                 pinned_keep.append(torch.empty(shape, dtype=torch.uint8, pin_memory=True))
             return pinned_keep[0].numpy()
 
-        pageable = e2e_variant(lambda shape: np.empty(shape, dtype=np.uint8), "fresh pageable buffer per step (np.empty: untouched pages, first-touch faults inside the timed region)")
+        def alloc_fresh(shape):
+            # what malloc / mallocForeignPtrBytes hand a caller for a buffer this size: a fresh anonymous mapping, untouched pages,
+            # no huge-page advice from the allocator (np.empty would add its own madvise(MADV_HUGEPAGE))
+            import mmap
+            m = mmap.mmap(-1, int(np.prod(shape)), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)  # (Python's default is MAP_SHARED: shmem)
+            return np.frombuffer(m, dtype=np.uint8).reshape(shape)
+
+        pageable = e2e_variant(alloc_fresh, "fresh anonymous mapping per step (untouched pageable memory: first-touch faults inside the timed region)")
         pinned = e2e_variant(alloc_pinned, "page-locked, pre-faulted buffer reused across steps (round 1's measurement)") if not args.no_e2e_pinned else None
         pinned_keep.clear()
+        packed_form = e2e_variant(alloc_fresh,
+                                  "elx_simulate_packed into a fresh anonymous mapping: the caller keeps the %d-bit form (no expansion on the host)"
+                                  % (2 if model.n_states <= 4 else 5), packed=True) if model.n_states <= 32 else None
         if rank == 0:
             h2d = int(model.weights.nbytes + model.pi.nbytes + model.exch.nbytes + tree.parent.nbytes + tree.brlen.nbytes + tree.leaf_row.nbytes) * world
             e2e = {"value": pageable["value_mean"], "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pageable["d2h_bytes_per_step"],
@@ -446,7 +460,9 @@ def run_product(args):
                                  % ((2, 2) if model.n_states <= 4 else (5, 5)) if pageable["d2h_bytes_per_step"] < T * total_sites else "1 byte per cell over PCIe"),
                    "includes": "elx_create (eigensystems, H2D of model+tree, K1 tables; per device) + simulation + D2H + the caller's [T][S] uint8 host "
                                "buffer completely written + elx_destroy; ONE call on ONE handle driving %d device(s)" % world,
-                   "pinned_prefaulted": pinned}
+                   "caller_buffer_advice": "madvise(MADV_HUGEPAGE) on the caller's buffer by the library (first-touch faults of 2 MB; "
+                                           "tools/bench_prefault.py: 10 GB in 0.16 s instead of 0.50 s on this host class)",
+                   "pinned_prefaulted": pinned, "packed_result_form": packed_form}
 
     traffic = None
     try:

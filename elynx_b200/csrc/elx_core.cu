@@ -20,6 +20,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 #include <cuda_runtime.h>
 
 #include "../../include/elynx_b200.h"
@@ -31,6 +35,108 @@
 namespace elx {
 
 static thread_local std::string g_last_error;
+
+// ---- device memory cache (see elx_state.hpp) -----------------------------------------------------------------------
+#undef cudaMalloc
+#undef cudaFree
+namespace {
+struct DevBlock { void *p; size_t bytes; };
+struct DevCache {
+  std::mutex mu;
+  std::vector<DevBlock> free_blocks[16];            // per device
+  size_t cached_bytes[16] = {};
+  std::vector<std::pair<void *, std::pair<int, size_t>>> live;  // ptr -> (device, bytes) of blocks handed out
+};
+DevCache &dev_cache() { static DevCache c; return c; }
+size_t dev_cache_cap() {
+  static const size_t cap = []() { const char *e = getenv("ELX_DEVICE_CACHE_MB"); return (size_t)(e ? std::max(0, atoi(e)) : 8192) << 20; }();
+  return cap;
+}
+}  // namespace
+
+cudaError_t dev_malloc(void **p, size_t bytes) {
+  if (!p) return cudaErrorInvalidValue;
+  *p = nullptr;
+  if (bytes == 0) bytes = 1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  DevCache &c = dev_cache();
+  if (dev >= 0 && dev < 16 && dev_cache_cap() > 0) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto &fl = c.free_blocks[dev];
+    size_t best = fl.size();
+    for (size_t i = 0; i < fl.size(); ++i)  // the tightest block that fits without wasting more than a quarter
+      if (fl[i].bytes >= bytes && fl[i].bytes <= bytes + bytes / 4 + 4096 && (best == fl.size() || fl[i].bytes < fl[best].bytes)) best = i;
+    if (best != fl.size()) {
+      *p = fl[best].p;
+      c.live.push_back({*p, {dev, fl[best].bytes}});
+      c.cached_bytes[dev] -= fl[best].bytes;
+      fl.erase(fl.begin() + (long)best);
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cache back and try again
+    cudaGetLastError();
+    dev_cache_trim();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess && dev >= 0 && dev < 16) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live.push_back({*p, {dev, bytes}});
+  }
+  return e;
+}
+
+cudaError_t dev_free(void *p) {
+  if (!p) return cudaSuccess;
+  DevCache &c = dev_cache();
+  int dev = -1;
+  size_t bytes = 0;
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (size_t i = 0; i < c.live.size(); ++i)
+      if (c.live[i].first == p) { dev = c.live[i].second.first; bytes = c.live[i].second.second; c.live.erase(c.live.begin() + (long)i); break; }
+  }
+  if (dev < 0) return cudaFree(p);  // not one of ours
+  int cur = dev;
+  cudaGetDevice(&cur);
+  if (cur != dev) cudaSetDevice(dev);
+  cudaDeviceSynchronize();  // what cudaFree does implicitly: nothing in flight uses the block when it is handed out again
+  bool keep = false;
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.cached_bytes[dev] + bytes <= dev_cache_cap()) {
+      c.free_blocks[dev].push_back({p, bytes});
+      c.cached_bytes[dev] += bytes;
+      keep = true;
+    }
+  }
+  cudaError_t e = keep ? cudaSuccess : cudaFree(p);
+  if (cur != dev) cudaSetDevice(cur);
+  return e;
+}
+
+void dev_cache_trim() {
+  DevCache &c = dev_cache();
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 16; ++d) {
+    std::vector<DevBlock> blocks;
+    {
+      std::lock_guard<std::mutex> lk(c.mu);
+      blocks.swap(c.free_blocks[d]);
+      c.cached_bytes[d] = 0;
+    }
+    if (blocks.empty()) continue;
+    cudaSetDevice(d);
+    for (const DevBlock &b : blocks) cudaFree(b.p);
+  }
+  cudaSetDevice(cur);
+}
+#define cudaMalloc(p, n) elx::dev_malloc((void **)(p), (n))
+#define cudaFree(p) elx::dev_free((void *)(p))
 
 int fail(elx_handle *h, int code, const std::string &msg) {
   if (h) h->last_error = msg;
@@ -668,6 +774,8 @@ extern "C" {
 
 int elx_version(void) { return 100; }
 
+void elx_trim_device_cache(void) { dev_cache_trim(); }
+
 const char *elx_last_error(const elx_handle *h) { return h ? h->last_error.c_str() : g_last_error.c_str(); }
 
 // One handle on ONE device: eigensystems, H2D of model + tree, K1, walk programs.  device_override >= 0 replaces
@@ -1198,6 +1306,7 @@ struct PackedChunk {
   uint8_t *dst = nullptr;        // caller's buffer + first site of the batch; row r of the chunk starts at dst + row_off[r]
   const int64_t *row_off = nullptr;
   const uint8_t *lut = nullptr;
+  int raw = 0;                   // 1: the caller takes the packed form itself (dst is a packed matrix: bytes are copied)
   int bits = 2;
   int64_t rows = 0, ppitch = 0, nb = 0, ncol = 0, units = 0;
   std::atomic<int> issued{0};  // its copy and event are enqueued
@@ -1246,7 +1355,7 @@ static bool want_packed_transport(const elx_handle *h, int64_t cells) {
 // alphabet (FASTA sequence lines; 4 characters for the 2-bit form, 32 for the 5-bit form).
 static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves,
                                 const int64_t *leaves_off, int32_t *comps, uint8_t *internal, const int64_t *internal_off,
-                                const uint8_t *lut) {
+                                const uint8_t *lut, bool raw = false) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int bits = h->K <= 4 ? 2 : 5;  // a packing group is 32 sites: 8 or 20 bytes
   auto packed_pitch = [bits](int64_t n) { return (n + 31) / 32 * (bits == 2 ? 8 : 20); };
@@ -1254,7 +1363,8 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   // (a batch that starts inside one has to draw the components of the sites in front of it again), the first one shorter
   // when site0 is not aligned.
   const int64_t BATCH = duo_batch_sites(h) > 0 ? duo_batch_sites(h) : (int64_t)1 << 20;
-  const int64_t boff = duo_batch_sites(h) > 0 ? site0 % BATCH : 0;
+  int64_t boff = duo_batch_sites(h) > 0 ? site0 % BATCH : 0;
+  if (raw && (boff & 31)) boff = 0;  // packed rows of the batches must join on byte boundaries (32-site packing groups)
   const int NB = 2;
   const int64_t nbatch = (nsites + boff + BATCH - 1) / BATCH;
   const int64_t bmax = nsites < BATCH ? nsites : BATCH;
@@ -1385,7 +1495,11 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
           if (u >= ch.units) break;
           const int64_t r = u / ch.ncol, k = u - r * ch.ncol;
           const int64_t c0 = k * UNPACK_COLS, c1 = std::min(ch.nb, c0 + UNPACK_COLS);
-          if (ch.bits == 2) elx::unpack2_rows(ch.src + r * ch.ppitch + c0 / 4, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut);
+          if (ch.raw) {
+            const int64_t p0 = ch.bits == 2 ? c0 / 4 : c0 / 8 * 5;
+            const int64_t p1 = c1 == ch.nb ? (ch.nb + 31) / 32 * (ch.bits == 2 ? 8 : 20) : (ch.bits == 2 ? c1 / 4 : c1 / 8 * 5);
+            memcpy(ch.dst + ch.row_off[r] + p0, ch.src + r * ch.ppitch + p0, (size_t)(p1 - p0));
+          } else if (ch.bits == 2) elx::unpack2_rows(ch.src + r * ch.ppitch + c0 / 4, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut);
           else elx::unpack5_rows(ch.src + r * ch.ppitch + c0 / 8 * 5, ch.ppitch, ch.dst + ch.row_off[r] + c0, 0, 0, 1, c1 - c0, ch.lut);
           if (ch.done.fetch_add(1, std::memory_order_acq_rel) + 1 == ch.units) {  // the stage can be refilled
             { std::lock_guard<std::mutex> lk(sync.mu); }
@@ -1448,7 +1562,8 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
       CT(cudaMemcpyAsync(stage, (pl.which ? d_pi[i] : d_pl[i]) + pl.r0 * pp, bytes, cudaMemcpyDeviceToHost, copy_stream));
       h->d2h_bytes += (int64_t)bytes;
       ch.src = stage;
-      ch.dst = (pl.which ? internal : leaves) + b0;
+      ch.raw = raw ? 1 : 0;
+      ch.dst = (pl.which ? internal : leaves) + (raw ? (bits == 2 ? b0 / 4 : b0 / 8 * 5) : b0);
       ch.row_off = (pl.which ? internal_off : leaves_off) + pl.r0;
       ch.lut = lut;
       ch.bits = bits;
@@ -1593,8 +1708,54 @@ static int run_sharded(elx_handle *h, int64_t nsites, const std::function<int(el
   return 0;
 }
 
+// A caller's result buffer is usually fresh memory (mallocForeignPtrBytes, np.empty): its pages are faulted in by the
+// threads that write the result, 4 KB at a time -- 0.5 s for 10 GB on a 16-core B200 host, three times the transport itself.
+// With transparent huge pages in `madvise` mode the same first touch takes 0.16 s (tools/bench_prefault.py), so big
+// result buffers are advised accordingly (a hint about FUTURE faults of the caller's pages, nothing is touched or moved;
+// ELX_NO_MADVISE=1 turns it off).
+static void advise_result_buffer(const void *p, int64_t bytes) {
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+  static const bool off = getenv("ELX_NO_MADVISE") != nullptr;
+  if (off || !p || bytes < ((int64_t)64 << 20)) return;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 0x1fffff) & ~(uintptr_t)0x1fffff;
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + (uintptr_t)bytes) & ~(uintptr_t)0x1fffff;
+  if (e > a) madvise(reinterpret_cast<void *>(a), e - a, MADV_HUGEPAGE);
+#else
+  (void)p; (void)bytes;
+#endif
+}
+
+int32_t elx_packed_bits(const elx_handle *h) { return !h ? 0 : h->K <= 4 ? 2 : h->K <= 32 ? 5 : 8; }
+
+int64_t elx_packed_pitch(const elx_handle *h, int64_t nsites) {
+  if (!h || nsites < 0) return -1;
+  return h->K <= 4 ? (nsites + 31) / 32 * 8 : h->K <= 32 ? (nsites + 31) / 32 * 20 : nsites;
+}
+
+int elx_simulate_packed(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *packed, int64_t packed_pitch,
+                        int32_t *comps) {
+  if (!h) return fail(nullptr, ELX_E_INVALID, "null handle");
+  if (nsites < 0 || site0 < 0) return fail(h, ELX_E_INVALID, "simulate_packed: negative site range");
+  if (h->K > 32) return fail(h, ELX_E_UNSUPPORTED, "simulate_packed: more than 32 states have no packed form (use elx_simulate)");
+  if (!packed && nsites > 0) return fail(h, ELX_E_INVALID, "simulate_packed: result buffer is NULL");
+  if (packed_pitch < elx_packed_pitch(h, nsites)) return fail(h, ELX_E_INVALID, "simulate_packed: packed_pitch < elx_packed_pitch(nsites)");
+  if (nsites == 0) return 0;
+  advise_result_buffer(packed, (int64_t)h->T * packed_pitch);
+  std::vector<int64_t> lo((size_t)h->T);
+  for (int t = 0; t < h->T; ++t) lo[(size_t)t] = t * packed_pitch;
+  const int bits = h->K <= 4 ? 2 : 5;
+  if (!h->peers.empty() && nsites >= 4096)  // shard boundaries are multiples of 64 sites: whole packing groups
+    return run_sharded(h, nsites, [&](elx_handle *hd, int64_t f, int64_t n) {
+      return simulate_host_packed(hd, seed, site0 + f, n, packed + (bits == 2 ? f / 4 : f / 8 * 5), lo.data(), comps ? comps + f : nullptr,
+                                  nullptr, nullptr, nullptr, true);
+    });
+  return simulate_host_packed(h, seed, site0, nsites, packed, lo.data(), comps, nullptr, nullptr, nullptr, true);
+}
+
 int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch,
                  int32_t *comps, uint8_t *internal, int64_t internal_pitch) {
+  if (h && leaves && nsites > 0) advise_result_buffer(leaves, (int64_t)h->T * leaves_pitch);
+  if (h && internal && nsites > 0) advise_result_buffer(internal, (int64_t)h->N * internal_pitch);
   if (h && !h->peers.empty() && nsites >= 4096) {
     int rc = check_sim_args(h, site0, nsites, leaves, leaves_pitch, internal, internal_pitch);
     if (rc) return rc;
@@ -1731,6 +1892,7 @@ int elx_simulate_fasta(elx_handle *h, uint64_t seed, int64_t total_sites, const 
   if (!h || !out || !alphabet) return fail(h, ELX_E_INVALID, "simulate_fasta: NULL argument");
   int64_t need = elx_fasta_size(h, names, total_sites);
   if (need < 0 || out_capacity < need) return fail(h, ELX_E_INVALID, "simulate_fasta: output buffer too small");
+  advise_result_buffer(out, need);
   {
     // sequence lines cross PCIe at 2 / 5 bits per character and are expanded to characters by host threads, the
     // `>name` lines are written here (same bytes as K3 writes on the device)

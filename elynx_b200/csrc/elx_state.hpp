@@ -45,6 +45,15 @@ struct elx_handle {
 
 namespace elx {
 
+// Device memory of the library goes through a small per-device cache (elx_core.cu): cudaMalloc / cudaFree of the gigabyte-size
+// staging buffers and tables cost tens of milliseconds per host-buffer call (measured: 40-60 ms of a 105 ms elx_simulate_packed
+// call), and handles are typically created, used and destroyed in a loop.  dev_free keeps cudaFree's implicit device
+// synchronisation (a block is never handed out again while work that uses it may be in flight); blocks beyond the cap
+// (ELX_DEVICE_CACHE_MB, default 8192 per device; 0 = off) go back to the driver, and everything does when an allocation fails.
+cudaError_t dev_malloc(void **p, size_t bytes);
+cudaError_t dev_free(void *p);
+void dev_cache_trim();  // return every cached block of every device to the driver
+
 // Device form of a PairRec (16 bytes, streamed through shared memory next to the group's alias rows).
 struct PairRecDev {
   int32_t nodeA;
@@ -133,3 +142,7 @@ int ensure_fast_tables(elx_handle *h);
 void launch_k1_alias(elx_handle *h, int64_t rows, int K, int A, const double *P, uint16_t *e16, uint32_t *qlo);
 
 }  // namespace elx
+
+// every cudaMalloc / cudaFree of the library's translation units is the cached form
+#define cudaMalloc(p, n) elx::dev_malloc((void **)(p), (n))
+#define cudaFree(p) elx::dev_free((void *)(p))

@@ -182,6 +182,15 @@ class Simulator:
                                      _ptr(comps), _ptr(internal), max(nsites, 1)), self._h)
         return leaves, comps, internal
 
+    def simulate_packed(self, seed: int, nsites: int, site0: int = 0, want_comps: bool = False):
+        """The alignment in the packed form it crosses PCIe in: (packed [T][elx_packed_pitch] uint8, bits per site, comps)."""
+        lib = L.lib()
+        pitch = int(lib.elx_packed_pitch(self._h, nsites))
+        packed = np.empty((self.n_leaves, max(pitch, 1)), dtype=np.uint8)
+        comps = np.empty(nsites, dtype=np.int32) if want_comps else None
+        L.check(lib.elx_simulate_packed(self._h, C.c_uint64(seed & (2 ** 64 - 1)), site0, nsites, _ptr(packed), max(pitch, 1), _ptr(comps)), self._h)
+        return packed, int(lib.elx_packed_bits(self._h)), comps
+
     def site_components(self, seed: int, nsites: int, site0: int = 0) -> np.ndarray:
         """Component index of every site (the `cs` of simulateAndFlattenMixtureModelPar) without simulating the alignment."""
         comps = np.empty(nsites, dtype=np.int32)

@@ -96,6 +96,9 @@ typedef struct {
                                     than 32 states always take it */
 
 int elx_version(void);
+/* The library keeps freed device buffers (tables, staging) in a per-device cache for the next handle / call (up to
+ * ELX_DEVICE_CACHE_MB, default 8192; 0 = off); this returns them to the driver. */
+void elx_trim_device_cache(void);
 const char *elx_last_error(const elx_handle *h);
 
 /* Builds the per-component eigensystems on the host, uploads the tree, and runs kernel K1
@@ -192,6 +195,16 @@ int elx_simulate(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, ui
                  int32_t *comps, uint8_t *internal, int64_t internal_pitch);
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves,
                         int64_t leaves_pitch, int32_t *d_comps, uint8_t *d_internal, int64_t internal_pitch);
+
+/* The same alignment in the form it crosses PCIe in, for callers that keep alignments packed (statistics, compressors, a
+ * .fasta.gz writer): leaves-only, no expansion on the host, so the call runs at PCIe speed instead of the host's store
+ * bandwidth.  elx_packed_bits: 2 (K <= 4: site 4i+k of a row in bits 2k..2k+1 of byte i) or 5 (K <= 32: site i in bits
+ * 5i..5i+4 of the row's little-endian bit stream, 8 sites = 5 bytes); rows are padded to whole 32-site groups:
+ * elx_packed_pitch(nsites) bytes.  elx_unpack2_rows / elx_unpack5_rows (below) expand such rows.  K > 32: ELX_E_UNSUPPORTED. */
+int32_t elx_packed_bits(const elx_handle *h);
+int64_t elx_packed_pitch(const elx_handle *h, int64_t nsites);
+int elx_simulate_packed(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *packed, int64_t packed_pitch,
+                        int32_t *comps);
 
 /* The component index of every site of [site0, site0 + nsites) alone -- the `cs` of simulateAndFlattenMixtureModelPar (:257)
  * without the alignment (writeSiteDists of a sharded run, slynx Simulate.hs:79-89).  Same values as `comps` above. */

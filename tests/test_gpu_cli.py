@@ -86,3 +86,28 @@ def test_cli_fasta_gz_and_site_components(tmp_path, ref_data):
     with eb.Simulator(ws, ds, es, t, is_mixture=True) as sim:
         _, comps, _ = sim.simulate(1, 3000, site0=1234567, want_comps=True)
         assert np.array_equal(sim.site_components(1, 3000, site0=1234567), comps)
+
+
+@pytest.mark.parametrize("name,site0,s", [("hky_g4", 0, (1 << 21) + 333), ("hky_g4", 96, 5000), ("lg_g4", 64, (1 << 20) + 4097), ("c10", 5, 3001)])
+def test_simulate_packed_is_the_alignment(name, site0, s):
+    """elx_simulate_packed: the 2- / 5-bit rows expand (elx_unpack2_rows / elx_unpack5_rows) to exactly what elx_simulate returns,
+    several batches, ragged ends, unaligned site0; d2h bytes are the packed size."""
+    import ctypes as C
+
+    from elynx_b200 import _lib as L
+
+    model = model_case(name)
+    is_mix, ws, ds, es, _ = model
+    tree = tree_from_file("UltraMetric.tree")
+    with eb.Simulator(ws if is_mix else None, ds, es, tree, is_mixture=is_mix) as sim:
+        ref, c0, _ = sim.simulate(4, s, site0=site0, want_comps=True)
+        b0 = sim.d2h_bytes
+        packed, bits, c1 = sim.simulate_packed(4, s, site0=site0, want_comps=True)
+        moved = sim.d2h_bytes - b0
+    assert bits == (2 if ds.shape[1] <= 4 else 5)
+    assert packed.shape == (tree.n_leaves, (s + 31) // 32 * (8 if bits == 2 else 20))
+    out = np.empty((tree.n_leaves, s), dtype=np.uint8)
+    fn = L.lib().elx_unpack2_rows if bits == 2 else L.lib().elx_unpack5_rows
+    L.check(fn(C.c_void_p(packed.ctypes.data), packed.shape[1], C.c_void_p(out.ctypes.data), s, tree.n_leaves, s, None, 2))
+    assert np.array_equal(out, ref) and np.array_equal(c0, c1)
+    assert moved <= packed.size + 4 * s + (1 << 12)

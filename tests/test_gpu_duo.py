@@ -122,9 +122,7 @@ def test_duo_chi_square_vs_exact_pattern_probabilities():
     assert pv > 1e-4, pv
 
 
-def test_duo_pipelined_call_equals_superblock_calls():
-    """A call spanning many superblocks is cut into batches whose un-permute passes run on a second stream under the next
-    batch's simulation; it must equal the concatenation of one-superblock calls (which are never pipelined)."""
+def _multi_superblock_check():
     model = model_case("lg_g4")
     tree = om.parse_newick("((a:0.3,b:0.1):0.2,((c:0.4,d:0.15):0.1,e:0.2):0.05,(f:0.1,g:0.2):0.3);")
     site0, s = SB - 4097, 7 * SB + 5000
@@ -135,3 +133,21 @@ def test_duo_pipelined_call_equals_superblock_calls():
             part, cp, _ = sim.simulate(21, b - a, site0=a, want_comps=True)
             assert np.array_equal(whole[:, a - site0:b - site0], part), (a, b)
             assert np.array_equal(cw[a - site0:b - site0], cp)
+
+
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_duo_many_superblocks_call_equals_superblock_calls(pipeline):
+    """A call spanning many superblocks must equal the concatenation of one-superblock calls -- also with ELX_DUO_PIPELINE=1,
+    where it is cut into batches whose un-permute passes run on a second stream under the next batch's simulation (the
+    switch is read once per process: that run happens in a child process)."""
+    if not pipeline:
+        return _multi_superblock_check()
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, ELX_DUO_PIPELINE="1", PYTHONPATH=os.pathsep.join([os.path.dirname(here), here, os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", "import test_gpu_duo as t; t._multi_superblock_check(); print('pipeline ok')"],
+                       env=env, cwd=here, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "pipeline ok" in r.stdout, r.stdout + r.stderr
