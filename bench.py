@@ -348,9 +348,18 @@ def run_product(args):
         achieved = T * sites / (kms * 1e-3) / 1e9
         res = dict(desc=desc, tree=tree, model=model, sites=sites, T=T, value=world * T * sites / (ms_per_step * 1e-3), ms_per_step=ms_per_step,
                    kernel_ms=kms, achieved=achieved, frac=achieved / peak, kernel=sim.last_kernel, launches=int(launches),
-                   wall_ms=wall / steps * 1e3, clocks=clocks, quad_groups=sim.quad_groups, pair_groups=sim.pair_groups)
+                   wall_ms=wall / steps * 1e3, clocks=clocks, quad_groups=sim.quad_groups, pair_groups=sim.pair_groups, duo_groups=sim.duo_groups)
         sim.close()
         return res
+
+    def draws_text(r):
+        if r["quad_groups"]:
+            return "one draw per cap of <= 4 frontier nodes (inner nodes summed out), %d draws per site" % r["quad_groups"]
+        if r["duo_groups"]:
+            return ("duo mode: one draw per cap of <= 2 frontier nodes (inner nodes summed out), %d draws per site, on component-bucketed "
+                    "sites; a step = bucketing passes + %s + the un-permute pass back to site order, all inside the timed region"
+                    % (r["duo_groups"], r["kernel"].split("<")[0]))
+        return "joint sibling pairs" if r["pair_groups"] else "node by node"
 
     head = measure(args.config, args.steps, args.warmup, 0.6)
     desc, tree, model, sites, T = head["desc"], head["tree"], head["model"], head["sites"], head["T"]
@@ -363,7 +372,7 @@ def run_product(args):
             r = measure(name, 3, 3, 0.3)
             configs[name] = {"workload": r["desc"], "taxa": r["T"], "sites_per_gpu": r["sites"], "components": r["model"].n_components,
                              "states": r["model"].n_states, "value": r["value"], "unit": "cells/s", "ms_per_step": r["ms_per_step"],
-                             "kernel": r["kernel"], "gpu_launches_per_step": r["launches"] / 3,
+                             "kernel": r["kernel"], "gpu_launches_per_step": r["launches"] / 3, "draws": draws_text(r),
                              "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
                                           "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["T"] * r["sites"]},
                              "clocks": r["clocks"]}
@@ -486,8 +495,7 @@ def run_product(args):
         "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": cfg,
         "kernel_info": {"kernel": head["kernel"], "path": "generic" if args.force_generic else "auto",
-                        "draws": ("one draw per cap of <= 4 frontier nodes (inner nodes summed out), %d draws per site" % head["quad_groups"]) if head["quad_groups"]
-                        else ("joint sibling pairs" if head["pair_groups"] else "node by node"), "philox_rounds": args.philox_rounds or 10},
+                        "draws": draws_text(head), "philox_rounds": args.philox_rounds or 10},
         "roofline": {"bound": "hbm", "achieved": head["achieved"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": T * sites, "kernel_ms": head["kernel_ms"], "kernel": head["kernel"],
                      "note": "1 byte per alignment cell (uint8 leaf state written once); CUDA events on the handle's stream; "

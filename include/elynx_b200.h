@@ -183,9 +183,15 @@ int32_t elx_duo_groups(const elx_handle *h);
 int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24);
 
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
- * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed); the result is a
+ * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed, draw mode); the result is a
  * pure function of (seed, global site index, node), so any partition of the site range over calls,
  * GPUs or processes yields the same alignment.
+ * Draw mode: leaves-only calls (internal == NULL) sum internal nodes out where they can -- quad mode for K <= 4, duo mode
+ * for 5 <= K <= 22 -- while calls that keep the internal states draw every node (pair mode for K <= 4, node by node
+ * otherwise): a different, equally exact stream, so the SAME handle and seed give different (identically distributed)
+ * leaf rows with and without `internal`.  (In the reference `simulate` and `simulateAndFlatten` consume the generator
+ * alike.)  A handle created with ELX_FLAG_PAIR_DRAWS (K <= 4) or ELX_FLAG_SINGLE_DRAWS (any K) uses ONE stream for both
+ * call shapes: leaves(internal != NULL) == leaves(internal == NULL).
  *   leaves   [T][leaves_pitch]   uint8, row = leaf_row, column = site - site0       (required)
  *   comps    [nsites]            int32 component index per site, or NULL             (:257, `cs`)
  *   internal [N][internal_pitch] uint8 states of every node in preorder, or NULL     (`simulate`, :130-155)

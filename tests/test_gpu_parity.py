@@ -207,6 +207,23 @@ def test_freerun_matches_spec(name, tree_file, s, force_generic, draws):
                 assert np.array_equal(l1, l0)
 
 
+@pytest.mark.parametrize("name,kw", [("hky_g4", {"pair_draws": True}), ("hky_g4", {"single_draws": True}), ("lg_g4", {"single_draws": True})])
+def test_one_stream_for_both_call_shapes(name, kw):
+    """include/elynx_b200.h: a handle created with ELX_FLAG_PAIR_DRAWS / ELX_FLAG_SINGLE_DRAWS draws the same stream whether or
+    not the internal states are kept (the default handle sums nodes out in leaves-only calls: a different stream)."""
+    model = model_case(name)
+    tree = tree_from_file("Newick.tree")
+    with make_sim(model, tree, **kw) as sim:
+        a, ca, internal = sim.simulate(17, 3000, site0=123, want_comps=True, keep_internal=True)
+        b, cb, _ = sim.simulate(17, 3000, site0=123, want_comps=True)
+        assert np.array_equal(a, b) and np.array_equal(ca, cb)
+        assert np.array_equal(internal[tree.leaf_row >= 0][np.argsort(tree.leaf_row[tree.leaf_row >= 0])], a)
+    with make_sim(model, tree) as sim:
+        a, _, _ = sim.simulate(17, 3000, site0=123, keep_internal=True)
+        b, _, _ = sim.simulate(17, 3000, site0=123)
+        assert not np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("shape", ["multifurcating", "caterpillar", "unary", "single", "cherry"])
 def test_pair_walk_odd_trees(shape):
     """Pair mode on trees that are not binary: groups of one, several groups per node, a node that is root and leaf."""
