@@ -18,7 +18,7 @@
 //   B = s >> SB;  rank = #{s' in [B << SB, s) : c(s') = c};  q = rank >> 4;  d = rank & 15
 //   record g = (out[0..1] | r), state i of r:  48 bytes Z[0..47] = little-endian words of
 //     philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
-//     x24 = Z[3d] | Z[3d+1] << 8 | Z[3d+2] << 16 = [t : 15][j : 9]
+//     x24 = draw d of the 12 words as in quad mode (elx_ptx.cuh ELX_DRAW24) = [t : 15][j : 9]
 //     e = de32[g][c][i][j] = [q_hi : 15][alias : 9][0 : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
 //     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 8) < dlo24[g][c][i][j] ? j : alias
 //     state(out[0]) = o mod K,  state(out[1]) = o div K
@@ -698,19 +698,14 @@ __global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *
 // ---------------------------------------------------------------------------------------------
 template <int ROUNDS>
 __device__ __forceinline__ uint32_t duo_draw24(uint32_t q, uint32_t comp, uint32_t sb_lo, uint32_t sb_hi, int d, uint32_t node0, uint2 key) {
-  const int byte0 = 3 * d, call = byte0 >> 4, call2 = (byte0 + 2) >> 4;
+  const int w0 = 3 * (d >> 2), wa = (d & 3) < 3 ? w0 + (d & 3) : w0, wb = (d & 3) < 3 ? wa : w0 + 2;
   const uint32_t cx = q | (comp << 20);
-  const uint4 x = philox4x32<ROUNDS>(make_uint4(cx, sb_lo, node0, (sb_hi << 8) | (4u * (uint32_t)call)), key);
-  uint4 y = x;
-  if (call2 != call) y = philox4x32<ROUNDS>(make_uint4(cx, sb_lo, node0, (sb_hi << 8) | (4u * (uint32_t)call2)), key);
-  const uint32_t wx[4] = {x.x, x.y, x.z, x.w}, wy[4] = {y.x, y.y, y.z, y.w};
-  uint32_t v = 0;
-  for (int bb = 0; bb < 3; ++bb) {
-    const int pos = byte0 + bb;
-    const uint32_t word = (pos >> 4) == call ? wx[(pos >> 2) & 3] : wy[(pos >> 2) & 3];
-    v |= ((word >> (8 * (pos & 3))) & 0xffu) << (8 * bb);
+  uint32_t X[12];
+  for (int call = wa >> 2; call <= wb >> 2; ++call) {  // the one or two Philox calls that hold the draw's words
+    const uint4 x = philox4x32<ROUNDS>(make_uint4(cx, sb_lo, node0, (sb_hi << 8) | (4u * (uint32_t)call)), key);
+    X[4 * call] = x.x; X[4 * call + 1] = x.y; X[4 * call + 2] = x.z; X[4 * call + 3] = x.w;
   }
-  return v;
+  return draw24_from_words(X, d);
 }
 
 template <int ROUNDS>
@@ -779,13 +774,6 @@ __device__ __forceinline__ uint32_t duo_mad(uint32_t a, uint32_t b, uint32_t c) 
   return d;
 }
 
-// draw d of the 48 random bytes X[0..11], in the upper three bytes of the result (the low byte is don't-care)
-#define ELX_DUO_DRAW(d)                                                                                      \
-  ((((3 * (d)) & 3) == 0)   ? duo_prmt<0x2100u>(X[(3 * (d)) >> 2], 0u)                                        \
-   : (((3 * (d)) & 3) == 1) ? X[(3 * (d)) >> 2]                                                               \
-   : (((3 * (d)) & 3) == 2) ? duo_prmt<0x4320u>(X[(3 * (d)) >> 2], X[((3 * (d)) >> 2) < 11 ? ((3 * (d)) >> 2) + 1 : 11]) \
-                            : duo_prmt<0x5430u>(X[(3 * (d)) >> 2], X[((3 * (d)) >> 2) < 11 ? ((3 * (d)) >> 2) + 1 : 11]))
-
 template <int ROUNDS, bool FAST>
 __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &tile, const uint32_t full_bar0, const uint32_t empty_bar0,
                                             const uint32_t stage_smem, const uint32_t slot_base, uint8_t *tmp_base, const bool active,
@@ -823,7 +811,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int d = 4 * qq + i;
-        const uint32_t w = ELX_DUO_DRAW(d);  // [t : 15][j : 9][x : 8]
+        const uint32_t w = ELX_DRAW24(X, d);  // [t : 15][j : 9][x : 8]
         // row offset = state x 2048: the slot byte (state x 8) moved to bits 8..15
         const uint32_t ro = i == 0 ? duo_prmt<0x4404u>(Rq[qq], 0u) : i == 1 ? duo_prmt<0x4414u>(Rq[qq], 0u)
                           : i == 2 ? duo_prmt<0x4424u>(Rq[qq], 0u) : duo_prmt<0x4434u>(Rq[qq], 0u);
@@ -847,7 +835,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
       // bits.  Unrolled with static register names: no calls, no dynamically indexed arrays (elx_fast.cu).
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
-        const uint32_t w = ELX_DUO_DRAW(d);
+        const uint32_t w = ELX_DRAW24(X, d);
         const uint32_t row8 = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
         const uint32_t j = (w >> 8) & 0x1ffu;
         const uint32_t e = duo_lds_u32(tbl + row8 * 256u + j * 4u);

@@ -64,6 +64,27 @@ __device__ __forceinline__ void stg_cs_v4(void *p, uint4 v) {
 }
 
 
+// prmt.b32 in its default mode: selector nibble n picks byte (n & 7) of {a, b}; bit 3 of the nibble replicates that byte's
+// sign bit over the whole byte instead (__byte_perm masks the selector with 0x7777 and loses this)
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt_sel(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+  return d;
+}
+// Draw d (0..15) of the 12 random words X[0..11] of a 16-site group (quad and duo mode), in the UPPER three bytes of the result
+// (the low byte is don't-care): draws 4k, 4k+1, 4k+2 are the words X[3k], X[3k+1], X[3k+2] as they are, draw 4k+3 collects the
+// low bytes those three leave over -- two byte permutes per four draws (contiguous 24-bit fields cost three).
+#define ELX_DRAW24(X, d)                                                                                                     \
+  ((((d) & 3) < 3) ? X[3 * ((d) >> 2) + (((d) & 3) < 3 ? ((d) & 3) : 0)]                                                     \
+                   : elx::prmt_sel<0x4210u>(elx::prmt_sel<0x0400u>(X[3 * ((d) >> 2)], X[3 * ((d) >> 2) + 1]), X[3 * ((d) >> 2) + 2]))
+// the same for one site of a group from scratch (generic kernels): word index and Philox call of draw d
+__host__ __device__ __forceinline__ uint32_t draw24_from_words(const uint32_t *X, int d) {
+  const int w0 = 3 * (d >> 2), i = d & 3;
+  if (i < 3) return X[w0 + i] >> 8;
+  return (X[w0] & 0xffu) | ((X[w0 + 1] & 0xffu) << 8) | ((X[w0 + 2] & 0xffu) << 16);
+}
+
 __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, double u) {
   double p = __dmul_rn(cv[K - 1], u);
   for (int i = 0; i < K; ++i)

@@ -11,8 +11,8 @@
 //
 // Draw specification (oracle/freerun_spec.c spec_freerun_quad executes it on the CPU; kernels must agree bit for bit):
 //   record g = (out[0..3] | r), site s, component c, state i of r.  A draw is 24 bits: the 16 sites of a group s >> 4 share
-//   three Philox calls, 48 bytes B[0..47] = little-endian words of philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2:
-//     x24 = B[3d] | B[3d+1] << 8 | B[3d+2] << 16,  d = s & 15;   x24 = [t : 16][j : 8]
+//   three Philox calls, 12 words X[0..11] = philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2;  d = s & 15:
+//     x24 = X[3(d>>2) + (d&3)] >> 8 for d&3 < 3, else the low bytes of X[3(d>>2)], X[3(d>>2)+1], X[3(d>>2)+2];  x24 = [t : 16][j : 8]
 //     e = qe32[g][c][i][j] = [q_hi : 16][alias : 8][0 : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
 //     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 8) < qlo24[g][c][i][j] ? j : alias
 //     state(out[k]) = (o >> 2k) & 3
@@ -180,18 +180,13 @@ __global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, ui
 template <int ROUNDS>
 __device__ __forceinline__ uint32_t quad_draw24(uint64_t s, uint32_t node0, uint2 key) {
   const uint64_t grp = s >> 4;
-  const int d = (int)(s & 15), byte0 = 3 * d, call = byte0 >> 4, call2 = (byte0 + 2) >> 4;
-  const uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), node0, 4u * (uint32_t)call), key);
-  uint4 y = x;
-  if (call2 != call) y = philox4x32<ROUNDS>(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), node0, 4u * (uint32_t)call2), key);
-  const uint32_t wx[4] = {x.x, x.y, x.z, x.w}, wy[4] = {y.x, y.y, y.z, y.w};
-  uint32_t v = 0;
-  for (int b = 0; b < 3; ++b) {
-    const int pos = byte0 + b;
-    const uint32_t word = (pos >> 4) == call ? wx[(pos >> 2) & 3] : wy[(pos >> 2) & 3];
-    v |= ((word >> (8 * (pos & 3))) & 0xffu) << (8 * b);
+  const int d = (int)(s & 15), w0 = 3 * (d >> 2), wa = (d & 3) < 3 ? w0 + (d & 3) : w0, wb = (d & 3) < 3 ? wa : w0 + 2;
+  uint32_t X[12];
+  for (int call = wa >> 2; call <= wb >> 2; ++call) {  // the one or two Philox calls that hold the draw's words
+    const uint4 x = philox4x32<ROUNDS>(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), node0, 4u * (uint32_t)call), key);
+    X[4 * call] = x.x; X[4 * call + 1] = x.y; X[4 * call + 2] = x.z; X[4 * call + 3] = x.w;
   }
-  return v;
+  return draw24_from_words(X, d);
 }
 
 template <int ROUNDS>
@@ -318,12 +313,9 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
       uint32_t c[4], t[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int d = 4 * q + i, wa = (3 * d) >> 2, off = (3 * d) & 3;
+        const int d = 4 * q + i;
         // draw d in the upper three bytes (the low byte is don't-care): [t : 16][j : 8][x : 8]
-        const uint32_t w = off == 0 ? prmt<0x2100u>(X[wa], 0u)
-                         : off == 1 ? X[wa]
-                         : off == 2 ? prmt<0x4320u>(X[wa], X[wa < 11 ? wa + 1 : wa])
-                                    : prmt<0x5430u>(X[wa], X[wa < 11 ? wa + 1 : wa]);
+        const uint32_t w = ELX_DRAW24(X, d);
         // entry index = row << 8 | j in ONE byte permute: byte 0 = j (byte 1 of the draw), byte 1 = row byte of site d,
         // bytes 2,3 = that byte's sign replicated = 0 (rows are < 128)
         const uint32_t idx = i == 0 ? prmt<0xcc41u>(w, Rq[q]) : i == 1 ? prmt<0xdd51u>(w, Rq[q])
@@ -343,11 +335,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
       // random bits.  Unrolled with static register names: no calls, no dynamically indexed arrays (elx_fast.cu).
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
-        const int wa = (3 * d) >> 2, off = (3 * d) & 3;
-        const uint32_t w = off == 0 ? prmt<0x2100u>(X[wa], 0u)
-                         : off == 1 ? X[wa]
-                         : off == 2 ? prmt<0x4320u>(X[wa], X[wa < 11 ? wa + 1 : wa])
-                                    : prmt<0x5430u>(X[wa], X[wa < 11 ? wa + 1 : wa]);
+        const uint32_t w = ELX_DRAW24(X, d);
         const uint32_t row = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
         const uint32_t j = (w >> 8) & 0xffu, idx = (row << 8) | j;
         const uint32_t e = lds_u32(tbl + idx * 4u);

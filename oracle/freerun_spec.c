@@ -25,7 +25,8 @@
  * four frontier nodes below r at once from a 256-outcome joint row (inner nodes summed out), o = sum_k state(out[k]) << 2k.
  * A draw is 24 bits; the 16 sites of a group s >> 4 share three Philox calls:
  *   B[0..47] = little-endian bytes of philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2;  d = s & 15
- *   x24 = B[3d] | B[3d+1] << 8 | B[3d+2] << 16;  j = x24 & 255; t = x24 >> 8; e = qe32[g][c][state of r][j] = [q_hi : 16][alias : 8][0 : 8]
+ *   X[0..11] = the 12 little-endian words of B; x24 = X[3(d>>2) + (d&3)] >> 8 for d&3 < 3, else the low bytes of X[3(d>>2)], X[3(d>>2)+1],
+ *   X[3(d>>2)+2] (first = least significant);  j = x24 & 255; t = x24 >> 8; e = qe32[g][c][state of r][j] = [q_hi : 16][alias : 8][0 : 8]
  *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < qlo24[g][c][state of r][j] ? j : alias
  * Records come in walk order (r is the root or a frontier node of an earlier record); recs = 52 int32 per record in the
  * layout include/elynx_b200.h documents.
@@ -35,7 +36,7 @@
  * component inside superblocks of 2^SB sites (SB = 20 for C <= 16, 22 for C <= 64, else 24): B = s >> SB, rank = number of earlier sites of B with the same component,
  * q = rank >> 4, d = rank & 15; the 16 sites of a group share three Philox calls:
  *   Z[0..47] = little-endian bytes of philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
- *   x24 = Z[3d] | Z[3d+1] << 8 | Z[3d+2] << 16;  j = x24 & 511; t = x24 >> 9; e = de32[g][c][state of r][j] = [q_hi : 15][alias : 9][0 : 8]
+ *   x24 = draw d of Z as in quad mode;  j = x24 & 511; t = x24 >> 9; e = de32[g][c][state of r][j] = [q_hi : 15][alias : 9][0 : 8]
  *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < dlo24[g][c][state of r][j] ? j : alias
  */
 #include <stdint.h>
@@ -171,6 +172,14 @@ int spec_freerun_pair(int N, int K, int C, int is_mixture, int rounds, const int
   return 0;
 }
 
+/* draw d (0..15) of the 48 random bytes = 12 little-endian words X[0..11]: draws 4k, 4k+1, 4k+2 are the upper 24 bits of
+ * X[3k], X[3k+1], X[3k+2]; draw 4k+3 collects the three low bytes those leave over (X[3k] first) */
+static uint32_t draw24(const uint8_t *B, int d) {
+  const int w0 = 3 * (d >> 2), i = d & 3;
+  if (i < 3) return (uint32_t)B[4 * (w0 + i) + 1] | ((uint32_t)B[4 * (w0 + i) + 2] << 8) | ((uint32_t)B[4 * (w0 + i) + 3] << 16);
+  return (uint32_t)B[4 * w0] | ((uint32_t)B[4 * (w0 + 1)] << 8) | ((uint32_t)B[4 * (w0 + 2)] << 16);
+}
+
 #define QUAD_REC_INTS 52
 static int64_t quad_ties = 0;
 int64_t spec_quad_ties(void) { return quad_ties; } /* ties seen by the last spec_freerun_quad call */
@@ -212,7 +221,7 @@ int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int
         for (int b = 0; b < 16; ++b) B[16 * call + b] = (uint8_t)(y[b >> 2] >> (8 * (b & 3)));
       }
       const int d = (int)(s & 15);
-      uint32_t x24 = (uint32_t)B[3 * d] | ((uint32_t)B[3 * d + 1] << 8) | ((uint32_t)B[3 * d + 2] << 16);
+      uint32_t x24 = draw24(B, d);
       uint32_t j = x24 & 255u, t = x24 >> 8;
       int64_t idx = (((int64_t)g * C + c) * 4 + st[rt]) * 256 + j;
       uint32_t e = qe32[idx], qh = e >> 16, al = (e >> 8) & 255u, o;
@@ -292,7 +301,7 @@ int spec_freerun_duo(int N, int K, int C, int is_mixture, int rounds, const int3
         philox(rounds, y, k0, k1);
         for (int b = 0; b < 16; ++b) B[16 * call + b] = (uint8_t)(y[b >> 2] >> (8 * (b & 3)));
       }
-      uint32_t x24 = (uint32_t)B[3 * d] | ((uint32_t)B[3 * d + 1] << 8) | ((uint32_t)B[3 * d + 2] << 16);
+      uint32_t x24 = draw24(B, d);
       uint32_t j = x24 & 511u, t = x24 >> 9;
       int64_t idx = (((int64_t)g * C + c) * K + st[rt]) * 512 + j;
       uint32_t e = de32[idx], qh = e >> 17, al = (e >> 8) & 511u, o;
