@@ -93,8 +93,10 @@ struct DuoTables {
   DuoCapDev *d_caps = nullptr;
   uint8_t *d_ftab = nullptr;    // [G][C] x (32 B header + K x 512 entries)
   uint32_t *d_dlo24 = nullptr;  // [G][C][K][512]
-  int tiled = 0, threads = 0, minb = 1, nstage = 0, stage_bytes = 0;
+  int tiled = 0, threads = 0, minb = 1, nstage = 0, stage_bytes = 0;  // threads: the biggest CTA class that fits
   size_t smem = 0;
+  int nstage512 = 0;    // > 0: the 512-thread class fits as well (preferred whenever the tile fits it: 2 % faster)
+  size_t smem512 = 0;
   // per-call scratch (grow-only)
   uint8_t *d_comp8 = nullptr, *d_root8 = nullptr, *d_rootb = nullptr, *d_tmp = nullptr;
   uint32_t *d_pos32 = nullptr, *d_site32 = nullptr, *d_hist = nullptr, *d_base = nullptr, *d_total = nullptr, *d_r0 = nullptr;
@@ -219,18 +221,18 @@ __global__ void k1_alias_duo(int64_t rows, int K, int stage_bytes, const double 
   }
 }
 
-// Stage header (32 bytes in front of the rows of (record g, component c)), as in quad mode: out[k] >= 0: leaf row;
-// 0x80000000 | byte offset of the slot: internal frontier node; 0xffffffff: absent.
+// Stage header (32 bytes in front of the rows of (record g, component c)): node0, slot holding the root's states; out[k] >= 0:
+// leaf row; 0x80000000 | slot: internal frontier node; 0xffffffff: absent.  (Slot NUMBERS: the slot stride is the launch's.)
 __global__ void k_build_duo_hdr(int G, int C, int stage_bytes, int threads, const DuoRecDev *__restrict__ recs, uint8_t *__restrict__ ftab) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)G * C) return;
   const DuoRecDev r = recs[i / C];
-  const uint32_t stride = (uint32_t)threads * 16u;
+  (void)threads;
   uint32_t o[2];
   for (int k = 0; k < 2; ++k)
-    o[k] = r.leaf[k] >= 0 ? (uint32_t)r.leaf[k] : (r.dst[k] >= 0 ? (0x80000000u | ((uint32_t)r.dst[k] * stride)) : 0xffffffffu);
+    o[k] = r.leaf[k] >= 0 ? (uint32_t)r.leaf[k] : (r.dst[k] >= 0 ? (0x80000000u | (uint32_t)r.dst[k]) : 0xffffffffu);
   uint4 *h = reinterpret_cast<uint4 *>(ftab + i * (int64_t)stage_bytes);
-  h[0] = make_uint4(r.node0, (uint32_t)r.src * stride, 0u, 0u);
+  h[0] = make_uint4(r.node0, (uint32_t)r.src, 0u, 0u);
   h[1] = make_uint4(o[0], o[1], 0xffffffffu, 0xffffffffu);
 }
 
@@ -314,37 +316,49 @@ __global__ void k_duo_scan(DuoBucketArgs b) {
 // Segments batch by batch, component-major inside a batch (concurrent CTAs then stream the same component's rows), and the
 // CTA tiles; tile_begin[b] = first tile of batch b.
 __global__ void k_duo_layout(DuoBucketArgs b) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  const int C = b.s.C;
-  uint64_t slot = 0;
-  int nt = 0;
-  const uint64_t sb0 = b.base0 >> b.sb;
-  for (int bt = 0; bt < b.nbatch; ++bt) {
-    b.tile_begin[bt] = nt < b.max_tiles ? nt : b.max_tiles;
-    for (int c = 0; c < C; ++c)
-      for (int j = b.batch_sb[bt]; j < b.batch_sb[bt + 1]; ++j) {
-        const uint32_t r0 = j == 0 ? b.r0[c] : 0u, r1 = b.total[(int64_t)j * C + c];
-        DuoSeg sg;
-        sg.q0 = r0 >> 4;
-        sg.ngroups = r1 > r0 ? ((r1 + 15u) >> 4) - sg.q0 : 0u;
-        sg.slot_off = slot;
-        b.seg[(int64_t)j * C + c] = sg;
-        for (uint32_t g = 0; g < sg.ngroups; g += (uint32_t)b.tile_groups) {
-          if (nt < b.max_tiles) {
-            DuoTile t;
-            t.comp = (uint32_t)c; t.q_first = sg.q0 + g; t.ngroups = min((uint32_t)b.tile_groups, sg.ngroups - g);
-            t.sb_lo = (uint32_t)(sb0 + j); t.sb_hi = (uint32_t)((sb0 + j) >> 32); t.pad = 0;
-            t.slot_off = slot + (uint64_t)g * 16u;
-            b.tiles[nt] = t;
-          }
-          ++nt;
+  // one block: thread 0 lays the segments out (a few hundred at most), then all threads write the tiles of their segments
+  const int C = b.s.C, nseg = b.NSB * C;
+  extern __shared__ int s_first[];  // [nseg] first tile of the segment with order index e (batch-major, component, superblock)
+  if (threadIdx.x == 0) {
+    uint64_t slot = 0;
+    int nt = 0, e = 0;
+    for (int bt = 0; bt < b.nbatch; ++bt) {
+      b.tile_begin[bt] = nt < b.max_tiles ? nt : b.max_tiles;
+      for (int c = 0; c < C; ++c)
+        for (int j = b.batch_sb[bt]; j < b.batch_sb[bt + 1]; ++j, ++e) {
+          const uint32_t r0 = j == 0 ? b.r0[c] : 0u, r1 = b.total[(int64_t)j * C + c];
+          DuoSeg sg;
+          sg.q0 = r0 >> 4;
+          sg.ngroups = r1 > r0 ? ((r1 + 15u) >> 4) - sg.q0 : 0u;
+          sg.slot_off = slot;
+          b.seg[(int64_t)j * C + c] = sg;
+          s_first[e] = nt;
+          nt += (int)((sg.ngroups + (uint32_t)b.tile_groups - 1) / (uint32_t)b.tile_groups);
+          slot += (uint64_t)sg.ngroups * 16u;
         }
-        slot += (uint64_t)sg.ngroups * 16u;
-      }
+    }
+    b.tile_begin[b.nbatch] = nt < b.max_tiles ? nt : b.max_tiles;
+    *b.ntiles = nt < b.max_tiles ? nt : b.max_tiles;
+    if (nt > b.max_tiles) atomicExch(b.s.error_flag, -21);
   }
-  b.tile_begin[b.nbatch] = nt < b.max_tiles ? nt : b.max_tiles;
-  *b.ntiles = nt < b.max_tiles ? nt : b.max_tiles;
-  if (nt > b.max_tiles) atomicExch(b.s.error_flag, -21);
+  __syncthreads();
+  const uint64_t sb0 = b.base0 >> b.sb;
+  for (int e = threadIdx.x; e < nseg; e += blockDim.x) {
+    // order index -> (batch, component, superblock)
+    int bt = 0, rem = e;
+    while (bt + 1 < b.nbatch && rem >= (b.batch_sb[bt + 1] - b.batch_sb[bt]) * C) { rem -= (b.batch_sb[bt + 1] - b.batch_sb[bt]) * C; ++bt; }
+    const int nsb = b.batch_sb[bt + 1] - b.batch_sb[bt], c = rem / nsb, j = b.batch_sb[bt] + rem % nsb;
+    const DuoSeg sg = b.seg[(int64_t)j * C + c];
+    int t = s_first[e];
+    for (uint32_t g = 0; g < sg.ngroups; g += (uint32_t)b.tile_groups, ++t) {
+      if (t >= b.max_tiles) break;
+      DuoTile tile;
+      tile.comp = (uint32_t)c; tile.q_first = sg.q0 + g; tile.ngroups = min((uint32_t)b.tile_groups, sg.ngroups - g);
+      tile.sb_lo = (uint32_t)(sb0 + j); tile.sb_hi = (uint32_t)((sb0 + j) >> 32); tile.pad = 0;
+      tile.slot_off = sg.slot_off + (uint64_t)g * 16u;
+      b.tiles[t] = tile;
+    }
+  }
 }
 
 // Stable rank of every site inside its (superblock, component) -> bucket slot; writes the slot's root state (x 8: the row
@@ -780,7 +794,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
                                             const uint32_t q, const uint64_t pos0, const int lane) {
   const SimArgs &a = fa.s;
   const uint32_t cx = q | (tile.comp << 20), cy = tile.sb_lo, cw = tile.sb_hi << 8;
-  const uint32_t slot_base_m = slot_base - 0x80000000u;  // + (0x80000000 | offset) = slot_base + offset
+  const uint32_t stride = (uint32_t)fa.slot_stride;
   const int nstage = fa.nstage;
   const uint32_t mhi = fa.mhi, negk = fa.negk256;
   int buf = 0;
@@ -793,9 +807,9 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
     const uint32_t node0 = h0.x;
     const uint32_t tbl = sbuf + 32u;
 #ifdef ELX_DEBUG_BOUNDS
-    if (h0.y >= (uint32_t)a.n_slots * (uint32_t)fa.slot_stride || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
+    if (h0.y >= (uint32_t)a.n_slots || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
 #endif
-    const uint4 rv = lds_v4(slot_base + h0.y);
+    const uint4 rv = lds_v4(slot_base + h0.y * stride);
     const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
     uint32_t X[12];
 #pragma unroll
@@ -859,7 +873,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
   if ((int32_t)(code) >= 0) {                                                                                   \
     if (FAST || active) stg_v4(tmp_base + (int64_t)(code) * fa.tmp_pitch, make_uint4(PW[0], PW[1], PW[2], PW[3])); \
   } else if ((code) != 0xffffffffu) {                                                                           \
-    sts_v4(slot_base_m + (code), make_uint4(PW[0] << 3, PW[1] << 3, PW[2] << 3, PW[3] << 3));                   \
+    sts_v4(slot_base + ((code) & 0x7fffffffu) * stride, make_uint4(PW[0] << 3, PW[1] << 3, PW[2] << 3, PW[3] << 3));                   \
   }
     ELX_DUO_OUT(P0, h1.x)
     ELX_DUO_OUT(P1, h1.y)
@@ -967,6 +981,12 @@ static bool duo_geometry(int K, int n_slots, DuoTables *dt) {
     if (nstage < 2) continue;
     dt->tiled = 1; dt->threads = th; dt->minb = minb; dt->nstage = nstage; dt->stage_bytes = (int)stage;
     dt->smem = 128 + (size_t)nstage * stage + slots;
+    if (th == 640) {  // the 512 class next to it
+      const size_t slots512 = (size_t)(n_slots > 0 ? n_slots : 1) * 512 * 16;
+      int ns = (int)((per_cta - 128 - slots512) / stage);
+      if (ns > cap) ns = cap;
+      dt->nstage512 = ns; dt->smem512 = 128 + (size_t)ns * stage + slots512;
+    }
     return true;
   }
   dt->tiled = 0; dt->threads = 512; dt->minb = 1; dt->nstage = 0; dt->stage_bytes = (int)stage; dt->smem = 0;
@@ -1159,6 +1179,8 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   const size_t slots_bound = (size_t)a.nsites + 32u * (size_t)NSB * C + 16;
   if (slots_bound >= ((size_t)1 << 32) || M >= ((int64_t)1 << 32))
     return fail(h, ELX_E_UNSUPPORTED, "duo mode: more than 2^32 sites in one device call; split the site range");
+  if ((size_t)NSB * C * sizeof(int) > 40 * 1024)
+    return fail(h, ELX_E_UNSUPPORTED, "duo mode: too many (superblock, component) segments in one device call; split the site range");
   const bool tiled = dt->tiled && !(h->flags & ELX_FLAG_FORCE_GENERIC);
   int tile_groups = duo_tile_groups(h, dt, u0, M);
   const int max_tiles = (int)((slots_bound / 16 + 511) / 512) * 2 + NSB * C + 1;  // (tiles are never smaller than 320 groups unless ELX_DUO_TILE says so)
@@ -1219,7 +1241,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   if (h->rounds == 7) k_duo_comps<7><<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
   else k_duo_comps<10><<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
   k_duo_scan<<<(unsigned)(((int64_t)NSB * C * 32 + 255) / 256), 256, 0, h->stream>>>(b);
-  k_duo_layout<<<1, 32, 0, h->stream>>>(b);
+  k_duo_layout<<<1, 256, sizeof(int) * (size_t)NSB * C, h->stream>>>(b);
   k_duo_scatter<<<(unsigned)ntile_b, 256, 0, h->stream>>>(b);
   h->launches += 4;
   DUO_CUDA(h, cudaGetLastError());
@@ -1230,7 +1252,11 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   fa.s = a;
   fa.s.n_slots = dt->prog.n_slots;
   fa.G = dt->G; fa.recs = dt->d_recs; fa.ftab = dt->d_ftab; fa.dlo24 = dt->d_dlo24;
-  fa.stage_bytes = dt->stage_bytes; fa.nstage = dt->nstage; fa.slot_stride = dt->threads * 16;
+  // the CTA class of this call: 512 threads whenever the tile fits (measured 2 % faster than the 640 class at the same tile)
+  const bool cls512 = dt->threads == 640 && dt->nstage512 >= 2 && tile_groups <= 512;
+  const int cls = cls512 ? 512 : dt->threads;
+  const size_t cls_smem = cls512 ? dt->smem512 : dt->smem;
+  fa.stage_bytes = dt->stage_bytes; fa.nstage = cls512 ? dt->nstage512 : dt->nstage; fa.slot_stride = cls * 16;
   fa.tiles = dt->d_tiles; fa.tile_begin = dt->d_tile_begin; fa.rootb = dt->d_rootb; fa.site32 = dt->d_site32;
   fa.tmp = dt->d_tmp; fa.tmp_pitch = tmp_pitch; fa.base0 = base0;
   fa.mhi = (uint32_t)((65536 / h->K + 1) << 8);
@@ -1256,8 +1282,8 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
     mark(ms);
     cudaError_t e;
     if (tiled) {
-      e = h->rounds == 7 ? launch_duo_tiled_t<7>(dt->threads, dt->minb, tile_groups, fa, grid_tiles, dt->smem, ms)
-                         : launch_duo_tiled_t<10>(dt->threads, dt->minb, tile_groups, fa, grid_tiles, dt->smem, ms);
+      e = h->rounds == 7 ? launch_duo_tiled_t<7>(cls, dt->minb, tile_groups, fa, grid_tiles, cls_smem, ms)
+                         : launch_duo_tiled_t<10>(cls, dt->minb, tile_groups, fa, grid_tiles, cls_smem, ms);
     } else {
       const dim3 grid((unsigned)grid_tiles, (unsigned)(tile_groups * 16 / 256));
       if (h->rounds == 7) k2_duo_generic<7><<<grid, 256, 0, ms>>>(fa);
@@ -1329,7 +1355,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
     DUO_CUDA(h, cudaEventRecord(dt->ev_done, dt->s2));
     DUO_CUDA(h, cudaStreamWaitEvent(h->stream, dt->ev_done, 0));
   }
-  h->last_kernel = tiled ? "k2_duo_tiled<" + std::to_string(h->rounds) + "," + std::to_string(dt->threads) + "," + std::to_string(dt->threads == 256 ? dt->minb : 1) + ">"
+  h->last_kernel = tiled ? "k2_duo_tiled<" + std::to_string(h->rounds) + "," + std::to_string(cls) + "," + std::to_string(cls == 256 ? dt->minb : 1) + ">"
                          : "k2_duo_generic<" + std::to_string(h->rounds) + ">";
   *used = 1;
   return 0;

@@ -85,8 +85,19 @@ __host__ __device__ __forceinline__ uint32_t draw24_from_words(const uint32_t *X
   return (X[w0] & 0xffu) | ((X[w0 + 1] & 0xffu) << 8) | ((X[w0 + 2] & 0xffu) << 16);
 }
 
+// mwc-random `categorical`: the first i with cv[i] >= cv[K-1] * u.  cv is a running sum of non-negative weights, hence
+// non-decreasing: for long vectors (C60: 60 components) a binary search finds the same index in 6 steps instead of 30.
 __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, double u) {
   double p = __dmul_rn(cv[K - 1], u);
+  if (K > 16) {
+    if (!(cv[K - 1] >= p)) return -1;
+    int lo = 0, hi = K - 1;  // invariant: cv[hi] >= p; everything below lo is < p
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cv[mid] >= p) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  }
   for (int i = 0; i < K; ++i)
     if (cv[i] >= p) return i;
   return -1;
