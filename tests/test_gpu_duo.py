@@ -151,3 +151,28 @@ def test_duo_many_superblocks_call_equals_superblock_calls(pipeline):
     r = subprocess.run([sys.executable, "-c", "import test_gpu_duo as t; t._multi_superblock_check(); print('pipeline ok')"],
                        env=env, cwd=here, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "pipeline ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("k,duo", [(5, True), (7, True), (22, True), (23, False)])
+def test_duo_state_counts_other_than_20(k, duo):
+    """The ABI takes any number of states: duo mode covers 5..22 (K^2 <= 512 columns; the outcome decode o -> (o mod K, o div K)
+    is a magic multiply that depends on K), 23 and more stay node by node."""
+    rng = np.random.default_rng(k)
+    c = 3
+    ds = rng.dirichlet(np.ones(k) * 3, size=c)
+    es = rng.uniform(0.2, 2.0, size=(c, k, k))
+    es = (es + es.transpose(0, 2, 1)) / 2
+    for i in range(c):
+        np.fill_diagonal(es[i], 0.0)
+    ws = np.array([0.5, 0.2, 0.3])
+    model = (True, ws, ds, es, None)
+    tree = tree_from_file("UltraMetric.tree")
+    for fg in (False, True):
+        with make_sim(model, tree, force_generic=fg) as sim:
+            assert (sim.duo_groups > 0) == duo
+            if duo and not fg:
+                check_duo_tables(sim.ptables(), sim.duo_tables(), tree.parent, tree.leaf_row, max_records=4)
+            leaves, comps, _ = sim.simulate(3, 5000, site0=SB - 2500, want_comps=True)
+            l0, c0, _ = spec_freerun(sim, model, tree, 3, SB - 2500, 5000)
+            assert np.array_equal(leaves, l0) and np.array_equal(comps, c0)
+            assert leaves.max() == k - 1
