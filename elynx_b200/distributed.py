@@ -57,8 +57,9 @@ def simulate_fasta_to_file(sim, seed: int, total_sites: int, names, alphabet: st
 
     Rank r owns the columns site_range(r, world, total_sites, align=16) of every sequence line.  Kernel K3 (slice
     mode) of every GPU packs the characters of its columns STRAIGHT into that rank's pinned host buffer over PCIe
-    (no device-side file image, no host-side interleaving, no collective); the host then writes each row segment at
-    its byte offset in the file (one pwrite per row and batch).  Rank 0 creates the file at its final size and writes
+    (no device-side file image, no host-side interleaving, no collective; the pack call only enqueues -- its alphabet travels
+    in the kernel's parameter block -- so batch b+1 is simulated and packed while the host writes batch b); the host then writes
+    each row segment at its byte offset in the file (one pwrite per row and batch, straight from the pinned buffer).  Rank 0 creates the file at its final size and writes
     the `>name` lines and the newlines.  `barrier` orders file creation before the other ranks open it
     (torch.distributed.barrier under torchrun)."""
     import os
@@ -108,7 +109,7 @@ def simulate_fasta_to_file(sim, seed: int, total_sites: int, names, alphabet: st
                     ev.synchronize()
                     arr = hb.numpy()
                     for i in range(t):
-                        os.pwrite(fd, arr[i, :k].tobytes(), row_off[i] + s0)
+                        os.pwrite(fd, memoryview(arr[i, :k]), row_off[i] + s0)  # (a view of the pinned row: no copy)
                 pending = cur
         finally:
             os.close(fd)
