@@ -87,6 +87,55 @@ __host__ __device__ __forceinline__ uint32_t draw24_from_words(const uint32_t *X
 
 // mwc-random `categorical`: the first i with cv[i] >= cv[K-1] * u.  cv is a running sum of non-negative weights, hence
 // non-decreasing: for long vectors (C60: 60 components) a binary search finds the same index in 6 steps instead of 30.
+// One alias row of KP columns by ONE WARP (quad rows: KP = 256, duo rows: KP = 512): integer masses m_o = round(p_o / sum * 2^48)
+// (residual to the largest), Vose pairing, column capacity CAP = 2^48 / KP.  The order-sensitive parts -- the sum, the two
+// stacks, the pairing -- run on lane 0 over shared-memory arrays exactly as a single thread would (same tables bit for bit);
+// loads, masses, the arg-max and the stores are spread over the lanes.  sm: KP doubles + 2 KP int64 + 3 KP int16 per warp.
+// On return q[j] / alias[j] hold the thresholds and aliases of the columns (q[j] == CAP: a full column).
+template <int KP>
+__device__ __forceinline__ void alias_row_warp(const double *__restrict__ p, double *v, int64_t *m, int64_t *q, int16_t *alias,
+                                               int16_t *small, int16_t *large, int lane) {
+  constexpr int64_t CAP = ((int64_t)1 << 48) / KP;
+  for (int j = lane; j < KP; j += 32) { const double x = p[j]; v[j] = x > 0.0 ? x : 0.0; }
+  __syncwarp();
+  double sum = 0.0;
+  if (lane == 0)
+    for (int j = 0; j < KP; ++j) sum += v[j];
+  sum = __shfl_sync(0xffffffffu, sum, 0);
+  int64_t tot = 0, best = -1;
+  int big = 0;
+  for (int j = lane; j < KP; j += 32) {
+    const int64_t mj = sum > 0.0 ? (int64_t)llrint(v[j] / sum * 0x1p48) : (j == 0 ? ((int64_t)1 << 48) : 0);
+    m[j] = mj;
+    tot += mj;
+    if (mj > best) { best = mj; big = j; }  // (ascending j per lane: the first maximum)
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const int64_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, big, o);
+    if (ob > best || (ob == best && oj < big)) { best = ob; big = oj; }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    m[big] += ((int64_t)1 << 48) - tot;
+    int ns = 0, nl = 0;
+    for (int j = KP - 1; j >= 0; --j) {
+      alias[j] = (int16_t)j;
+      q[j] = CAP;
+      if (m[j] < CAP) small[ns++] = (int16_t)j; else large[nl++] = (int16_t)j;
+    }
+    while (ns > 0 && nl > 0) {
+      const int s_ = small[--ns], l_ = large[--nl];
+      q[s_] = m[s_];
+      alias[s_] = (int16_t)l_;
+      m[l_] -= CAP - m[s_];
+      if (m[l_] < CAP) small[ns++] = (int16_t)l_; else large[nl++] = (int16_t)l_;
+    }
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, double u) {
   double p = __dmul_rn(cv[K - 1], u);
   if (K > 16) {

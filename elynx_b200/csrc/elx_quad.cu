@@ -131,40 +131,23 @@ __global__ void k1_quad_joint(int G, int C, int K, const QuadCapDev *__restrict_
 }
 
 // Alias rows of 256 columns: integer masses m_o = round(p_o / sum * 2^48) (residual to the largest), Vose pairing, column
-// capacity 2^40; entry = [threshold bits 39..24 : 16][alias : 8][0 : 8], qlo24 = threshold bits 23..0.  One thread per row.
-__global__ void k1_alias_quad(int64_t rows, const double *__restrict__ joint, uint32_t *__restrict__ e32, uint32_t *__restrict__ qlo24) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
+// capacity 2^40; entry = [threshold bits 39..24 : 16][alias : 8][0 : 8], qlo24 = threshold bits 23..0.  One WARP per row
+// (alias_row_warp, elx_ptx.cuh; one thread per row with 5.5 KB of local arrays took 0.36 ms for cfg2's 5808 rows).
+constexpr int ALIAS_WARPS = 4;
+__global__ void __launch_bounds__(ALIAS_WARPS * 32) k1_alias_quad(int64_t rows, const double *__restrict__ joint, uint32_t *__restrict__ e32,
+                                                              uint32_t *__restrict__ qlo24) {
   constexpr int KP = QUAD_COLS;
   constexpr int64_t CAP = (int64_t)1 << 40;
-  int64_t m[KP], q[KP];
-  int16_t alias[KP], small[KP], large[KP];
-  const double *p = joint + r * KP;
-  double sum = 0.0;
-  for (int j = 0; j < KP; ++j) sum += p[j] > 0.0 ? p[j] : 0.0;
-  int64_t tot = 0;
-  int big = 0;
-  for (int j = 0; j < KP; ++j) {
-    const double v = p[j] > 0.0 ? p[j] : 0.0;
-    m[j] = sum > 0.0 ? (int64_t)llrint(v / sum * 0x1p48) : (j == 0 ? ((int64_t)1 << 48) : 0);
-    tot += m[j];
-    if (m[j] > m[big]) big = j;
-  }
-  m[big] += ((int64_t)1 << 48) - tot;
-  int ns = 0, nl = 0;
-  for (int j = KP - 1; j >= 0; --j) {
-    alias[j] = (int16_t)j;
-    q[j] = CAP;
-    if (m[j] < CAP) small[ns++] = (int16_t)j; else large[nl++] = (int16_t)j;
-  }
-  while (ns > 0 && nl > 0) {
-    const int s = small[--ns], l = large[--nl];
-    q[s] = m[s];
-    alias[s] = (int16_t)l;
-    m[l] -= CAP - m[s];
-    if (m[l] < CAP) small[ns++] = (int16_t)l; else large[nl++] = (int16_t)l;
-  }
-  for (int j = 0; j < KP; ++j) {
+  extern __shared__ __align__(16) uint8_t sm_alias[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * ALIAS_WARPS + w;
+  if (r >= rows) return;
+  uint8_t *base = sm_alias + (size_t)w * (KP * (8 + 8 + 8 + 6));
+  double *v = reinterpret_cast<double *>(base);
+  int64_t *m = reinterpret_cast<int64_t *>(base + KP * 8), *q = reinterpret_cast<int64_t *>(base + KP * 16);
+  int16_t *alias = reinterpret_cast<int16_t *>(base + KP * 24), *small = alias + KP, *large = alias + 2 * KP;
+  alias_row_warp<KP>(joint + r * KP, v, m, q, alias, small, large, lane);
+  for (int j = lane; j < KP; j += 32) {
     int64_t qq = q[j];
     int al = alias[j];
     if (qq >= CAP) { qq = CAP - 1; al = j; }  // a full column: always accept (alias = self)
@@ -574,7 +557,7 @@ int quad_tables_build(elx_handle *h) {
   h->launches++;
   QUAD_CUDA(h, cudaGetLastError());
   const int64_t rows = ents / QUAD_COLS;
-  k1_alias_quad<<<(unsigned)((rows + 63) / 64), 64, 0, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qlo24);
+  k1_alias_quad<<<(unsigned)((rows + ALIAS_WARPS - 1) / ALIAS_WARPS), ALIAS_WARPS * 32, (size_t)ALIAS_WARPS * QUAD_COLS * 30, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qlo24);
   h->launches++;
   QUAD_CUDA(h, cudaGetLastError());
   if (qt->tiled) {
