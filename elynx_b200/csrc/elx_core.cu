@@ -1320,7 +1320,18 @@ struct TransportSync {
   std::condition_variable cv_issue; // the waiter thread: the next chunk's copy is enqueued
   std::atomic<int> abort_flag{0};
 };
-constexpr int64_t UNPACK_COLS = 65536;  // sites per work unit of the unpack threads
+static int64_t env_i64(const char *name, int64_t dflt) {
+  const char *e = getenv(name);
+  return e ? atoll(e) : dflt;
+}
+// Sites per work unit of the unpack threads: a unit is one row's piece of a batch, whole (2 MB of the caller's buffer for the
+// default batch of 2^21 sites).  Round 1 cut the pieces into 64 KB units handed out in row order; on a FRESH result buffer the
+// thirteen threads then all faulted on the same huge page at once -- each of them allocates and zeroes a 2 MB page and all but
+// one throw theirs away (cfg2, 10 GB into a fresh mapping: 312 ms; units handed out row-interleaved 270 ms; whole pieces of
+// 2^20 sites 226 ms; of 2^21 sites 217 ms; a reused buffer is indifferent: 95-98 ms either way).  Streaming stores stay ahead
+// of plain ones on fresh pages too (226 against 257 ms).  ELX_UNPACK_COLS / ELX_UNPACK_ORDER=1 / ELX_HOST_BATCH_LOG2 for A/B runs.
+static const int64_t UNPACK_COLS = std::max<int64_t>(4096, env_i64("ELX_UNPACK_COLS", (int64_t)1 << 21)) & ~(int64_t)63;
+static const int UNPACK_ORDER = (int)env_i64("ELX_UNPACK_ORDER", 0);
 }  // namespace
 
 // Unpack threads of a host-buffer call: all cores but three (the calling thread feeds the streams, the waiter wakes per
@@ -1362,7 +1373,7 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   // Duo handles bucket every device call by component inside superblocks (elx_duo.cu): their batches are whole superblocks
   // (a batch that starts inside one has to draw the components of the sites in front of it again), the first one shorter
   // when site0 is not aligned.
-  const int64_t BATCH = duo_batch_sites(h) > 0 ? duo_batch_sites(h) : (int64_t)1 << 20;
+  const int64_t BATCH = duo_batch_sites(h) > 0 ? duo_batch_sites(h) : (int64_t)1 << std::min<int64_t>(24, std::max<int64_t>(16, env_i64("ELX_HOST_BATCH_LOG2", 21)));
   int64_t boff = duo_batch_sites(h) > 0 ? site0 % BATCH : 0;
   if (raw && (boff & 31)) boff = 0;  // packed rows of the batches must join on byte boundaries (32-site packing groups)
   const int NB = 2;
@@ -1493,7 +1504,9 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
         for (;;) {
           const int64_t u = ch.next.fetch_add(1, std::memory_order_relaxed);
           if (u >= ch.units) break;
-          const int64_t r = u / ch.ncol, k = u - r * ch.ncol;
+          int64_t r, k;
+          if (UNPACK_ORDER) { k = u / ch.rows; r = u - k * ch.rows; }
+          else { r = u / ch.ncol; k = u - r * ch.ncol; }
           const int64_t c0 = k * UNPACK_COLS, c1 = std::min(ch.nb, c0 + UNPACK_COLS);
           if (ch.raw) {
             const int64_t p0 = ch.bits == 2 ? c0 / 4 : c0 / 8 * 5;

@@ -232,7 +232,7 @@ __global__ void k_build_duo_hdr(int G, int C, int stage_bytes, int threads, cons
   for (int k = 0; k < 2; ++k)
     o[k] = r.leaf[k] >= 0 ? (uint32_t)r.leaf[k] : (r.dst[k] >= 0 ? (0x80000000u | (uint32_t)r.dst[k]) : 0xffffffffu);
   uint4 *h = reinterpret_cast<uint4 *>(ftab + i * (int64_t)stage_bytes);
-  h[0] = make_uint4(r.node0, (uint32_t)r.src, 0u, 0u);
+  h[0] = make_uint4(r.node0, (uint32_t)r.src, __umulhi(PHILOX_M1, r.node0), PHILOX_M1 * r.node0);  // .z, .w: the record's share of the first Philox round (philox3_split)
   h[1] = make_uint4(o[0], o[1], 0xffffffffu, 0xffffffffu);
 }
 
@@ -799,6 +799,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
   const uint32_t mhi = fa.mhi, negk = fa.negk256;
   int buf = 0;
   uint32_t phase = 0;
+  const PhiloxThreadPart tp = philox_thread_part<ROUNDS>(cx, cw, cw | 4u, cw | 8u, fa.rk);
   for (int g = 0; g < fa.G; ++g) {
     mbar_wait(full_bar0 + 8u * (uint32_t)buf, phase);
     const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
@@ -808,15 +809,12 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
     const uint32_t tbl = sbuf + 32u;
 #ifdef ELX_DEBUG_BOUNDS
     if (h0.y >= (uint32_t)a.n_slots || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
+    if (h0.z != __umulhi(PHILOX_M1, node0) || h0.w != PHILOX_M1 * node0) atomicExch(a.error_flag, -9);
 #endif
     const uint4 rv = lds_v4(slot_base + h0.y * stride);
     const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
     uint32_t X[12];
-#pragma unroll
-    for (int cl = 0; cl < 3; ++cl) {
-      const uint4 x = philox4x32_rk<ROUNDS>(make_uint4(cx, cy, node0, cw | (4u * (uint32_t)cl)), fa.rk);
-      X[4 * cl] = x.x; X[4 * cl + 1] = x.y; X[4 * cl + 2] = x.z; X[4 * cl + 3] = x.w;
-    }
+    philox3_split<ROUNDS>(tp, h0.z, h0.w, cy, fa.rk, X);  // = philox4x32(cx, cy, node0, cw | 4 * call), call = 0, 1, 2
     uint32_t P0[4], P1[4];
     uint32_t m = 0xffffffffu;
 #pragma unroll

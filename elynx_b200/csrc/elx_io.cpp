@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <deque>
@@ -92,7 +93,14 @@ __attribute__((target("avx2"))) void unpack2_avx2(const uint8_t *src, uint8_t *d
     r = _mm256_or_si256(r, _mm256_and_si256(_mm256_srli_epi32(x, 6), m3));
     return lut4 ? _mm256_shuffle_epi8(lutv, r) : r;
   };
-  if (can_align) {
+  static const bool no_nt = getenv("ELX_UNPACK_NO_NT") != nullptr;
+  if (can_align && no_nt) {
+    for (; i + 64 <= n; i += 64) {
+      const __m256i a = expand(src + (i >> 2)), b = expand(src + (i >> 2) + 8);
+      _mm256_store_si256(reinterpret_cast<__m256i *>(dst + i), a);
+      _mm256_store_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+    }
+  } else if (can_align) {
     for (; i + 64 <= n; i += 64) {  // one cache line of output per iteration, streaming stores (no read for ownership)
       const __m256i a = expand(src + (i >> 2)), b = expand(src + (i >> 2) + 8);
       _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);

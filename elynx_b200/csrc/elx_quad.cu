@@ -249,7 +249,7 @@ __device__ __forceinline__ uint32_t entry_addr(uint32_t idx, uint32_t entry_byte
 struct QuadStageHdr {
   uint32_t node0;
   uint32_t src_off;  // byte offset of the slot holding the root's states (slot * slot stride)
-  uint32_t pad[2];
+  uint32_t nhi, nlo;  // hi / lo of PHILOX_M1 * node0: the record's share of the first Philox round (philox3_split)
   uint32_t out[4];
 };
 static_assert(sizeof(QuadStageHdr) == 32, "QuadStageHdr must stay 32 bytes");
@@ -270,6 +270,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
   const int nstage = fa.nstage;
   int buf = 0;
   uint32_t phase = 0;
+  const PhiloxThreadPart tp = philox_thread_part<ROUNDS>(G0lo, 0u, 4u, 8u, fa.rk);
   for (int g = 0; g < fa.G; ++g) {
     mbar_wait(full_bar0 + 8u * (uint32_t)buf, phase);
     const uint32_t sbuf = stage_smem + (uint32_t)(buf * fa.stage_bytes);
@@ -279,16 +280,13 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
     const uint32_t tbl = sbuf + 32u;
 #ifdef ELX_DEBUG_BOUNDS
     if (h0.y >= (uint32_t)a.n_slots * (uint32_t)fa.slot_stride || node0 >= (uint32_t)a.N) atomicExch(a.error_flag, -8);
+    if (h0.z != __umulhi(PHILOX_M1, node0) || h0.w != PHILOX_M1 * node0) atomicExch(a.error_flag, -9);
 #endif
     const uint4 rv = lds_v4(slot_base + h0.y);
     const uint32_t Rq[4] = {rv.x, rv.y, rv.z, rv.w};
     // 48 random bytes = 16 draws of 24 bits
     uint32_t X[12];
-#pragma unroll
-    for (int cl = 0; cl < 3; ++cl) {
-      const uint4 x = philox4x32_rk<ROUNDS>(make_uint4(G0lo, Ghi, node0, 4u * (uint32_t)cl), fa.rk);
-      X[4 * cl] = x.x; X[4 * cl + 1] = x.y; X[4 * cl + 2] = x.z; X[4 * cl + 3] = x.w;
-    }
+    philox3_split<ROUNDS>(tp, h0.z, h0.w, Ghi, fa.rk, X);  // = philox4x32(G0lo, Ghi, node0, 4 * call), call = 0, 1, 2
     uint32_t W[4];
     uint32_t m = 0xffffffffu;
 #pragma unroll
@@ -445,7 +443,7 @@ __global__ void k_build_quad_ftab(int G, int stage_bytes, int threads, const Qua
     const QuadRecDev r = recs[g];
     const uint32_t stride = (uint32_t)threads * 16u;
     if (ch == 0) {
-      v = make_uint4(r.node0, (uint32_t)r.src * stride, 0u, 0u);
+      v = make_uint4(r.node0, (uint32_t)r.src * stride, __umulhi(PHILOX_M1, r.node0), PHILOX_M1 * r.node0);
     } else {
       uint32_t o[4];
       for (int k = 0; k < 4; ++k)

@@ -49,6 +49,8 @@ def main():
                               ("packed / fresh pageable", lambda: fresh((T, ppitch)), True),
                               ("packed / touched pageable", lambda: touched.reshape(-1)[:T * ppitch].reshape(T, ppitch), True),
                               ("packed / pinned", lambda: pinned.reshape(-1)[:T * ppitch].reshape(T, ppitch), True)):
+        if os.environ.get("PHASES_ONLY") and os.environ["PHASES_ONLY"] not in label:
+            continue
         run(mk(), packed)
         for _ in range(reps):
             t0 = time.perf_counter()
