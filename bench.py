@@ -404,7 +404,7 @@ def run_product(args):
         total_sites = max(64, min(e2e_sites * world, int(24e9 / T) // 64 * 64))
         k_e2e = max(1, min(args.steps, 5))
         if rank == 0 and world > 1 and "ELX_HOST_THREADS" not in os.environ:
-            os.environ["ELX_HOST_THREADS"] = str(max(1, (os.cpu_count() or 4) - 3))  # this process alone uses the box's cores here
+            os.environ["ELX_HOST_THREADS"] = str(max(1, (os.cpu_count() or 4) - 1))  # this process alone uses the box's cores here
 
         def host_barrier():
             torch.cuda.synchronize()
@@ -453,9 +453,25 @@ def run_product(args):
             m = mmap.mmap(-1, int(np.prod(shape)), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)  # (Python's default is MAP_SHARED: shmem)
             return np.frombuffer(m, dtype=np.uint8).reshape(shape)
 
+        def alloc_library(shape):
+            # the library's own result allocator (elx_result_alloc / elx_result_free, as INTEGRATION.md's Haskell stub uses them):
+            # 2 MB aligned, huge-page advised, recycled on free -- faulted in by the first (untimed) step only
+            import weakref
+            n = int(np.prod(shape))
+            L.lib().elx_result_alloc.restype = C.c_void_p
+            ptr = L.lib().elx_result_alloc(C.c_int64(n))
+            if not ptr:
+                raise MemoryError("elx_result_alloc(%d)" % n)
+            arr = np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr)).reshape(shape)
+            weakref.finalize(arr, L.lib().elx_result_free, C.c_void_p(ptr))
+            return arr
+
         pageable = e2e_variant(alloc_fresh, "fresh anonymous mapping per step (untouched pageable memory: first-touch faults inside the timed region)")
         pinned = e2e_variant(alloc_pinned, "page-locked, pre-faulted buffer reused across steps (round 1's measurement)") if not args.no_e2e_pinned else None
         pinned_keep.clear()
+        library_owned = e2e_variant(alloc_library, "elx_result_alloc + elx_result_free per step (the library's recycled, huge-page advised result buffers)")
+        if rank == 0:
+            L.lib().elx_result_pool_trim()
         packed_form = e2e_variant(alloc_fresh,
                                   "elx_simulate_packed into a fresh anonymous mapping: the caller keeps the %d-bit form (no expansion on the host)"
                                   % (2 if model.n_states <= 4 else 5), packed=True) if model.n_states <= 32 else None
@@ -471,7 +487,7 @@ def run_product(args):
                                "buffer completely written + elx_destroy; ONE call on ONE handle driving %d device(s)" % world,
                    "caller_buffer_advice": "madvise(MADV_HUGEPAGE) on the caller's buffer by the library (first-touch faults of 2 MB; "
                                            "tools/bench_prefault.py: 10 GB in 0.16 s instead of 0.50 s on this host class)",
-                   "pinned_prefaulted": pinned, "packed_result_form": packed_form}
+                   "pinned_prefaulted": pinned, "library_result_buffer": library_owned, "packed_result_form": packed_form}
 
     traffic = None
     try:

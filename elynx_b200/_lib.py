@@ -91,6 +91,9 @@ SIGNATURES = {
     "elx_simulate_device": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP, _VP, _I64]),
     "elx_simulate_fasta_gz": (C.c_int, [_VP, _U64, _I64, _CSTRS, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "elx_trim_device_cache": (None, []),
+    "elx_result_alloc": (_VP, [_I64]),
+    "elx_result_free": (None, [_VP]),
+    "elx_result_pool_trim": (None, []),
     "elx_packed_bits": (_I32, [_VP]),
     "elx_packed_pitch": (_I64, [_VP, _I64]),
     "elx_simulate_packed": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _I64, _VP]),

@@ -1334,12 +1334,12 @@ static const int64_t UNPACK_COLS = std::max<int64_t>(4096, env_i64("ELX_UNPACK_C
 static const int UNPACK_ORDER = (int)env_i64("ELX_UNPACK_ORDER", 0);
 }  // namespace
 
-// Unpack threads of a host-buffer call: all cores but three (the calling thread feeds the streams, the waiter wakes per
-// chunk, the driver has threads of its own); ELX_HOST_THREADS when several processes share a box.
+// Unpack threads of a host-buffer call: all cores but one (the calling thread that feeds the streams and the waiter sleep
+// most of the time; round 1 kept three cores free, which measures 5 % slower into a fresh buffer and the same into a reused one); ELX_HOST_THREADS when several processes share a box.
 static thread_local int g_thread_budget = 0;  // > 0: unpack threads of the host-buffer call running on this thread (multi-device calls divide the cores)
 static int transport_threads() {
   if (g_thread_budget > 0) return g_thread_budget;
-  int nt = (int)std::thread::hardware_concurrency() - 3;
+  int nt = (int)std::thread::hardware_concurrency() - 1;  // (round 2: 15 of 16 against 13: fresh buffer 218 -> 207 ms, reused buffer unchanged)
   if (const char *e = getenv("ELX_HOST_THREADS")) {
     nt = atoi(e);
   } else if (const char *w = getenv("LOCAL_WORLD_SIZE")) {  // torchrun: the ranks of this box share its cores
@@ -1478,7 +1478,6 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
       sync.cv.notify_all();
     }
   });
-  // all cores but three (this thread feeds the streams, the waiter wakes per chunk, the driver has threads of its own);
   // waits are blocking: spinning
   // workers were measured to starve the dispatcher (16 spinning threads on 16 cores: 160 ms for cfg2, 8: 122 ms)
   const int nt = transport_threads();

@@ -893,17 +893,22 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) k2_duo_tiled(DuoArgs fa) {
   const uint32_t slots_smem = stage_smem + (uint32_t)(nstage * fa.stage_bytes);
   const DuoTile tile = fa.tiles[tile_first + blockIdx.x];
 
+  // warps without a single group of the tile leave at once (the tile that ends a segment is mostly empty, and big mixtures
+  // have many short segments): the ring is released by the warps that stay
+  const int live_warps = max(1, min(THREADS / 32, ((int)tile.ngroups + 31) >> 5));
   if (tid == 0) {
     for (int i = 0; i < nstage; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), THREADS / 32);
+      mbar_init(smem_u32(&empty_bar[i]), live_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   __syncthreads();
 
-  if (__shfl_sync(0xffffffffu, tid, 0) >= THREADS) {  // (through a shuffle: provably warp-uniform for ptxas)
+  const int tid0 = __shfl_sync(0xffffffffu, tid, 0);  // (through a shuffle: provably warp-uniform for ptxas)
+  if (tid0 < THREADS && (tid0 >> 5) >= live_warps) return;
+  if (tid0 >= THREADS) {
     if (tid == THREADS) {  // producer: one lane keeps the ring full with the rows of this tile's component
       const uint8_t *src = fa.ftab + (size_t)tile.comp * fa.stage_bytes;
       const size_t step = (size_t)fa.s.C * fa.stage_bytes;

@@ -18,6 +18,8 @@
 #include <thread>
 #include <vector>
 
+#include <map>
+#include <sys/mman.h>
 #include <zlib.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -417,6 +419,82 @@ int elx_gzip_write(const char *path, const uint8_t *data, int64_t size, int32_t 
   if (fclose(f) != 0 && !failed) { failed = true; first_error = "close failed"; }
   if (failed) return elx::fail(nullptr, ELX_E_INVALID, std::string("elx_gzip_write: ") + (first_error.empty() ? "failed" : first_error));
   return 0;
+}
+
+// ---- result buffers owned by the library ---------------------------------------------------------------------------
+// simulateAndFlatten*Par RETURN their result, so whoever stands in for them decides where it lives.  A fresh allocation of
+// 10 GB costs more than the simulation and its transport together (every page is zeroed by the kernel when it is first
+// written: +110 ms with 2 MB pages, +400 ms with 4 KB pages); buffers from this pool are huge-page advised, recycled on
+// free and therefore faulted in once per process, not once per call.
+namespace {
+std::mutex g_res_mu;
+std::map<void *, size_t> g_res_live;                  // handed out: pointer -> mapped bytes
+std::multimap<size_t, void *> g_res_free;             // mapped bytes -> pointer
+size_t g_res_free_bytes = 0;
+size_t res_pool_cap() {
+  static const size_t cap = [] {
+    const char *e = getenv("ELX_RESULT_POOL_MB");
+    return (size_t)(e ? atoll(e) : 32768) << 20;
+  }();
+  return cap;
+}
+}  // namespace
+
+void *elx_result_alloc(int64_t bytes) {
+  if (bytes <= 0) return nullptr;
+  const size_t need = ((size_t)bytes + 0x1fffff) & ~(size_t)0x1fffff;
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    auto it = g_res_free.lower_bound(need);
+    if (it != g_res_free.end() && it->first <= need + need / 4) {  // best fit within +25 %
+      void *p = it->second;
+      g_res_live[p] = it->first;
+      g_res_free_bytes -= it->first;
+      g_res_free.erase(it);
+      return p;
+    }
+  }
+  // 2 MB aligned, so that every huge page of the mapping can be one
+  const size_t span = need + 0x200000;
+  uint8_t *raw = static_cast<uint8_t *>(mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+  if (raw == MAP_FAILED) return nullptr;
+  uint8_t *p = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 0x1fffff) & ~(uintptr_t)0x1fffff);
+  if (p > raw) munmap(raw, (size_t)(p - raw));
+  if (p + need < raw + span) munmap(p + need, (size_t)(raw + span - (p + need)));
+#ifdef MADV_HUGEPAGE
+  madvise(p, need, MADV_HUGEPAGE);
+#endif
+  std::lock_guard<std::mutex> lk(g_res_mu);
+  g_res_live[p] = need;
+  return p;
+}
+
+void elx_result_free(void *p) {
+  if (!p) return;
+  size_t n = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    auto it = g_res_live.find(p);
+    if (it == g_res_live.end()) return;  // not ours
+    n = it->second;
+    g_res_live.erase(it);
+    if (g_res_free_bytes + n <= res_pool_cap()) {
+      g_res_free.emplace(n, p);
+      g_res_free_bytes += n;
+      return;
+    }
+  }
+  munmap(p, n);
+}
+
+void elx_result_pool_trim(void) {
+  std::multimap<size_t, void *> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    drop.swap(g_res_free);
+    g_res_free_bytes = 0;
+  }
+  for (auto &kv : drop) munmap(kv.second, kv.first);
 }
 
 }  // extern "C"

@@ -99,6 +99,15 @@ int elx_version(void);
 /* The library keeps freed device buffers (tables, staging) in a per-device cache for the next handle / call (up to
  * ELX_DEVICE_CACHE_MB, default 8192; 0 = off); this returns them to the driver. */
 void elx_trim_device_cache(void);
+/* Result buffers owned by the library.  simulateAndFlatten*Par (MarkovProcessAlongTree.hs:101-125, :238-262) RETURN their
+ * result, so the stand-in decides where it lives: a fresh 10 GB allocation costs more than the simulation and its transport
+ * together (the kernel zeroes every page at its first write).  elx_result_alloc returns 2 MB aligned, huge-page advised host
+ * memory; elx_result_free recycles it for the next elx_result_alloc of a similar size (up to ELX_RESULT_POOL_MB, default
+ * 32768, of idle buffers are kept; elx_result_pool_trim unmaps them), so that a process that simulates repeatedly pays the
+ * page faults once.  Any other host pointer works for every call as well. */
+void *elx_result_alloc(int64_t bytes);
+void elx_result_free(void *p);
+void elx_result_pool_trim(void);
 const char *elx_last_error(const elx_handle *h);
 
 /* Builds the per-component eigensystems on the host, uploads the tree, and runs kernel K1
@@ -304,7 +313,7 @@ int64_t elx_launch_count(const elx_handle *h);
 const char *elx_last_kernel(const elx_handle *h);
 /* Bytes the host-buffer calls of this handle (elx_simulate, elx_simulate_injected) have copied device -> host so far.
  * Alignments over <= 4 states cross PCIe packed to 2 bits per site, over <= 32 states to 5 bits, and are expanded into the
- * caller's buffer by host threads (ELX_HOST_THREADS, default: all cores but three -- divided by LOCAL_WORLD_SIZE under
+ * caller's buffer by host threads (ELX_HOST_THREADS, default: all cores but one -- divided by LOCAL_WORLD_SIZE under
  * torchrun --, at most 32; ELX_PACKED_D2H=0 turns the packed transport off). */
 int64_t elx_d2h_bytes(const elx_handle *h);
 /* The host half of that transport, exported for tests and for callers that keep packed alignments: expands a 2-bit packed

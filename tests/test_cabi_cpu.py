@@ -416,3 +416,29 @@ def test_shard_range_follows_get_chunks():
     f, c = C.c_int64(), C.c_int64()
     assert lib.elx_shard_range(10, 0, 0, 1, C.byref(f), C.byref(c)) == L.ELX_E_INVALID
     assert lib.elx_shard_range(10, 2, 2, 1, C.byref(f), C.byref(c)) == L.ELX_E_INVALID
+
+
+def test_result_pool_recycles_buffers():
+    """elx_result_alloc / elx_result_free: 2 MB aligned host buffers, recycled for the next allocation of a similar size
+    (the stand-in for the fresh allocation simulateAndFlatten*Par return their result in)."""
+    import ctypes as C
+
+    lib = L.lib()
+    lib.elx_result_pool_trim()
+    n = 5 << 20
+    p = lib.elx_result_alloc(n)
+    assert p and p % (2 << 20) == 0
+    buf = (C.c_uint8 * n).from_address(p)
+    buf[0] = 7
+    buf[n - 1] = 9
+    lib.elx_result_free(p)
+    q = lib.elx_result_alloc(n - 4096)  # similar size: the same mapping comes back, contents and all
+    assert q == p
+    assert (C.c_uint8 * n).from_address(q)[0] == 7
+    r = lib.elx_result_alloc(64 << 20)  # much larger: a new mapping
+    assert r and r != q
+    lib.elx_result_free(q)
+    lib.elx_result_free(r)
+    lib.elx_result_free(12345)  # not ours: ignored
+    lib.elx_result_pool_trim()
+    assert lib.elx_result_alloc(0) is None
