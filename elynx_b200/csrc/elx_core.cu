@@ -1121,18 +1121,18 @@ int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16
 
 int32_t elx_quad_groups(const elx_handle *h) { return h ? quad_groups(h) : 0; }
 
-int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24) {
+int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qres32) {
   if (!h) return fail(nullptr, ELX_E_INVALID, "elx_quad_get: null handle");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  return quad_get(h, recs, qe32, qlo24);
+  return quad_get(h, recs, qe32, qres32);
 }
 
 int32_t elx_duo_groups(const elx_handle *h) { return h ? duo_groups(h) : 0; }
 
-int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24) {
+int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dres32) {
   if (!h) return fail(nullptr, ELX_E_INVALID, "elx_duo_get: null handle");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  return duo_get(h, recs, de32, dlo24);
+  return duo_get(h, recs, de32, dres32);
 }
 
 int elx_simulate_device(elx_handle *h, uint64_t seed, int64_t site0, int64_t nsites, uint8_t *d_leaves, int64_t leaves_pitch,
@@ -1373,7 +1373,11 @@ static int simulate_host_packed(elx_handle *h, uint64_t seed, int64_t site0, int
   // Duo handles bucket every device call by component inside superblocks (elx_duo.cu): their batches are whole superblocks
   // (a batch that starts inside one has to draw the components of the sites in front of it again), the first one shorter
   // when site0 is not aligned.
-  const int64_t BATCH = duo_batch_sites(h) > 0 ? duo_batch_sites(h) : (int64_t)1 << std::min<int64_t>(24, std::max<int64_t>(16, env_i64("ELX_HOST_BATCH_LOG2", 21)));
+  // 2^21 sites per batch (a row's piece of a batch is then a whole huge page of the caller's buffer), fewer for very tall
+  // matrices: the two device staging sets stay under 16 GB
+  int64_t batch_log2 = std::min<int64_t>(24, std::max<int64_t>(16, env_i64("ELX_HOST_BATCH_LOG2", 21)));
+  while (batch_log2 > 16 && (((int64_t)2 * (h->T + (internal ? h->N : 0))) << batch_log2) > ((int64_t)16 << 30)) --batch_log2;
+  const int64_t BATCH = duo_batch_sites(h) > 0 ? duo_batch_sites(h) : (int64_t)1 << batch_log2;
   int64_t boff = duo_batch_sites(h) > 0 ? site0 % BATCH : 0;
   if (raw && (boff & 31)) boff = 0;  // packed rows of the batches must join on byte boundaries (32-site packing groups)
   const int NB = 2;

@@ -19,11 +19,12 @@
 //   record g = (out[0..1] | r), state i of r:  48 bytes Z[0..47] = little-endian words of
 //     philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
 //     x24 = draw d of the 12 words as in quad mode (elx_ptx.cuh ELX_DRAW24) = [t : 15][j : 9]
-//     e = de32[g][c][i][j] = [q_hi : 15][alias : 9][0 : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
-//     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 8) < dlo24[g][c][i][j] ? j : alias
+//     t != 0:  e = de32[g][c][i][j] = [q : 15][alias : 9][0 : 8];  o = x24 < (e >> 8) ? j : alias   (one 24-bit compare)
+//     t == 0 (escape, 2^-15 per draw):  u = philox(s lo, s hi, out[0], TAG_REFINE).x = [tr : 23][jr : 9];
+//              er = dres32[g][c][i][jr] = [thr : 23][alias : 9];  o = tr < thr ? jr : alias
 //     state(out[0]) = o mod K,  state(out[1]) = o div K
-// Rows carry integer masses round(p / sum * 2^48) (Vose pairing in exact integer arithmetic, column capacity 2^39 = 15 high
-// + 24 low threshold bits); ties come at 2^-15 per draw and are settled exactly.
+// Rows carry integer masses round(p / sum * 2^47), split into a main level of 2^-24 cells and an exact residual (two-level
+// alias rows, elx_ptx.cuh): no draw ever ties with a threshold.
 //
 // Per call: k_duo_comps (component + root state of every site from the superblock start, tile histograms) -> k_duo_scan
 // (ranks of the tiles) -> k_duo_layout (segments = (superblock, component) runs of 16-site groups, CTA tiles) ->
@@ -92,7 +93,7 @@ struct DuoTables {
   DuoRecDev *d_recs = nullptr;
   DuoCapDev *d_caps = nullptr;
   uint8_t *d_ftab = nullptr;    // [G][C] x (32 B header + K x 512 entries)
-  uint32_t *d_dlo24 = nullptr;  // [G][C][K][512]
+  uint32_t *d_dres32 = nullptr;  // [G][C][K][512]
   int tiled = 0, threads = 0, minb = 1, nstage = 0, stage_bytes = 0;  // threads: the biggest CTA class that fits
   size_t smem = 0;
   int nstage512 = 0;    // > 0: the 512-thread class fits as well (preferred whenever the tile fits it: 2 % faster)
@@ -116,7 +117,7 @@ struct DuoArgs {
   int G;
   const DuoRecDev *recs;
   const uint8_t *ftab;
-  const uint32_t *dlo24;
+  const uint32_t *dres32;
   int stage_bytes, nstage, slot_stride;
   const DuoTile *tiles;
   const int *tile_begin;  // [nbatch + 1]
@@ -175,16 +176,15 @@ __global__ void k1_duo_joint(int G, int C, int K, const DuoCapDev *__restrict__ 
   joint[idx] = top;
 }
 
-// Alias rows of 512 columns written straight into the stage images: integer masses m_o = round(p_o / sum * 2^48) (residual
-// to the largest), Vose pairing, column capacity 2^39; entry = [threshold bits 38..24 : 15][alias : 9][0 : 8], dlo24 =
-// threshold bits 23..0.  One thread per row (g, c, i).
+// Two-level alias rows of 512 columns (elx_ptx.cuh) written straight into the stage images: integer masses
+// round(p_o / sum * 2^47) (residual to the largest); main entry = [q : 15][alias : 9][0 : 8], escape entry dres32 =
+// [thr : 23][alias : 9].  One thread per row (g, c, i).
 __global__ void k1_alias_duo(int64_t rows, int K, int stage_bytes, const double *__restrict__ joint, uint8_t *__restrict__ ftab,
-                             uint32_t *__restrict__ dlo24) {
+                             uint32_t *__restrict__ dres32) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  constexpr int KP = DUO_COLS;
-  constexpr int64_t CAP = (int64_t)1 << 39;
-  int64_t m[KP], q[KP];
+  constexpr int KP = DUO_COLS, TB = 15, AB = 9, W = 47, SH = W - 24;
+  int64_t m[KP], q[KP], R[KP];
   int16_t alias[KP], small[KP], large[KP];
   const double *p = joint + r * KP;
   double sum = 0.0;
@@ -193,32 +193,26 @@ __global__ void k1_alias_duo(int64_t rows, int K, int stage_bytes, const double 
   int big = 0;
   for (int j = 0; j < KP; ++j) {
     const double v = p[j] > 0.0 ? p[j] : 0.0;
-    m[j] = sum > 0.0 ? (int64_t)llrint(v / sum * 0x1p48) : (j == 0 ? ((int64_t)1 << 48) : 0);
+    m[j] = sum > 0.0 ? (int64_t)llrint(v / sum * (double)((int64_t)1 << W)) : (j == 0 ? ((int64_t)1 << W) : 0);
     tot += m[j];
     if (m[j] > m[big]) big = j;
   }
-  m[big] += ((int64_t)1 << 48) - tot;
-  int ns = 0, nl = 0;
-  for (int j = KP - 1; j >= 0; --j) {
-    alias[j] = (int16_t)j;
-    q[j] = CAP;
-    if (m[j] < CAP) small[ns++] = (int16_t)j; else large[nl++] = (int16_t)j;
-  }
-  while (ns > 0 && nl > 0) {
-    const int s = small[--ns], l = large[--nl];
-    q[s] = m[s];
-    alias[s] = (int16_t)l;
-    m[l] -= CAP - m[s];
-    if (m[l] < CAP) small[ns++] = (int16_t)l; else large[nl++] = (int16_t)l;
-  }
-  uint32_t *e32 = reinterpret_cast<uint32_t *>(ftab + (r / K) * (int64_t)stage_bytes + 32) + (r % K) * KP;
+  m[big] += ((int64_t)1 << W) - tot;
+  int64_t msum = 0;
   for (int j = 0; j < KP; ++j) {
-    int64_t qq = q[j];
-    int al = alias[j];
-    if (qq >= CAP) { qq = CAP - 1; al = j; }  // a full column: always accept (alias = self)
-    e32[j] = (uint32_t)(((qq >> 24) << 17) | ((int64_t)al << 8));
-    dlo24[r * KP + j] = (uint32_t)(qq & 0xffffff);
+    const int64_t P = m[j], M = P >> SH;
+    R[j] = P - (M << SH);
+    m[j] = M;
+    msum += M;
   }
+  const int64_t excess = msum - (((int64_t)1 << TB) - 1) * KP;  // 1..KP, and the largest outcome holds at least 2^24 / KP cells
+  m[big] -= excess;
+  R[big] += excess << SH;
+  uint32_t *e32 = reinterpret_cast<uint32_t *>(ftab + (r / K) * (int64_t)stage_bytes + 32) + (r % K) * KP;
+  vose_exact<KP>(m, ((int64_t)1 << TB) - 1, q, alias, small, large);
+  for (int j = 0; j < KP; ++j) e32[j] = alias2_main_entry<TB, AB>(j, q[j], alias[j]);
+  vose_exact<KP>(R, (int64_t)1 << SH, q, alias, small, large);
+  for (int j = 0; j < KP; ++j) dres32[r * KP + j] = alias2_escape_entry<AB>(j, q[j], alias[j]);
 }
 
 // Stage header (32 bytes in front of the rows of (record g, component c)): node0, slot holding the root's states; out[k] >= 0:
@@ -743,14 +737,14 @@ __global__ void __launch_bounds__(256) k2_duo_generic(DuoArgs fa) {
     const uint32_t j = x24 & 511u, t = x24 >> 9;
     const uint32_t row = slot[r.src];
     const uint32_t e = __ldg(reinterpret_cast<const uint32_t *>(fa.ftab + ((int64_t)g * a.C + c) * fa.stage_bytes + 32) + row * DUO_COLS + j);
-    const uint32_t qh = e >> 17, al = (e >> 8) & 511u;
     uint32_t o;
-    if (t < qh) o = j;
-    else if (t > qh) o = al;
-    else {
+    if (t != 0u) {
+      o = x24 < (e >> 8) ? j : ((e >> 8) & 511u);
+    } else {  // escape level
       const uint64_t s = fa.base0 + fa.site32[pos];
       const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), r.node0, TAG_REFINE), key);
-      o = (z.x >> 8) < __ldg(fa.dlo24 + ((((int64_t)g * a.C + c) * K + row) << 9) + j) ? j : al;
+      const uint32_t er = __ldg(fa.dres32 + ((((int64_t)g * a.C + c) * K + row) << 9) + (z.x & 511u));
+      o = (z.x >> 9) < (er >> 9) ? (z.x & 511u) : (er & 511u);
     }
     const uint32_t st[2] = {o % (uint32_t)K, o / (uint32_t)K};
 #pragma unroll
@@ -833,7 +827,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
 #endif
         const uint32_t e = duo_lds_u32(tbl + off);
         const uint32_t c = min(w, e);
-        t[i] = w ^ e;
+        t[i] = w;
         const uint32_t mo = c & 0x1ff00u;        // o << 8
         s1[i] = __umulhi(mo, mhi);               // o div K
         v0[i] = duo_mad(s1[i], negk, mo);        // (o mod K) << 8
@@ -843,19 +837,18 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
       P1[qq] = duo_mad(s1[3], 0x1000000u, duo_mad(s1[2], 0x10000u, duo_mad(s1[1], 0x100u, s1[0])));
     }
     if (m < 0x20000u && (FAST || active)) {
-      // exact path (2^-15 per draw): some draw hit its threshold's 15 high bits; settle the tied draws with 24 more random
+      // escape level (2^-15 per draw): some draw has t == 0; its outcome comes from the row's residual masses with 32 fresh
       // bits.  Unrolled with static register names: no calls, no dynamically indexed arrays (elx_fast.cu).
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
         const uint32_t w = ELX_DRAW24(X, d);
-        const uint32_t row8 = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
-        const uint32_t j = (w >> 8) & 0x1ffu;
-        const uint32_t e = duo_lds_u32(tbl + row8 * 256u + j * 4u);
-        if ((w ^ e) < 0x20000u) {
+        if (w < 0x20000u) {
+          const uint32_t row8 = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
           const uint64_t sg = fa.base0 + (uint64_t)__ldg(fa.site32 + pos0 + d);
           const uint4 z = philox4x32_rk<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), fa.rk);
-          const uint32_t ql = __ldg(fa.dlo24 + (((((int64_t)g * a.C + tile.comp) * a.K + (row8 >> 3)) << 9) | j));
-          const uint32_t o = (z.x >> 8) < ql ? j : ((e >> 8) & 0x1ffu);
+          const uint32_t jr = z.x & 0x1ffu;
+          const uint32_t er = __ldg(fa.dres32 + (((((int64_t)g * a.C + tile.comp) * a.K + (row8 >> 3)) << 9) | jr));
+          const uint32_t o = (z.x >> 9) < (er >> 9) ? jr : (er & 0x1ffu);
           const uint32_t s1 = o / (uint32_t)a.K, s0 = o - s1 * (uint32_t)a.K;
           P0[d >> 2] = (P0[d >> 2] & ~(0xffu << (8 * (d & 3)))) | (s0 << (8 * (d & 3)));
           P1[d >> 2] = (P1[d >> 2] & ~(0xffu << (8 * (d & 3)))) | (s1 << (8 * (d & 3)));
@@ -1022,7 +1015,7 @@ int duo_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_recs, sizeof(DuoRecDev) * (size_t)G));
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_caps, sizeof(DuoCapDev) * (size_t)G));
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_ftab, (size_t)G * h->C * dt->stage_bytes));
-  DUO_CUDA(h, cudaMalloc((void **)&dt->d_dlo24, sizeof(uint32_t) * rows * DUO_COLS));
+  DUO_CUDA(h, cudaMalloc((void **)&dt->d_dres32, sizeof(uint32_t) * rows * DUO_COLS));
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_ntiles, sizeof(int)));
   DUO_CUDA(h, cudaMalloc((void **)&dt->d_tile_begin, sizeof(int) * (DUO_MAX_BATCH + 1)));
   dt->sb = duo_sb_log2(h->C);
@@ -1060,7 +1053,7 @@ int duo_tables_build(elx_handle *h) {
     const int64_t rows = (int64_t)gn * rows_per_rec;
     k1_alias_duo<<<(unsigned)((rows + 63) / 64), 64, 0, h->stream>>>(rows, h->K, dt->stage_bytes, d_joint,
                                                                     dt->d_ftab + (size_t)g0 * h->C * dt->stage_bytes,
-                                                                    dt->d_dlo24 + (size_t)g0 * rows_per_rec * DUO_COLS);
+                                                                    dt->d_dres32 + (size_t)g0 * rows_per_rec * DUO_COLS);
     h->launches++;
   }
   const int64_t n = (int64_t)dt->G * h->C;
@@ -1075,7 +1068,7 @@ int duo_tables_build(elx_handle *h) {
 void duo_free(elx_handle *h) {
   DuoTables *dt = static_cast<DuoTables *>(h->duo);
   if (!dt) return;
-  cudaFree(dt->d_recs); cudaFree(dt->d_caps); cudaFree(dt->d_ftab); cudaFree(dt->d_dlo24); cudaFree(dt->d_ntiles);
+  cudaFree(dt->d_recs); cudaFree(dt->d_caps); cudaFree(dt->d_ftab); cudaFree(dt->d_dres32); cudaFree(dt->d_ntiles);
   cudaFree(dt->d_comp8); cudaFree(dt->d_root8); cudaFree(dt->d_rootb); cudaFree(dt->d_tmp); cudaFree(dt->d_pos32);
   cudaFree(dt->d_site32); cudaFree(dt->d_hist); cudaFree(dt->d_base); cudaFree(dt->d_total); cudaFree(dt->d_r0);
   cudaFree(dt->d_seg); cudaFree(dt->d_tiles); cudaFree(dt->d_tile_begin);
@@ -1088,7 +1081,7 @@ void duo_free(elx_handle *h) {
   h->duo = nullptr;
 }
 
-int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24) {
+int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dres32) {
   DuoTables *dt = static_cast<DuoTables *>(h->duo);
   if (!dt) return fail(h, ELX_E_INVALID, "elx_duo_get: this handle has no duo tables");
   if (recs)
@@ -1097,8 +1090,8 @@ int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24) {
   if (de32)
     DUO_CUDA(h, cudaMemcpy2DAsync(de32, row_bytes, dt->d_ftab + 32, (size_t)dt->stage_bytes, row_bytes, (size_t)dt->G * h->C,
                                   cudaMemcpyDeviceToHost, h->stream));
-  if (dlo24)
-    DUO_CUDA(h, cudaMemcpyAsync(dlo24, dt->d_dlo24, (size_t)dt->G * h->C * row_bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (dres32)
+    DUO_CUDA(h, cudaMemcpyAsync(dres32, dt->d_dres32, (size_t)dt->G * h->C * row_bytes, cudaMemcpyDeviceToHost, h->stream));
   DUO_CUDA(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1254,7 +1247,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   memset(&fa, 0, sizeof fa);
   fa.s = a;
   fa.s.n_slots = dt->prog.n_slots;
-  fa.G = dt->G; fa.recs = dt->d_recs; fa.ftab = dt->d_ftab; fa.dlo24 = dt->d_dlo24;
+  fa.G = dt->G; fa.recs = dt->d_recs; fa.ftab = dt->d_ftab; fa.dres32 = dt->d_dres32;
   // the CTA class of this call: 512 threads whenever the tile fits (measured 2 % faster than the 640 class at the same tile)
   const bool cls512 = dt->threads == 640 && dt->nstage512 >= 2 && tile_groups <= 512;
   const int cls = cls512 ? 512 : dt->threads;

@@ -85,17 +85,64 @@ __host__ __device__ __forceinline__ uint32_t draw24_from_words(const uint32_t *X
   return (X[w0] & 0xffu) | ((X[w0 + 1] & 0xffu) << 8) | ((X[w0 + 2] & 0xffu) << 16);
 }
 
-// mwc-random `categorical`: the first i with cv[i] >= cv[K-1] * u.  cv is a running sum of non-negative weights, hence
-// non-decreasing: for long vectors (C60: 60 components) a binary search finds the same index in 6 steps instead of 30.
-// One alias row of KP columns by ONE WARP (quad rows: KP = 256, duo rows: KP = 512): integer masses m_o = round(p_o / sum * 2^48)
-// (residual to the largest), Vose pairing, column capacity CAP = 2^48 / KP.  The order-sensitive parts -- the sum, the two
-// stacks, the pairing -- run on lane 0 over shared-memory arrays exactly as a single thread would (same tables bit for bit);
-// loads, masses, the arg-max and the stores are spread over the lanes.  sm: KP doubles + 2 KP int64 + 3 KP int16 per warp.
-// On return q[j] / alias[j] hold the thresholds and aliases of the columns (q[j] == CAP: a full column).
+// ---- two-level alias rows (quad / duo mode) ------------------------------------------------------------------------
+// A row of KP outcomes with integer masses P_o = round(p_o / sum * 2^W) (residual to the largest; sum = 2^W) is sampled EXACTLY
+// by a draw x = [t : TB][j : log2 KP] without any tie between draw and threshold:
+//   t != 0 (main level): the 2^TB - 1 values of t times the KP columns are cells of probability 2^-24 each (TB + log2 KP = 24);
+//     masses M_o = floor(P_o / 2^(W-24)), reduced at the largest outcome so that sum M = (2^TB - 1) KP; Vose pairing with column
+//     capacity 2^TB - 1 gives column j an acceptance count A_j and an alias.  The kernels compare  [t][j] < [q][alias]  as ONE
+//     integer (outcome = that field of min(draw, entry)), which accepts t < q, and t == q when j < alias: the stored q is
+//     A_j + 1 - [j < alias]  (0 when A_j = 0; a full column is its own alias with q = 2^TB - 1);
+//   t == 0 (escape level, probability 2^-TB): the residual masses R_o = P_o - M_o 2^(W-24) >= 0 (sum = KP 2^(W-24) = 2^32) in a
+//     second alias row of column capacity 2^(W-24): entry [thr : W-24][alias : log2 KP], sampled with 32 fresh bits
+//     u = [tr : W-24][jr : log2 KP]:  tr < thr -> jr, else alias.
+// Total: M_o 2^-24 + R_o 2^-W = P_o 2^-W.  (Round 1 compared t with a 16-bit threshold prefix and settled the ties t == q_hi
+// with 24 more bits: the tie detector cost one XOR per draw in the hot loops; the escape test needs the draw alone.)
+// vose_exact: single-thread Vose pairing over integer masses m[0..KP) with sum = CAP * KP; q[j] = acceptance units of column j
+// (q[j] == CAP and alias[j] == j: a full column).  m is consumed.
 template <int KP>
-__device__ __forceinline__ void alias_row_warp(const double *__restrict__ p, double *v, int64_t *m, int64_t *q, int16_t *alias,
-                                               int16_t *small, int16_t *large, int lane) {
-  constexpr int64_t CAP = ((int64_t)1 << 48) / KP;
+__device__ __forceinline__ void vose_exact(int64_t *m, const int64_t CAP, int64_t *q, int16_t *alias, int16_t *small, int16_t *large) {
+  int ns = 0, nl = 0;
+  for (int j = KP - 1; j >= 0; --j) {
+    alias[j] = (int16_t)j;
+    q[j] = CAP;
+    if (m[j] < CAP) small[ns++] = (int16_t)j; else large[nl++] = (int16_t)j;
+  }
+  while (ns > 0 && nl > 0) {
+    const int s_ = small[--ns], l_ = large[--nl];
+    q[s_] = m[s_];
+    alias[s_] = (int16_t)l_;
+    m[l_] -= CAP - m[s_];
+    if (m[l_] < CAP) small[ns++] = (int16_t)l_; else large[nl++] = (int16_t)l_;
+  }
+}
+// main-level entry of column j: [q : TB][alias : AB][0 : 32 - TB - AB]
+template <int TB, int AB>
+__device__ __forceinline__ uint32_t alias2_main_entry(int j, int64_t A, int al) {
+  constexpr int64_t CAPM = ((int64_t)1 << TB) - 1;
+  int64_t qq;
+  if (al == j || A >= CAPM) { qq = CAPM; al = j; }  // a full column: every t gives j
+  else if (A <= 0) qq = 0;
+  else qq = A + 1 - (j < al ? 1 : 0);
+  return (uint32_t)((qq << (32 - TB)) | ((int64_t)al << (32 - TB - AB)));
+}
+// escape-level entry of column j: [thr : 32 - AB][alias : AB]
+template <int AB>
+__device__ __forceinline__ uint32_t alias2_escape_entry(int j, int64_t thr, int al) {
+  constexpr int64_t CAPR = (int64_t)1 << (32 - AB);
+  if (al == j || thr >= CAPR) { thr = CAPR - 1; al = j; }
+  return (uint32_t)((thr << AB) | (int64_t)al);
+}
+// One two-level row by ONE WARP (quad rows: KP = 256, TB = 16, W = 48).  The order-sensitive parts -- the sum, the pairings --
+// run on lane 0 over shared-memory arrays exactly as a single thread would; loads, masses, the arg-max and the stores are spread
+// over the lanes.  sm: 3 KP int64 (v doubles as the residual masses) + 3 KP int16 per warp.
+template <int KP, int TB, int W>
+__device__ __forceinline__ void alias2_row_warp(const double *__restrict__ p, double *v, int64_t *m, int64_t *q, int16_t *alias,
+                                                int16_t *small, int16_t *large, int lane, uint32_t *__restrict__ e32,
+                                                uint32_t *__restrict__ res32) {
+  constexpr int AB = 24 - TB;   // log2 KP
+  constexpr int SH = W - 24;    // log2 of the main level's mass unit
+  static_assert((1 << AB) == KP, "TB + log2 KP must be 24");
   for (int j = lane; j < KP; j += 32) { const double x = p[j]; v[j] = x > 0.0 ? x : 0.0; }
   __syncwarp();
   double sum = 0.0;
@@ -105,7 +152,7 @@ __device__ __forceinline__ void alias_row_warp(const double *__restrict__ p, dou
   int64_t tot = 0, best = -1;
   int big = 0;
   for (int j = lane; j < KP; j += 32) {
-    const int64_t mj = sum > 0.0 ? (int64_t)llrint(v[j] / sum * 0x1p48) : (j == 0 ? ((int64_t)1 << 48) : 0);
+    const int64_t mj = sum > 0.0 ? (int64_t)llrint(v[j] / sum * (double)((int64_t)1 << W)) : (j == 0 ? ((int64_t)1 << W) : 0);
     m[j] = mj;
     tot += mj;
     if (mj > best) { best = mj; big = j; }  // (ascending j per lane: the first maximum)
@@ -117,25 +164,36 @@ __device__ __forceinline__ void alias_row_warp(const double *__restrict__ p, dou
     if (ob > best || (ob == best && oj < big)) { best = ob; big = oj; }
   }
   __syncwarp();
-  if (lane == 0) {
-    m[big] += ((int64_t)1 << 48) - tot;
-    int ns = 0, nl = 0;
-    for (int j = KP - 1; j >= 0; --j) {
-      alias[j] = (int16_t)j;
-      q[j] = CAP;
-      if (m[j] < CAP) small[ns++] = (int16_t)j; else large[nl++] = (int16_t)j;
-    }
-    while (ns > 0 && nl > 0) {
-      const int s_ = small[--ns], l_ = large[--nl];
-      q[s_] = m[s_];
-      alias[s_] = (int16_t)l_;
-      m[l_] -= CAP - m[s_];
-      if (m[l_] < CAP) small[ns++] = (int16_t)l_; else large[nl++] = (int16_t)l_;
-    }
+  if (lane == 0) m[big] += ((int64_t)1 << W) - tot;
+  __syncwarp();
+  // split into the two levels
+  int64_t *R = reinterpret_cast<int64_t *>(v);
+  int64_t msum = 0;
+  for (int j = lane; j < KP; j += 32) {
+    const int64_t P = m[j], M = P >> SH;
+    R[j] = P - (M << SH);
+    m[j] = M;
+    msum += M;
   }
+  for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+  __syncwarp();
+  if (lane == 0) {
+    const int64_t excess = msum - (((int64_t)1 << TB) - 1) * KP;  // 1..KP, and the largest outcome holds at least 2^24 / KP cells
+    m[big] -= excess;
+    R[big] += excess << SH;
+    vose_exact<KP>(m, ((int64_t)1 << TB) - 1, q, alias, small, large);
+  }
+  __syncwarp();
+  for (int j = lane; j < KP; j += 32) e32[j] = alias2_main_entry<TB, AB>(j, q[j], alias[j]);
+  __syncwarp();
+  if (lane == 0) vose_exact<KP>(R, (int64_t)1 << SH, q, alias, small, large);
+  __syncwarp();
+  for (int j = lane; j < KP; j += 32) res32[j] = alias2_escape_entry<AB>(j, q[j], alias[j]);
   __syncwarp();
 }
 
+// mwc-random `categorical`: the first i with cv[i] >= cv[K-1] * u.  cv is a running sum of non-negative weights, hence
+// non-decreasing: for long vectors (C60: 60 components) a binary search finds the same index in 6 steps instead of 30.
 __device__ __forceinline__ int cat_cum(const double *__restrict__ cv, int K, double u) {
   double p = __dmul_rn(cv[K - 1], u);
   if (K > 16) {

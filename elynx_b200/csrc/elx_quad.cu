@@ -13,12 +13,13 @@
 //   record g = (out[0..3] | r), site s, component c, state i of r.  A draw is 24 bits: the 16 sites of a group s >> 4 share
 //   three Philox calls, 12 words X[0..11] = philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2;  d = s & 15:
 //     x24 = X[3(d>>2) + (d&3)] >> 8 for d&3 < 3, else the low bytes of X[3(d>>2)], X[3(d>>2)+1], X[3(d>>2)+2];  x24 = [t : 16][j : 8]
-//     e = qe32[g][c][i][j] = [q_hi : 16][alias : 8][0 : 8];  t < q_hi -> o = j;  t > q_hi -> o = alias;
-//     tie -> (philox(s lo, s hi, out[0], TAG_REFINE).x >> 8) < qlo24[g][c][i][j] ? j : alias
+//     t != 0:  e = qe32[g][c][i][j] = [q : 16][alias : 8][0 : 8];  o = x24 < (e >> 8) ? j : alias   (one 24-bit compare)
+//     t == 0 (escape, 2^-16 per draw):  u = philox(s lo, s hi, out[0], TAG_REFINE).x = [tr : 24][jr : 8];
+//              er = qres32[g][c][i][jr] = [thr : 24][alias : 8];  o = tr < thr ? jr : alias
 //     state(out[k]) = (o >> 2k) & 3
-// The joint rows carry integer masses round(p / sum * 2^48) (Vose pairing in exact integer arithmetic, column capacity
-// 2^40 = 16 high + 24 low threshold bits); ties come at 2^-16 per draw and are settled exactly.  24-bit draws instead of
-// 32-bit ones cut the Philox work -- 60 % of the hot loop -- by a quarter.
+// The joint rows carry integer masses round(p / sum * 2^48), split into a main level of 2^-24 cells and an exact residual
+// (two-level alias rows, elx_ptx.cuh): no draw ever ties with a threshold, and the escape test needs the draw alone.  24-bit
+// draws instead of 32-bit ones cut the Philox work -- 60 % of the hot loop -- by a quarter.
 //
 // Kernels: k1_quad_joint, k1_alias_quad (tables), k2_quad_generic (tables through L1/L2; the cross-check),
 // k2_quad_tiled (the hot kernel: one record + its 4 KB x C joint rows per stage, streamed through shared memory by a
@@ -66,7 +67,7 @@ struct QuadTables {
   QuadCapDev *d_caps = nullptr;
   double *d_joint = nullptr;    // [G][C][4][256]
   uint32_t *d_qe32 = nullptr;   // [G][C][4][256]
-  uint32_t *d_qlo24 = nullptr;  // [G][C][4][256]
+  uint32_t *d_qres32 = nullptr;  // [G][C][4][256]
   uint8_t *d_ftab = nullptr;    // [G] x (32 B record + tb bytes of rows)
   int tiled = 0, threads = 0, minb = 1, nstage = 0, tb = 0, stage_bytes = 0;  // threads: the CTA class (MAXT)
   size_t smem = 0;
@@ -77,7 +78,7 @@ struct QuadArgs {
   int G;
   const QuadRecDev *recs;
   const uint32_t *qe32;
-  const uint32_t *qlo24;
+  const uint32_t *qres32;
   const uint8_t *ftab;
   int tb, stage_bytes, nstage, slot_stride;
   uint32_t entry_bytes;  // 4 (see entry_addr)
@@ -130,14 +131,13 @@ __global__ void k1_quad_joint(int G, int C, int K, const QuadCapDev *__restrict_
   joint[idx] = top;
 }
 
-// Alias rows of 256 columns: integer masses m_o = round(p_o / sum * 2^48) (residual to the largest), Vose pairing, column
-// capacity 2^40; entry = [threshold bits 39..24 : 16][alias : 8][0 : 8], qlo24 = threshold bits 23..0.  One WARP per row
-// (alias_row_warp, elx_ptx.cuh; one thread per row with 5.5 KB of local arrays took 0.36 ms for cfg2's 5808 rows).
+// Two-level alias rows of 256 columns (elx_ptx.cuh alias2_row_warp): integer masses round(p_o / sum * 2^48) (residual to the
+// largest); main entry = [q : 16][alias : 8][0 : 8], escape entry qres32 = [thr : 24][alias : 8].  One WARP per row (one
+// thread per row with 5.5 KB of local arrays took 0.36 ms for cfg2's 5808 rows).
 constexpr int ALIAS_WARPS = 4;
 __global__ void __launch_bounds__(ALIAS_WARPS * 32) k1_alias_quad(int64_t rows, const double *__restrict__ joint, uint32_t *__restrict__ e32,
-                                                              uint32_t *__restrict__ qlo24) {
+                                                              uint32_t *__restrict__ qres32) {
   constexpr int KP = QUAD_COLS;
-  constexpr int64_t CAP = (int64_t)1 << 40;
   extern __shared__ __align__(16) uint8_t sm_alias[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * ALIAS_WARPS + w;
@@ -146,14 +146,7 @@ __global__ void __launch_bounds__(ALIAS_WARPS * 32) k1_alias_quad(int64_t rows, 
   double *v = reinterpret_cast<double *>(base);
   int64_t *m = reinterpret_cast<int64_t *>(base + KP * 8), *q = reinterpret_cast<int64_t *>(base + KP * 16);
   int16_t *alias = reinterpret_cast<int16_t *>(base + KP * 24), *small = alias + KP, *large = alias + 2 * KP;
-  alias_row_warp<KP>(joint + r * KP, v, m, q, alias, small, large, lane);
-  for (int j = lane; j < KP; j += 32) {
-    int64_t qq = q[j];
-    int al = alias[j];
-    if (qq >= CAP) { qq = CAP - 1; al = j; }  // a full column: always accept (alias = self)
-    e32[r * KP + j] = (uint32_t)(((qq >> 24) << 16) | ((int64_t)al << 8));
-    qlo24[r * KP + j] = (uint32_t)(qq & 0xffffff);
-  }
+  alias2_row_warp<KP, 16, 48>(joint + r * KP, v, m, q, alias, small, large, lane, e32 + r * KP, qres32 + r * KP);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -194,13 +187,14 @@ __global__ void k2_quad_generic(QuadArgs fa) {
     const uint32_t x24 = quad_draw24<ROUNDS>(s, h0.x, key);
     const uint32_t j = x24 & 0xffu, t = x24 >> 8;
     const int64_t idx = ((((int64_t)g * a.C + c) * 4 + slot[src]) << 8) | j;
-    const uint32_t e = __ldg(fa.qe32 + idx), qh = e >> 16, al = (e >> 8) & 0xffu;
     uint32_t o;
-    if (t < qh) o = j;
-    else if (t > qh) o = al;
-    else {
+    if (t != 0u) {
+      const uint32_t e = __ldg(fa.qe32 + idx);
+      o = x24 < (e >> 8) ? j : ((e >> 8) & 0xffu);
+    } else {  // escape level
       const uint4 z = philox4x32<ROUNDS>(make_uint4((uint32_t)s, (uint32_t)(s >> 32), h0.x, TAG_REFINE), key);
-      o = (z.x >> 8) < __ldg(fa.qlo24 + idx) ? j : al;
+      const uint32_t er = __ldg(fa.qres32 + (idx & ~(int64_t)255) + (z.x & 0xffu));
+      o = (z.x >> 8) < (er >> 8) ? (z.x & 0xffu) : (er & 0xffu);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -306,25 +300,24 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
 #endif
         const uint32_t e = lds_u32(entry_addr(idx, fa.entry_bytes, tbl));
         c[i] = min(w, e);
-        t[i] = w ^ e;
+        t[i] = w;
       }
       m = min(min(m, t[0]), min(t[1], min(t[2], t[3])));
       W[q] = __byte_perm(__byte_perm(c[0], c[1], 0x0051u), __byte_perm(c[2], c[3], 0x0051u), 0x5410u);
     }
     if (m < 0x10000u) {
-      // exact path (2^-16 per draw): some draw hit its threshold's 16 high bits; settle the tied draws with 24 more
-      // random bits.  Unrolled with static register names: no calls, no dynamically indexed arrays (elx_fast.cu).
+      // escape level (2^-16 per draw): some draw has t == 0; its outcome comes from the row's residual masses with 32 fresh
+      // bits.  Unrolled with static register names: no calls, no dynamically indexed arrays (elx_fast.cu).
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
         const uint32_t w = ELX_DRAW24(X, d);
-        const uint32_t row = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
-        const uint32_t j = (w >> 8) & 0xffu, idx = (row << 8) | j;
-        const uint32_t e = lds_u32(tbl + idx * 4u);
-        if ((w ^ e) < 0x10000u) {
+        if (w < 0x10000u) {
+          const uint32_t row = (Rq[d >> 2] >> (8 * (d & 3))) & 0xffu;
           const uint64_t sg = (uint64_t)sbase + (uint64_t)d;
           const uint4 z = philox4x32_rk<ROUNDS>(make_uint4((uint32_t)sg, (uint32_t)(sg >> 32), node0, TAG_REFINE), fa.rk);
-          const uint32_t ql = __ldg(fa.qlo24 + ((((int64_t)g * a.C * 4 + row) << 8) | j));
-          const uint32_t o = (z.x >> 8) < ql ? j : ((e >> 8) & 0xffu);
+          const uint32_t jr = z.x & 0xffu;
+          const uint32_t er = __ldg(fa.qres32 + ((((int64_t)g * a.C * 4 + row) << 8) | jr));
+          const uint32_t o = (z.x >> 8) < (er >> 8) ? jr : (er & 0xffu);
           W[d >> 2] = (W[d >> 2] & ~(0xffu << (8 * (d & 3)))) | (o << (8 * (d & 3)));
         }
       }
@@ -540,7 +533,7 @@ int quad_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row) {
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_caps, sizeof(QuadCapDev) * (size_t)G));
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_joint, sizeof(double) * ents));
   QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qe32, sizeof(uint32_t) * ents));
-  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qlo24, sizeof(uint32_t) * ents));
+  QUAD_CUDA(h, cudaMalloc((void **)&qt->d_qres32, sizeof(uint32_t) * ents));
   QUAD_CUDA(h, cudaMemcpy(qt->d_recs, dev.data(), sizeof(QuadRecDev) * (size_t)G, cudaMemcpyHostToDevice));
   QUAD_CUDA(h, cudaMemcpy(qt->d_caps, caps.data(), sizeof(QuadCapDev) * (size_t)G, cudaMemcpyHostToDevice));
   if (qt->tiled) QUAD_CUDA(h, cudaMalloc((void **)&qt->d_ftab, (size_t)G * qt->stage_bytes));
@@ -555,7 +548,7 @@ int quad_tables_build(elx_handle *h) {
   h->launches++;
   QUAD_CUDA(h, cudaGetLastError());
   const int64_t rows = ents / QUAD_COLS;
-  k1_alias_quad<<<(unsigned)((rows + ALIAS_WARPS - 1) / ALIAS_WARPS), ALIAS_WARPS * 32, (size_t)ALIAS_WARPS * QUAD_COLS * 30, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qlo24);
+  k1_alias_quad<<<(unsigned)((rows + ALIAS_WARPS - 1) / ALIAS_WARPS), ALIAS_WARPS * 32, (size_t)ALIAS_WARPS * QUAD_COLS * 30, h->stream>>>(rows, qt->d_joint, qt->d_qe32, qt->d_qres32);
   h->launches++;
   QUAD_CUDA(h, cudaGetLastError());
   if (qt->tiled) {
@@ -570,19 +563,19 @@ int quad_tables_build(elx_handle *h) {
 void quad_free(elx_handle *h) {
   QuadTables *qt = static_cast<QuadTables *>(h->quad);
   if (!qt) return;
-  cudaFree(qt->d_recs); cudaFree(qt->d_caps); cudaFree(qt->d_joint); cudaFree(qt->d_qe32); cudaFree(qt->d_qlo24); cudaFree(qt->d_ftab);
+  cudaFree(qt->d_recs); cudaFree(qt->d_caps); cudaFree(qt->d_joint); cudaFree(qt->d_qe32); cudaFree(qt->d_qres32); cudaFree(qt->d_ftab);
   delete qt;
   h->quad = nullptr;
 }
 
-int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24) {
+int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qres32) {
   QuadTables *qt = static_cast<QuadTables *>(h->quad);
   if (!qt) return fail(h, ELX_E_INVALID, "elx_quad_get: this handle has no quad tables");
   if (recs)
     for (int g = 0; g < qt->G; ++g) quad_rec_to_ints(qt->prog.recs[g], recs + (size_t)g * ELX_QUAD_REC_INTS);
   const size_t n = (size_t)qt->G * h->C * 4 * QUAD_COLS;
   if (qe32) QUAD_CUDA(h, cudaMemcpyAsync(qe32, qt->d_qe32, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-  if (qlo24) QUAD_CUDA(h, cudaMemcpyAsync(qlo24, qt->d_qlo24, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (qres32) QUAD_CUDA(h, cudaMemcpyAsync(qres32, qt->d_qres32, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   QUAD_CUDA(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -611,7 +604,7 @@ int quad_simulate(elx_handle *h, SimArgs &a, int *used) {
   QuadArgs fa;
   fa.s = a;
   fa.s.n_slots = qt->prog.n_slots;
-  fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qlo24 = qt->d_qlo24; fa.ftab = qt->d_ftab;
+  fa.G = qt->G; fa.recs = qt->d_recs; fa.qe32 = qt->d_qe32; fa.qres32 = qt->d_qres32; fa.ftab = qt->d_ftab;
   fa.tb = qt->tb; fa.stage_bytes = qt->stage_bytes; fa.nstage = qt->nstage; fa.slot_stride = qt->threads * 16;
   fa.rk = philox_round_keys(a.seed);
   fa.entry_bytes = 4;

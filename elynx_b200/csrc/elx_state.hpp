@@ -123,7 +123,7 @@ int quad_tables_build(elx_handle *h);
 void quad_free(elx_handle *h);
 int quad_groups(const elx_handle *h);
 void quad_rec_to_ints(const QuadRec &r, int32_t *o);  // ELX_QUAD_REC_INTS values, the layout include/elynx_b200.h documents
-int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
+int quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qres32);
 int quad_simulate(elx_handle *h, SimArgs &a, int *used);
 
 // elx_duo.cu: duo mode (models with 5..22 states unless ELX_FLAG_SINGLE_DRAWS; leaves-only calls); leaves h->duo null when
@@ -132,7 +132,7 @@ int duo_create(elx_handle *h, const int32_t *parent, const int32_t *leaf_row);
 int duo_tables_build(elx_handle *h);
 void duo_free(elx_handle *h);
 int duo_groups(const elx_handle *h);
-int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24);
+int duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dres32);
 int duo_simulate(elx_handle *h, SimArgs &a, int *used);
 int64_t duo_batch_sites(const elx_handle *h);  // sites per batch of a host-buffer call (whole superblocks), 0: no duo tables
 

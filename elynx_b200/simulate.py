@@ -147,28 +147,28 @@ class Simulator:
         return node_a, node_b, pe16, pqlo
 
     def quad_tables(self):
-        """(recs[G][ELX_QUAD_REC_INTS], qe32[G][C][4][256], qlo24[G][C][4][256]) of the quad-mode records, or None."""
+        """(recs[G][ELX_QUAD_REC_INTS], qe32[G][C][4][256], qres32[G][C][4][256]) of the quad-mode records, or None."""
         g = self.quad_groups
         if g == 0:
             return None
         recs = np.empty((g, L.ELX_QUAD_REC_INTS), dtype=np.int32)
         shape = (g, self.n_components, 4, 256)
         qe32 = np.empty(shape, dtype=np.uint32)
-        qlo24 = np.empty(shape, dtype=np.uint32)
-        L.check(L.lib().elx_quad_get(self._h, _ptr(recs), _ptr(qe32), _ptr(qlo24)), self._h)
-        return recs, qe32, qlo24
+        qres32 = np.empty(shape, dtype=np.uint32)
+        L.check(L.lib().elx_quad_get(self._h, _ptr(recs), _ptr(qe32), _ptr(qres32)), self._h)
+        return recs, qe32, qres32
 
     # -- simulation ----------------------------------------------------------------------------
     def duo_tables(self):
-        """(recs[G][ELX_QUAD_REC_INTS], de32[G][C][K][512], dlo24[G][C][K][512]) of the duo-mode records, or None."""
+        """(recs[G][ELX_QUAD_REC_INTS], de32[G][C][K][512], dres32[G][C][K][512]) of the duo-mode records, or None."""
         g = self.duo_groups
         if g == 0:
             return None
         recs = np.empty((g, L.ELX_QUAD_REC_INTS), dtype=np.int32)
         de32 = np.empty((g, self.n_components, self.n_states, 512), dtype=np.uint32)
-        dlo24 = np.empty_like(de32)
-        L.check(L.lib().elx_duo_get(self._h, _ptr(recs), _ptr(de32), _ptr(dlo24)), self._h)
-        return recs, de32, dlo24
+        dres32 = np.empty_like(de32)
+        L.check(L.lib().elx_duo_get(self._h, _ptr(recs), _ptr(de32), _ptr(dres32)), self._h)
+        return recs, de32, dres32
 
     def simulate(self, seed: int, nsites: int, site0: int = 0, want_comps: bool = False, keep_internal: bool = False):
         """(leaves[T][nsites] uint8, comps[nsites] int32 | None, internal[N][nsites] uint8 | None) in host memory."""

@@ -170,12 +170,14 @@ int elx_pair_get(elx_handle *h, int32_t *node_a, int32_t *node_b, uint16_t *pe16
  * [9..12] slot receiving out[k] (-1: none), [13] slot holding r, [14] number of cap nodes n, [15] 0, then n triples
  * [16+3i..] = (node, index of its parent in this list or -1 for r, frontier position or -1 for a summed-out node), parents
  * first.  elx_quad_groups: number of records (0: no quad tables); elx_quad_get: the records in walk order and their alias
- * rows qe32 / qlo24 [G][C][4][256] (uint32: [threshold bits 39..24 : 16][alias : 8][0 : 8] / threshold bits 23..0).  A draw is
- * 24 bits ([t : 16][column : 8], three Philox calls per 16 sites); t == threshold high bits (2^-16) is settled with 24 more bits.
+ * rows qe32 / qres32 [G][C][4][256] (uint32).  A draw is 24 bits, x24 = [t : 16][column j : 8] (three Philox calls per 16 sites).
+ * Two-level rows, exact for the integer masses round(p 2^48) without any draw / threshold tie: t != 0 -> main entry qe32[..][j] =
+ * [q : 16][alias : 8][0 : 8], outcome = x24 < (entry >> 8) ? j : alias (cells of 2^-24); t == 0 (2^-16) -> 32 fresh bits
+ * u = [tr : 24][jr : 8] against the escape entry qres32[..][jr] = [thr : 24][alias : 8] (the residual masses): tr < thr ? jr : alias.
  * elx_tree_quad_walk_info: host-only, the records of a tree (recs may be NULL; it must hold ELX_QUAD_REC_INTS * n_nodes). */
 #define ELX_QUAD_REC_INTS 52
 int32_t elx_quad_groups(const elx_handle *h);
-int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qlo24);
+int elx_quad_get(elx_handle *h, int32_t *recs, uint32_t *qe32, uint32_t *qres32);
 int elx_tree_quad_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
 /* the same cut with at most TWO frontier nodes per cap: the records of duo mode (below) */
 int elx_tree_duo_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_slots, int32_t *recs);
@@ -186,10 +188,11 @@ int elx_tree_duo_walk_info(const elx_tree *tree, int32_t *n_records, int32_t *n_
  * component, so every call first buckets its sites by component (stable inside superblocks of 2^20 .. 2^24 sites); the rank of a site
  * among the sites of its component and superblock selects its 16-site Philox group (see elx_duo.cu for the specification).
  * elx_duo_groups: number of records (0: the handle draws node by node); elx_duo_get: the records (ELX_QUAD_REC_INTS layout,
- * frontier positions 0..1) and their alias rows de32 / dlo24 [G][C][K][512] (uint32: [threshold bits 38..24 : 15][alias : 9][0 : 8]
- * / threshold bits 23..0).  A draw is 24 bits ([t : 15][column : 9]); t == threshold high bits (2^-15) is settled with 24 more. */
+ * frontier positions 0..1) and their two-level alias rows de32 / dres32 [G][C][K][512] (uint32): x24 = [t : 15][column j : 9];
+ * t != 0 -> de32[..][j] = [q : 15][alias : 9][0 : 8], outcome = x24 < (entry >> 8) ? j : alias; t == 0 (2^-15) -> u =
+ * [tr : 23][jr : 9] against dres32[..][jr] = [thr : 23][alias : 9]; integer masses round(p 2^47). */
 int32_t elx_duo_groups(const elx_handle *h);
-int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dlo24);
+int elx_duo_get(elx_handle *h, int32_t *recs, uint32_t *de32, uint32_t *dres32);
 
 /* ---- simulateAndFlatten[MixtureModel]Par ------------------------------------------------------
  * Simulates sites [site0, site0 + nsites) of the alignment defined by (handle, seed, draw mode); the result is a

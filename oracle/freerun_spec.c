@@ -26,8 +26,10 @@
  * A draw is 24 bits; the 16 sites of a group s >> 4 share three Philox calls:
  *   B[0..47] = little-endian bytes of philox(s>>4 lo, s>>4 hi, out[0], 4 * call), call = 0, 1, 2;  d = s & 15
  *   X[0..11] = the 12 little-endian words of B; x24 = X[3(d>>2) + (d&3)] >> 8 for d&3 < 3, else the low bytes of X[3(d>>2)], X[3(d>>2)+1],
- *   X[3(d>>2)+2] (first = least significant);  j = x24 & 255; t = x24 >> 8; e = qe32[g][c][state of r][j] = [q_hi : 16][alias : 8][0 : 8]
- *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < qlo24[g][c][state of r][j] ? j : alias
+ *   X[3(d>>2)+2] (first = least significant);  j = x24 & 255; t = x24 >> 8
+ *   t != 0:  e = qe32[g][c][state of r][j] = [q : 16][alias : 8][0 : 8];  o = x24 < (e >> 8) ? j : alias     (two-level alias rows:
+ *   t == 0:  u = philox(s lo, s hi, out[0], 1).x0;  er = qres32[g][c][state of r][u & 255] = [thr : 24][alias : 8];     no ties)
+ *            o = (u >> 8) < thr ? u & 255 : alias
  * Records come in walk order (r is the root or a frontier node of an earlier record); recs = 52 int32 per record in the
  * layout include/elynx_b200.h documents.
  *
@@ -36,8 +38,10 @@
  * component inside superblocks of 2^SB sites (SB = 20 for C <= 16, 22 for C <= 64, else 24): B = s >> SB, rank = number of earlier sites of B with the same component,
  * q = rank >> 4, d = rank & 15; the 16 sites of a group share three Philox calls:
  *   Z[0..47] = little-endian bytes of philox(q | c << 20, B lo, out[0], (B hi << 8) | 4 * call), call = 0, 1, 2
- *   x24 = draw d of Z as in quad mode;  j = x24 & 511; t = x24 >> 9; e = de32[g][c][state of r][j] = [q_hi : 15][alias : 9][0 : 8]
- *   t < q_hi -> o = j ;  t > q_hi -> o = alias ;  tie -> (philox(s lo, s hi, out[0], 1).x0 >> 8) < dlo24[g][c][state of r][j] ? j : alias
+ *   x24 = draw d of Z as in quad mode;  j = x24 & 511; t = x24 >> 9
+ *   t != 0:  e = de32[g][c][state of r][j] = [q : 15][alias : 9][0 : 8];  o = x24 < (e >> 8) ? j : alias
+ *   t == 0:  u = philox(s lo, s hi, out[0], 1).x0;  er = dres32[g][c][state of r][u & 511] = [thr : 23][alias : 9];
+ *            o = (u >> 9) < thr ? u & 511 : alias
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -182,9 +186,9 @@ static uint32_t draw24(const uint8_t *B, int d) {
 
 #define QUAD_REC_INTS 52
 static int64_t quad_ties = 0;
-int64_t spec_quad_ties(void) { return quad_ties; } /* ties seen by the last spec_freerun_quad call */
+int64_t spec_quad_ties(void) { return quad_ties; } /* escape-level draws (t == 0) seen by the last spec_freerun_quad call */
 int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int32_t *leaf_row, const double *cumw,
-                      const double *cumpi, int G, const int32_t *recs, const uint32_t *qe32, const uint32_t *qlo24, uint64_t seed,
+                      const double *cumpi, int G, const int32_t *recs, const uint32_t *qe32, const uint32_t *qres32, uint64_t seed,
                       int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch, int32_t *comps) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint8_t *st = (uint8_t *)malloc((size_t)N);
@@ -224,13 +228,15 @@ int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int
       uint32_t x24 = draw24(B, d);
       uint32_t j = x24 & 255u, t = x24 >> 8;
       int64_t idx = (((int64_t)g * C + c) * 4 + st[rt]) * 256 + j;
-      uint32_t e = qe32[idx], qh = e >> 16, al = (e >> 8) & 255u, o;
-      if (t < qh) o = j;
-      else if (t > qh) o = al;
-      else {
+      uint32_t o;
+      if (t != 0) {
+        uint32_t e = qe32[idx];
+        o = x24 < (e >> 8) ? j : ((e >> 8) & 255u);
+      } else { /* escape level: the row's residual masses, 32 fresh bits */
         uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)n0, 1};
         philox(rounds, z, k0, k1);
-        o = (z[0] >> 8) < qlo24[idx] ? j : al;
+        uint32_t jr = z[0] & 255u, er = qres32[idx - j + jr];
+        o = (z[0] >> 8) < (er >> 8) ? jr : (er & 255u);
         ++quad_ties;
       }
       for (int k = 0; k < 4; ++k) {
@@ -254,9 +260,9 @@ int spec_freerun_quad(int N, int K, int C, int is_mixture, int rounds, const int
 
 static int duo_sb(int C) { return C <= 16 ? 20 : C <= 64 ? 22 : 24; }
 static int64_t duo_ties = 0;
-int64_t spec_duo_ties(void) { return duo_ties; } /* ties seen by the last spec_freerun_duo call */
+int64_t spec_duo_ties(void) { return duo_ties; } /* escape-level draws (t == 0) seen by the last spec_freerun_duo call */
 int spec_freerun_duo(int N, int K, int C, int is_mixture, int rounds, const int32_t *leaf_row, const double *cumw,
-                     const double *cumpi, int G, const int32_t *recs, const uint32_t *de32, const uint32_t *dlo24, uint64_t seed,
+                     const double *cumpi, int G, const int32_t *recs, const uint32_t *de32, const uint32_t *dres32, uint64_t seed,
                      int64_t site0, int64_t nsites, uint8_t *leaves, int64_t leaves_pitch, int32_t *comps) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint8_t *st = (uint8_t *)malloc((size_t)N);
@@ -304,13 +310,15 @@ int spec_freerun_duo(int N, int K, int C, int is_mixture, int rounds, const int3
       uint32_t x24 = draw24(B, d);
       uint32_t j = x24 & 511u, t = x24 >> 9;
       int64_t idx = (((int64_t)g * C + c) * K + st[rt]) * 512 + j;
-      uint32_t e = de32[idx], qh = e >> 17, al = (e >> 8) & 511u, o;
-      if (t < qh) o = j;
-      else if (t > qh) o = al;
-      else {
+      uint32_t o;
+      if (t != 0) {
+        uint32_t e = de32[idx];
+        o = x24 < (e >> 8) ? j : ((e >> 8) & 511u);
+      } else { /* escape level */
         uint32_t z[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)n0, 1};
         philox(rounds, z, k0, k1);
-        o = (z[0] >> 8) < dlo24[idx] ? j : al;
+        uint32_t jr = z[0] & 511u, er = dres32[idx - j + jr];
+        o = (z[0] >> 9) < (er >> 9) ? jr : (er & 511u);
         ++duo_ties;
       }
       const uint32_t sv[2] = {o % (uint32_t)K, o / (uint32_t)K};

@@ -104,13 +104,13 @@ QUAD_REC_INTS = 52
 
 
 def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites, rounds=10):
-    """Quad mode (K <= 4, leaves only): quad = (recs[G][52], qe32[G][C][4][256], qlo24[G][C][4][256]) in walk order."""
+    """Quad mode (K <= 4, leaves only): quad = (recs[G][52], qe32[G][C][4][256], qres32[G][C][4][256]) in walk order."""
     leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
     recs = np.ascontiguousarray(quad[0], dtype=np.int32)
     qe32 = np.ascontiguousarray(quad[1], dtype=np.uint32)
-    qlo24 = np.ascontiguousarray(quad[2], dtype=np.uint32)
+    qres32 = np.ascontiguousarray(quad[2], dtype=np.uint32)
     g, c, four, cols = qe32.shape
-    assert four == 4 and cols == 256 and qlo24.shape == qe32.shape and recs.shape == (g, QUAD_REC_INTS)
+    assert four == 4 and cols == 256 and qres32.shape == qe32.shape and recs.shape == (g, QUAD_REC_INTS)
     n = len(leaf_row)
     k = np.asarray(ds).reshape(c, -1).shape[1]
     cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
@@ -120,7 +120,7 @@ def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites
     comps = np.zeros(max(nsites, 1), dtype=np.int32)
     vp = C.c_void_p
     rc = lib().spec_freerun_quad(n, k, c, int(bool(is_mixture)), rounds, vp(leaf_row.ctypes.data), vp(cumw.ctypes.data),
-                                 vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(qe32.ctypes.data), vp(qlo24.ctypes.data),
+                                 vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(qe32.ctypes.data), vp(qres32.ctypes.data),
                                  C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0), C.c_int64(nsites), vp(leaves.ctypes.data),
                                  C.c_int64(max(nsites, 1)), vp(comps.ctypes.data))
     if rc:
@@ -129,18 +129,18 @@ def freerun_quad(is_mixture, parent, leaf_row, ws, ds, quad, seed, site0, nsites
 
 
 def quad_ties():
-    """Number of tied draws the last freerun_quad call had to refine."""
+    """Number of escape-level draws (t == 0) the last freerun_quad call took."""
     return int(lib().spec_quad_ties())
 
 
 def freerun_duo(is_mixture, parent, leaf_row, ws, ds, duo, seed, site0, nsites, rounds=10):
-    """Duo mode (5 <= K <= 22, leaves only): duo = (recs[G][52], de32[G][C][K][512], dlo24[G][C][K][512]) in walk order."""
+    """Duo mode (5 <= K <= 22, leaves only): duo = (recs[G][52], de32[G][C][K][512], dres32[G][C][K][512]) in walk order."""
     leaf_row = np.ascontiguousarray(leaf_row, dtype=np.int32)
     recs = np.ascontiguousarray(duo[0], dtype=np.int32)
     de32 = np.ascontiguousarray(duo[1], dtype=np.uint32)
-    dlo24 = np.ascontiguousarray(duo[2], dtype=np.uint32)
+    dres32 = np.ascontiguousarray(duo[2], dtype=np.uint32)
     g, c, k, cols = de32.shape
-    assert cols == 512 and dlo24.shape == de32.shape and recs.shape == (g, QUAD_REC_INTS)
+    assert cols == 512 and dres32.shape == de32.shape and recs.shape == (g, QUAD_REC_INTS)
     n = len(leaf_row)
     assert np.asarray(ds).reshape(c, -1).shape[1] == k
     cumw = np.cumsum(np.asarray(ws, dtype=np.float64)) if is_mixture else np.ones(1)
@@ -150,7 +150,7 @@ def freerun_duo(is_mixture, parent, leaf_row, ws, ds, duo, seed, site0, nsites, 
     comps = np.zeros(max(nsites, 1), dtype=np.int32)
     vp = C.c_void_p
     rc = lib().spec_freerun_duo(n, k, c, int(bool(is_mixture)), rounds, vp(leaf_row.ctypes.data), vp(cumw.ctypes.data),
-                                vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(de32.ctypes.data), vp(dlo24.ctypes.data),
+                                vp(cumpi.ctypes.data), g, vp(recs.ctypes.data), vp(de32.ctypes.data), vp(dres32.ctypes.data),
                                 C.c_uint64(seed & (2 ** 64 - 1)), C.c_int64(site0), C.c_int64(nsites), vp(leaves.ctypes.data),
                                 C.c_int64(max(nsites, 1)), vp(comps.ctypes.data))
     if rc:
@@ -159,5 +159,5 @@ def freerun_duo(is_mixture, parent, leaf_row, ws, ds, duo, seed, site0, nsites, 
 
 
 def duo_ties():
-    """Number of tied draws the last freerun_duo call had to refine."""
+    """Number of escape-level draws (t == 0) the last freerun_duo call took."""
     return int(lib().spec_duo_ties())

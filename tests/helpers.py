@@ -127,22 +127,37 @@ def check_pair_tables(p, pair, parent):
     assert np.max(np.abs(mass / float(1 << 48) - joint)) < 2.0 ** -44
 
 
-def quad_masses(qe32, qlo24):
-    """Integer outcome masses (sum 2^48 per row) encoded by quad alias rows qe32 = [q bits 39..24 : 16][alias : 8][0 : 8], qlo24."""
-    cap = 1 << 40
-    e = qe32.astype(np.int64)
+def alias2_masses(e32, res32, tb, w):
+    """Integer outcome masses (sum 2^w per row) encoded by two-level alias rows (elx_ptx.cuh): main entries e32 =
+    [q : tb][alias : 24 - tb][0 : 8] on cells of 2^-24 (t = 1 .. 2^tb - 1; the kernels accept [t][j] < [q][alias]), escape entries
+    res32 = [thr : 8 + tb][alias : 24 - tb] on the t == 0 draws (probability 2^-tb, column capacity 2^(w - 24))."""
+    ab = 24 - tb
+    kp = 1 << ab
+    capm, capr, unit = (1 << tb) - 1, 1 << (w - 24), 1 << (w - 24)
+    e = e32.astype(np.int64)
     assert np.all((e & 255) == 0)
-    al = (e >> 8) & 255
-    q = ((e >> 16) << 24) | qlo24.astype(np.int64)
-    assert np.all(qlo24 < (1 << 24))
-    q = np.where(al == np.arange(256), cap, q)
-    flat_q = q.reshape(-1, 256)
-    flat_al = al.reshape(-1, 256)
-    mass = flat_q.copy()
-    rows = np.arange(flat_q.shape[0])
-    for j in range(256):
-        np.add.at(mass, (rows, flat_al[:, j]), cap - flat_q[:, j])
-    return mass.reshape(q.shape)
+    al = (e >> 8) & (kp - 1)
+    q = e >> (32 - tb)
+    cols = np.arange(kp)
+    # t in 1..capm accepted: t < q, and t == q when j < alias
+    acc = np.minimum(np.maximum(q - 1, 0), capm) + ((q >= 1) & (q <= capm) & (cols < al))
+    assert np.all(acc <= capm)
+    r = res32.astype(np.int64)
+    ral, thr = r & (kp - 1), r >> ab
+    assert np.all(thr < capr)
+    shape = e.shape
+    acc, al, thr, ral = (x.reshape(-1, kp) for x in (acc, al, thr, ral))
+    mass = acc * unit + thr
+    rows = np.arange(acc.shape[0])
+    for j in range(kp):
+        np.add.at(mass, (rows, al[:, j]), (capm - acc[:, j]) * unit)
+        np.add.at(mass, (rows, ral[:, j]), capr - thr[:, j])
+    return mass.reshape(shape)
+
+
+def quad_masses(qe32, qres32):
+    """Integer outcome masses (sum 2^48 per row) of quad rows: 16-bit t, 256 columns."""
+    return alias2_masses(qe32, qres32, 16, 48)
 
 
 def check_quad_walk(recs, parent, leaf_row, n_slots=None):
@@ -230,10 +245,10 @@ def quad_joint_reference(p, rec, k):
 
 def check_quad_tables(p, quad, parent, leaf_row, max_records=40):
     """The walk is valid and the alias rows carry integer masses (sum 2^48) equal to the caps' joint probabilities."""
-    recs, qe32, qlo24 = quad
+    recs, qe32, qres32 = quad
     check_quad_walk(recs, parent, leaf_row)
     k = p.shape[2]
-    mass = quad_masses(qe32, qlo24)
+    mass = quad_masses(qe32, qres32)
     assert np.all(mass[:, :, :k].sum(-1) == 1 << 48)
     pn = p / p.sum(-1, keepdims=True)
     step = max(1, len(recs) // max_records)
@@ -244,22 +259,9 @@ def check_quad_tables(p, quad, parent, leaf_row, max_records=40):
         assert np.max(np.abs(got - ref)) < 2.0 ** -40, (g, np.max(np.abs(got - ref)))
 
 
-def duo_masses(de32, dlo24):
-    """Integer outcome masses (sum 2^48 per row) encoded by duo alias rows de32 = [q bits 38..24 : 15][alias : 9][0 : 8], dlo24."""
-    cap = 1 << 39
-    e = de32.astype(np.int64)
-    assert np.all((e & 255) == 0)
-    al = (e >> 8) & 511
-    q = ((e >> 17) << 24) | dlo24.astype(np.int64)
-    assert np.all(dlo24 < (1 << 24))
-    q = np.where(al == np.arange(512), cap, q)
-    flat_q = q.reshape(-1, 512)
-    flat_al = al.reshape(-1, 512)
-    mass = flat_q.copy()
-    rows = np.arange(flat_q.shape[0])
-    for j in range(512):
-        np.add.at(mass, (rows, flat_al[:, j]), cap - flat_q[:, j])
-    return mass.reshape(q.shape)
+def duo_masses(de32, dres32):
+    """Integer outcome masses (sum 2^47 per row) of duo rows: 15-bit t, 512 columns."""
+    return alias2_masses(de32, dres32, 15, 47)
 
 
 def duo_joint_reference(p, rec):
@@ -292,16 +294,16 @@ def duo_joint_reference(p, rec):
 def check_duo_tables(p, duo, parent, leaf_row, max_records=12):
     """The walk is valid (caps of at most two frontier nodes) and the alias rows carry integer masses (sum 2^48) equal to the
     caps' joint probabilities."""
-    recs, de32, dlo24 = duo
+    recs, de32, dres32 = duo
     check_quad_walk(recs, parent, leaf_row)
     assert np.all(recs[:, 3:5] == -1), "a duo cap has at most two frontier nodes"
     k = p.shape[2]
     pn = p / p.sum(-1, keepdims=True)
     step = max(1, len(recs) // max_records)
     for g in range(0, len(recs), step):
-        mass = duo_masses(de32[g], dlo24[g])
-        assert np.all(mass.sum(-1) == 1 << 48)
+        mass = duo_masses(de32[g], dres32[g])
+        assert np.all(mass.sum(-1) == 1 << 47)
         ref = duo_joint_reference(pn, recs[g])
         ref = ref / ref.sum(-1, keepdims=True)
-        got = mass / float(1 << 48)
+        got = mass / float(1 << 47)
         assert np.max(np.abs(got - ref)) < 2.0 ** -40, (g, np.max(np.abs(got - ref)))
