@@ -791,6 +791,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
   const uint32_t stride = (uint32_t)fa.slot_stride;
   const int nstage = fa.nstage;
   const uint32_t mhi = fa.mhi, negk = fa.negk256;
+  const uint32_t pitch32 = (uint32_t)fa.tmp_pitch;
   int buf = 0;
   uint32_t phase = 0;
   const PhiloxThreadPart tp = philox_thread_part<ROUNDS>(cx, cw, cw | 4u, cw | 8u, fa.rk);
@@ -862,7 +863,7 @@ __device__ __forceinline__ void duo_records(const DuoArgs &fa, const DuoTile &ti
 
 #define ELX_DUO_OUT(PW, code)                                                                                   \
   if ((int32_t)(code) >= 0) {                                                                                   \
-    if (FAST || active) stg_v4(tmp_base + (int64_t)(code) * fa.tmp_pitch, make_uint4(PW[0], PW[1], PW[2], PW[3])); \
+    if (FAST || active) stg_v4(tmp_base + (uint64_t)(uint32_t)(code) * (uint64_t)pitch32, make_uint4(PW[0], PW[1], PW[2], PW[3])); /* one IMAD.WIDE: tmp_pitch < 2^32 (duo_simulate) */ \
   } else if ((code) != 0xffffffffu) {                                                                           \
     sts_v4(slot_base + ((code) & 0x7fffffffu) * stride, make_uint4(PW[0] << 3, PW[1] << 3, PW[2] << 3, PW[3] << 3));                   \
   }
@@ -1173,7 +1174,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   const int NSB = (int)((M + ((int64_t)1 << dt->sb) - 1) >> dt->sb);
   const int64_t ntile_b = (M + DUO_TILE - 1) / DUO_TILE;
   const size_t slots_bound = (size_t)a.nsites + 32u * (size_t)NSB * C + 16;
-  if (slots_bound >= ((size_t)1 << 32) || M >= ((int64_t)1 << 32))
+  if (slots_bound + 256 >= ((size_t)1 << 32) || M >= ((int64_t)1 << 32))  // (tmp_pitch fits 32 bits: the kernels form row offsets with one IMAD.WIDE)
     return fail(h, ELX_E_UNSUPPORTED, "duo mode: more than 2^32 sites in one device call; split the site range");
   if ((size_t)NSB * C * sizeof(int) > 40 * 1024)
     return fail(h, ELX_E_UNSUPPORTED, "duo mode: too many (superblock, component) segments in one device call; split the site range");

@@ -262,6 +262,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
   constexpr uint32_t SM = 0x03030303u;
   const uint32_t slot_base_m = slot_base - 0x80000000u;  // + (0x80000000 | offset) = slot_base + offset
   const int nstage = fa.nstage;
+  const uint32_t pitch32 = (uint32_t)a.leaves_pitch;
   int buf = 0;
   uint32_t phase = 0;
   const PhiloxThreadPart tp = philox_thread_part<ROUNDS>(G0lo, 0u, 4u, 8u, fa.rk);
@@ -330,7 +331,7 @@ __device__ __forceinline__ void quad_records(const QuadArgs &fa, const uint32_t 
 #define ELX_QUAD_OUT(k, code)                                                                                                  \
   if ((int32_t)(code) >= 0) {                                                                                                  \
     const uint4 v = make_uint4((W[0] >> (2 * k)) & SM, (W[1] >> (2 * k)) & SM, (W[2] >> (2 * k)) & SM, (W[3] >> (2 * k)) & SM); \
-    if (FAST) stg_cs_v4(leaf_base + (int64_t)(code) * a.leaves_pitch, v);                                                      \
+    if (FAST) stg_cs_v4(leaf_base + (uint64_t)(uint32_t)(code) * (uint64_t)pitch32, v); /* one IMAD.WIDE (FAST: pitch < 2^32) */ \
     else if (store_mode) store_leaf(a, leaf_base, (int)(code), col0, store_mode, v);                                           \
   } else if ((code) != 0xffffffffu) {                                                                                          \
     sts_v4(slot_base_m + (code),                                                                                               \
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(MAXT + 32, MINB) k2_quad_tiled(QuadArgs fa) {
   const uint32_t slot_base = slots_smem + (uint32_t)tid * 16u;
   sts_v4(slot_base, make_uint4(R[0], R[1], R[2], R[3]));  // slot 0 = the root states
   const int store_mode = !any ? 0
-                              : (full && ((a.leaves_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
+                              : (full && ((a.leaves_pitch & 15) == 0) && a.leaves_pitch < ((int64_t)1 << 32) && ((reinterpret_cast<uintptr_t>(a.leaves) & 15) == 0) &&
                                  ((col0 & 15) == 0)) ? 1 : 2;
   uint8_t *leaf_base = a.leaves + col0;
   asm volatile("" : "+l"(leaf_base));  // keep the sum in registers: recomputed per store it costs two ALU adds
