@@ -547,6 +547,11 @@ __global__ void __launch_bounds__(256, 3) k_duo_unpermute_smem(const uint8_t *__
 // shared memory, 8 K registers) fits onto an SM NEXT TO a CTA of the simulation kernel: that is how the pass hides under the
 // next batch's simulation.  Row buffer = TS + 32 C bytes: C <= UNP_ASYNC_MAX_C.
 constexpr int UNP_ASYNC_MAX_C = 128;
+__device__ __forceinline__ uint32_t unp_lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 constexpr int UNP_MAX_CHUNKS = 3;  // 16-byte chunks per thread and row of the cp.async form: (TS + 32 C) / 16 / THREADS
 template <int THREADS, bool TMA>
 __global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *__restrict__ tmp, int64_t tmp_pitch, const uint32_t *__restrict__ pos32,
@@ -661,6 +666,10 @@ __global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *
     vec[k] = ub0 >= ua && ub0 + 4 <= ub && ((out_pitch & 3) == 0) && (((reinterpret_cast<uintptr_t>(out) + (uintptr_t)(colq + QS * k)) & 3) == 0);
   }
   uint8_t *dst = out + (int64_t)t0 * out_pitch + colq;
+  const bool all_vec = __syncthreads_and(vec[0] && vec[1] && vec[2] && vec[3]) != 0;
+  uint32_t sa[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) sa[x] = dsm_u32 + (uint32_t)sidx[x];
   for (int g = 0; g < ngroups; ++g) {
     const int s = g & 1, ta = t0 + g * UNP_R, nr = min(UNP_R, t1 - ta);
     if (row_bytes) {
@@ -672,6 +681,25 @@ __global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *
       }
     }
     const uint8_t *sb = dsm + (size_t)s * stage_bytes;
+    if (all_vec) {
+      // the common case, free of per-quarter tests: 16 byte loads at precomputed shared-memory addresses plus a uniform row
+      // offset, packed on the FMA pipe, four contiguous 32-bit streaming stores (2.1 instructions per cell; the general path
+      // below -- first / last block of a range, unaligned rows -- issues 8)
+      const uint32_t so = (uint32_t)s * stage_bytes;
+#pragma unroll
+      for (int r = 0; r < UNP_R; ++r) {
+        if (r < nr) {
+          const uint32_t ro = so + (uint32_t)r * (uint32_t)rowb;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t b0 = unp_lds_u8(sa[4 * k] + ro), b1 = unp_lds_u8(sa[4 * k + 1] + ro), b2 = unp_lds_u8(sa[4 * k + 2] + ro),
+                           b3 = unp_lds_u8(sa[4 * k + 3] + ro);
+            __stcs(reinterpret_cast<uint32_t *>(dst + QS * k), b3 * 0x1000000u + (b2 * 0x10000u + (b1 * 0x100u + b0)));
+          }
+        }
+        dst += out_pitch;
+      }
+    } else
 #pragma unroll
     for (int r = 0; r < UNP_R; ++r) {
       if (r < nr) {
@@ -1200,15 +1228,18 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   DUO_CUDA(h, duo_grow(&dt->d_tiles, &dt->cap_tiles, (size_t)max_tiles));
   DUO_CUDA(h, duo_grow(&dt->d_tmp, &dt->cap_tmp, (size_t)tmp_pitch * h->T));
 
-  // Optional pipeline (ELX_DUO_PIPELINE=1): batches of consecutive superblocks, the un-permute pass of a batch (HBM-bound) on
-  // a second stream under the simulation of the next one (integer-bound).  Measured on cfg3 / cfg4 (B200): the two kernels do
-  // run side by side (128-thread un-permute blocks next to a 544-thread simulation CTA), but the simulation slows down by
-  // half while they do -- both hammer shared memory with random byte / word reads -- and the call ends 5 % sooner (cfg3,
-  // 15.7 against 16.5 ms) or 5 % later (cfg4): off by default.
+  // Pipeline: batches of consecutive superblocks, the un-permute pass of a batch (HBM-bound) on a second stream under the
+  // simulation of the next one (integer-bound).  The two kernels do run side by side (128-thread un-permute blocks next to a
+  // 544-thread simulation CTA), but each slows the other down (cfg3 time line: the simulation kernels end after 13.6 instead
+  // of 10.2 ms, the passes take 6.5 instead of 4.7 ms in total), so the gain is a few per cent, and only on long calls.
   int conc = 148;
   cudaDeviceGetAttribute(&conc, cudaDevAttrMultiProcessorCount, h->device);
   conc *= dt->threads == 256 ? dt->minb : 1;
-  static const int want_batches = getenv("ELX_DUO_PIPELINE") && atoi(getenv("ELX_DUO_PIPELINE")) > 0 ? 0 : 1;
+  // Round 2, end: with the leaner un-permute blocks cfg3 (12 superblocks, 4 batches) ends 4.5 % sooner (15.21 -> 14.52 ms), cfg4
+  // (3 superblocks) is unchanged and cfg5 (1.2 superblocks: the one-wave tile sizing is lost) 38 % later: calls of at least 8
+  // superblocks are pipelined, ELX_DUO_PIPELINE=0 / 1 forces either way.
+  static const int pipe_env = getenv("ELX_DUO_PIPELINE") ? atoi(getenv("ELX_DUO_PIPELINE")) : -1;
+  const int want_batches = (pipe_env > 0 || (pipe_env < 0 && NSB >= 8)) ? 0 : 1;
   if (NSB >= 2 && want_batches != 1 && tile_groups > 544) tile_groups = 512;  // (registers for a co-resident un-permute block)
   const double sb_tiles = (double)((int64_t)1 << dt->sb) / 16.0 / tile_groups;  // CTA tiles of one full superblock
   const int L = std::max(1, (int)std::ceil(0.75 * conc / sb_tiles));
