@@ -135,19 +135,20 @@ def _multi_superblock_check():
             assert np.array_equal(cw[a - site0:b - site0], cp)
 
 
-@pytest.mark.parametrize("pipeline", [False, True])
+@pytest.mark.parametrize("pipeline", [None, "0", "1"])
 def test_duo_many_superblocks_call_equals_superblock_calls(pipeline):
-    """A call spanning many superblocks must equal the concatenation of one-superblock calls -- also with ELX_DUO_PIPELINE=1,
-    where it is cut into batches whose un-permute passes run on a second stream under the next batch's simulation (the
-    switch is read once per process: that run happens in a child process)."""
-    if not pipeline:
+    """A call spanning many superblocks must equal the concatenation of one-superblock calls.  Calls of at least 8 superblocks are
+    cut into batches whose un-permute passes run on a second stream under the next batch's simulation (None: that default, the
+    whole call here spans 9); ELX_DUO_PIPELINE=0 / 1 switch the pipeline off / on for every call (the switch is read once per
+    process: those runs happen in a child process)."""
+    if pipeline is None:
         return _multi_superblock_check()
     import os
     import subprocess
     import sys
 
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, ELX_DUO_PIPELINE="1", PYTHONPATH=os.pathsep.join([os.path.dirname(here), here, os.environ.get("PYTHONPATH", "")]))
+    env = dict(os.environ, ELX_DUO_PIPELINE=pipeline, PYTHONPATH=os.pathsep.join([os.path.dirname(here), here, os.environ.get("PYTHONPATH", "")]))
     r = subprocess.run([sys.executable, "-c", "import test_gpu_duo as t; t._multi_superblock_check(); print('pipeline ok')"],
                        env=env, cwd=here, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "pipeline ok" in r.stdout, r.stdout + r.stderr
