@@ -556,7 +556,7 @@ constexpr int UNP_MAX_CHUNKS = 3;  // 16-byte chunks per thread and row of the c
 template <int THREADS, bool TMA>
 __global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *__restrict__ tmp, int64_t tmp_pitch, const uint32_t *__restrict__ pos32,
                                                                 const uint8_t *__restrict__ comp8, int64_t u0, int64_t ua, int64_t ub, int C, int T,
-                                                                int rows_per_block, int rowb, uint8_t *__restrict__ out, int64_t out_pitch) {
+                                                                int rows_per_block, int rowb, uint8_t *__restrict__ out, int64_t out_pitch, int lean) {
   constexpr int TS = THREADS * 16, QS = THREADS * 4;
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ uint32_t s_min[UNP_ASYNC_MAX_C], s_cnt[UNP_ASYNC_MAX_C], s_off[UNP_ASYNC_MAX_C + 1];
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(THREADS) k_duo_unpermute_async(const uint8_t *
     vec[k] = ub0 >= ua && ub0 + 4 <= ub && ((out_pitch & 3) == 0) && (((reinterpret_cast<uintptr_t>(out) + (uintptr_t)(colq + QS * k)) & 3) == 0);
   }
   uint8_t *dst = out + (int64_t)t0 * out_pitch + colq;
-  const bool all_vec = __syncthreads_and(vec[0] && vec[1] && vec[2] && vec[3]) != 0;
+  const bool all_vec = __syncthreads_and(lean && vec[0] && vec[1] && vec[2] && vec[3]) != 0;
   uint32_t sa[16];
 #pragma unroll
   for (int x = 0; x < 16; ++x) sa[x] = dsm_u32 + (uint32_t)sidx[x];
@@ -1291,6 +1291,10 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
   fa.negk256 = (uint32_t)(-(h->K << 8));
   fa.rk = philox_round_keys(a.seed);
   static const int unperm_mode = getenv("ELX_DUO_UNPERM") ? atoi(getenv("ELX_DUO_UNPERM")) : 3;  // tuning knob: 1 = plain gather, 2 = word copies, 3 = TMA
+  // the un-permute blocks' lean gather path (3.2 instead of 8.1 instructions per cell), measured on ONE box (box-to-box variance
+  // is as large as the effect): cfg3 pipelined 14.53 against 14.96 ms, cfg4 7.04 against 7.18 ms, cfg5 16.77 against 17.33 ms.
+  // ELX_DUO_UNPERM_LEAN=0 selects the general path for every block (A/B runs).
+  static const int lean_env = getenv("ELX_DUO_UNPERM_LEAN") ? atoi(getenv("ELX_DUO_UNPERM_LEAN")) : -1;
   static const bool timeline = getenv("ELX_DUO_TIMELINE") != nullptr;  // debug: per-kernel start / end times of a call on stderr
   std::vector<cudaEvent_t> tev;
   auto mark = [&](cudaStream_t st) { if (timeline) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
@@ -1348,7 +1352,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
       DUO_CUDA(h, cudaFuncSetAttribute(k_duo_unpermute_async<128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       const dim3 ugrid((unsigned)nt, (unsigned)((h->T + rpb - 1) / rpb));
       k_duo_unpermute_async<128, true><<<ugrid, 128, dsmem, us>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, dt->d_comp8, u0, ua, ub, C, h->T, rpb, rowb,
-                                                                a.leaves, a.leaves_pitch);
+                                                                a.leaves, a.leaves_pitch, lean_env >= 0 ? lean_env : 1);
     } else if (unperm_mode == 3 && C <= UNP_ASYNC_MAX_C) {
       constexpr int TS = 256 * 16;
       const int64_t nt = (ub + TS - 1) / TS - ua / TS;
@@ -1357,7 +1361,7 @@ int duo_simulate(elx_handle *h, SimArgs &a, int *used) {
       DUO_CUDA(h, cudaFuncSetAttribute(k_duo_unpermute_async<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
       const dim3 ugrid((unsigned)nt, (unsigned)((h->T + rpb - 1) / rpb));
       k_duo_unpermute_async<256, false><<<ugrid, 256, dsmem, us>>>(dt->d_tmp, tmp_pitch, dt->d_pos32, dt->d_comp8, u0, ua, ub, C, h->T, rpb, rowb,
-                                                                 a.leaves, a.leaves_pitch);
+                                                                 a.leaves, a.leaves_pitch, lean_env >= 0 ? lean_env : 1);
     } else {
       const int64_t nt = (ub + UNP_TS - 1) / UNP_TS - ua / UNP_TS;
       const int rpb = rows_per_block(nt);
