@@ -88,7 +88,7 @@ def test_cli_fasta_gz_and_site_components(tmp_path, ref_data):
         assert np.array_equal(sim.site_components(1, 3000, site0=1234567), comps)
 
 
-@pytest.mark.parametrize("name,site0,s", [("hky_g4", 0, (1 << 21) + 333), ("hky_g4", 96, 5000), ("lg_g4", 64, (1 << 20) + 4097), ("c10", 5, 3001)])
+@pytest.mark.parametrize("name,site0,s", [("hky_g4", 0, (1 << 22) + 333), ("hky_g4", 96, 5000), ("lg_g4", 64, (1 << 20) + 4097), ("c10", 5, 3001)])
 def test_simulate_packed_is_the_alignment(name, site0, s):
     """elx_simulate_packed: the 2- / 5-bit rows expand (elx_unpack2_rows / elx_unpack5_rows) to exactly what elx_simulate returns,
     several batches, ragged ends, unaligned site0; d2h bytes are the packed size."""

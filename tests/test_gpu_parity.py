@@ -409,7 +409,7 @@ def test_host_buffer_call_packed_transport_is_byte_identical(keep_internal, monk
     component vector and the internal states, and the packed call must move a quarter of the bytes."""
     model = model_case("hky_g4")
     tree = tree_from_file("Newick.tree")
-    nsites = 2 * (1 << 20) + 12345  # three device batches, the last one ragged (not a multiple of 4)
+    nsites = 2 * (1 << 21) + 12345  # three device batches of 2^21 sites, the last one ragged (not a multiple of 4)
     with make_sim(model, tree) as sim:
         monkeypatch.setenv("ELX_PACKED_D2H", "0")
         b0 = sim.d2h_bytes
